@@ -1,0 +1,123 @@
+/*
+ * salamander_b200.h -- C ABI of libsalamander_b200.so (sm_100a).
+ *
+ * The reference (parklab/Salamander v0.4.2) has no FFI layer: its compiled code is the
+ * numba-JIT output of 17 @njit functions.  Each entry point below
+ * replaces one or more of those functions; the reference site is cited per function.
+ * A maintainer binds them with ctypes.
+ *
+ * Conventions
+ *   - every function returns int: 0 ok, <0 invalid argument (SAL_E*), >0 a cudaError_t;
+ *     sal_last_error() returns a thread-local message.  Nothing throws across the ABI.
+ *   - all array arguments are DEVICE pointers unless the name ends in _host;
+ *     element type `real` is float (dtype SAL_F32) or double (SAL_F64), fixed per handle.
+ *   - layouts are the AnnData memory of the reference:
+ *        X [D][V]  counts, sample-major  (adata.X,            signature_nmf.py:281)
+ *        H [D][k]  exposures             (adata.obsm["exposures"], klnmf.py:106)
+ *        W [k][V]  signatures            (asignatures.X,      klnmf.py:105)
+ *   - calls are asynchronous on `stream` (a cudaStream_t passed as void*); scalar
+ *     outputs are device doubles.  A handle may be used from one stream at a time.
+ *   - D is the number of samples LOCAL to this GPU (sample-sharded data parallel).
+ */
+#ifndef SALAMANDER_B200_H
+#define SALAMANDER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sal_ctx* sal_handle_t;
+
+enum { SAL_F32 = 0, SAL_F64 = 1 };
+
+/* arithmetic used for the three thin contractions of the fused pass (fp32 handles only) */
+enum {
+    SAL_MATH_FMA = 0,  /* CUDA-core FMA in the handle's dtype (exact fp32 / fp64)          */
+    SAL_MATH_TF32 = 1  /* tcgen05 kind::tf32 tensor-core contractions, fp32 accumulation   */
+};
+
+enum {
+    SAL_EINVAL = -1,      /* null pointer / bad size / bad enum            */
+    SAL_EUNSUPPORTED = -2 /* V > 96 or k > 32 (not yet covered by kernels)  */
+};
+
+/* flags of sal_klnmf_pass */
+enum {
+    SAL_PASS_UPDATE_H = 1,   /* write H_out = clip(H * W^T A)  (or the l-half closed form)   */
+    SAL_PASS_WNUM = 2,       /* write Wnum[k][V] = sum_d wkl_d A[v,d] H[k,d]  (RAW, no W *)  */
+    SAL_PASS_OBJECTIVE = 4,  /* write *objective = KL(X||WH) (+ l-half term) of the INPUT W,H */
+    SAL_PASS_SAMPLEWISE = 8, /* write per_sample[d] = unweighted KL of sample d              */
+    SAL_PASS_HSUM = 16,      /* write hsum[k] = sum_d H_in[d][k]                             */
+    SAL_PASS_POISSON = 32    /* objective = sum x ln(wh) - wh  (Poisson llh w/o ln Gamma)    */
+};
+
+const char* sal_last_error(void);
+int sal_version(void);
+
+/* Create / destroy a workspace for problems of shape (V, D_local, k).  Owns only small
+ * scratch (per-CTA partial sums).  `device` is the CUDA ordinal. */
+int sal_create(sal_handle_t* out, int V, int64_t D_local, int k, int dtype, int device);
+int sal_destroy(sal_handle_t h);
+int sal_set_math(sal_handle_t h, int math_mode);
+/* number of kernels this handle has launched since creation (bench.py "gpu_launches") */
+int64_t sal_launch_count(sal_handle_t h);
+
+/*
+ * The fused KL-NMF pass: streams X once and, per sample, rebuilds (WH) on the fly,
+ * forms A = X / (WH) and accumulates whatever `flags` asks for.  (WH) and A never touch HBM.
+ *
+ *   replaces  update_WH          models/_utils_klnmf.py:281-361   (UPDATE_H | WNUM)
+ *             update_H           models/_utils_klnmf.py:220-278   (UPDATE_H)
+ *             update_W           models/_utils_klnmf.py:164-217   (WNUM; then sal_w_epilogue)
+ *             kl_divergence      models/_utils_klnmf.py:11-55     (OBJECTIVE)
+ *             samplewise_kl_divergence  _utils_klnmf.py:58-97     (SAMPLEWISE)
+ *             _poisson_llh_wo_factorial _utils_klnmf.py:100-135   (POISSON)
+ *             KLNMF.objective_function  models/klnmf.py:64-80     (OBJECTIVE with w_lhalf)
+ *
+ *   w_kl, w_lhalf : [D] or NULL (per-sample KL weights / l-half penalty weights)
+ *   h_scale       : [k] or NULL; when given the pass reads H as clip(H_in * h_scale[k])
+ *                   (MvNMF line-search trial: normalize_WH + clip, utils.py:155-158,
+ *                   mvnmf.py:80-81) and, with UPDATE_H, writes that H to H_out unchanged.
+ *   H_out may alias H_in.  Wnum / objective / per_sample / hsum may be NULL if not flagged.
+ */
+int sal_klnmf_pass(sal_handle_t h, const void* X, const void* W, const void* H_in, void* H_out,
+                   const void* w_kl, const void* w_lhalf, const void* h_scale, int flags,
+                   void* Wnum, double* objective, void* per_sample, void* hsum, void* stream);
+
+/*
+ * W epilogue: W_out = clip(colnorm(W_in * Wnum)) with given signatures restored.
+ *   replaces the W tail of update_WH (_utils_klnmf.py:338-341, clip_given = 1: ALL columns
+ *   clipped) and of update_W (:212-215, clip_given = 0: only non-given columns clipped).
+ *   n_given == k leaves W unchanged.  W_out may alias W_in.
+ */
+int sal_w_epilogue(sal_handle_t h, const void* W_in, const void* Wnum, int n_given, int clip_given,
+                   void* W_out, void* stream);
+
+/* ---- MvNMF single-CTA k x k steps (models/mvnmf.py) -------------------------------- */
+
+/* out[0] = ln det(W^T W + delta I)   (volume_logdet, mvnmf.py:19-24; LU with pivoting) */
+int sal_mvnmf_logdet(sal_handle_t h, const void* W, double delta, double* out, void* stream);
+
+/*
+ * W_unc = update_W_unconstrained (mvnmf.py:37-66) given the raw numerator
+ * N = (X/(WH)) H^T (sal_klnmf_pass WNUM) and rowsums of H (HSUM).
+ */
+int sal_mvnmf_w_unconstrained(sal_handle_t h, const void* W, const void* N, const void* hsum,
+                              double lam, double delta, int n_given, void* W_unc, void* stream);
+
+/*
+ * One line-search candidate (mvnmf.py:80-81, 85-88 + utils.py:155-158):
+ *   Wb = gamma_blend < 0 ? W_unc : (1 - gamma) W + gamma W_unc ;  s = colsum(Wb)
+ *   W_trial = clip(Wb / s) ;  h_scale[k] = s[k] ;  logdet_out = ln det(W_trial^T W_trial + delta I)
+ * The trial objective is then sal_klnmf_pass(OBJECTIVE, h_scale) + lam * logdet.
+ */
+int sal_mvnmf_trial(sal_handle_t h, const void* W, const void* W_unc, double gamma_blend, double delta,
+                    void* W_trial, void* h_scale, double* logdet_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SALAMANDER_B200_H */

@@ -1,0 +1,119 @@
+"""
+Generate tests/golden/trajectories/*.npz by running the LIVE reference (parklab/Salamander
+v0.4.2 mounted at /root/reference) in the build container.  The reference has no test that
+pins a multi-iteration trajectory, so these files are the known answers for
+the north-star criteria (fp64: objective history within 1e-9 relative; fp32: final KL within
+1e-4 relative and signature cosine >= 0.9999).
+
+    python -m oracle.make_golden            # writes the fixtures (a few minutes, CPU)
+
+Each file stores the inputs needed to start from the identical point (W0, H0 after the
+reference's own initialisation) plus the reference's history / final parameters.
+"""
+
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import pandas as pd
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import reference_loader as rl  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden", "trajectories")
+DATA = os.path.join(ROOT, "salamander_b200", "data")
+
+
+def _adata(name="pcawg_breast_sbs.csv", n_samples=None):
+    counts = pd.read_csv(os.path.join(DATA, name), index_col=0)
+    df = counts.T if n_samples is None else counts.T.iloc[:n_samples]
+    return rl.RefAnnData(df)
+
+
+def klnmf_case(tag, k, seed, fitting_kwargs=None, n_given=0, **ctor):
+    sal = rl.load_package()
+    adata = _adata()
+    model = sal.models.KLNMF(n_signatures=k, init_method="random", **ctor)
+    given = None
+    if n_given:
+        g = _adata()[:n_given, :]
+        g.X = g.X / g.X.sum(axis=1, keepdims=True)
+        given = {"asignatures": g}
+    # replay the reference's own initialisation to record the starting point
+    model._setup_adata(adata)
+    model._initialize(given, {"seed": seed})
+    W0 = np.array(model.asignatures.X)
+    H0 = np.array(model.adata.obsm["exposures"])
+    adata2 = _adata()
+    model.fit(adata2, given_parameters=given, init_kwargs={"seed": seed}, fitting_kwargs=fitting_kwargs)
+    fk = fitting_kwargs or {}
+    np.savez_compressed(
+        os.path.join(OUT, f"{tag}.npz"),
+        W0=W0,
+        H0=H0,
+        history=np.array(model.history["objective_function"]),
+        W=np.array(model.asignatures.X),
+        H=np.array(model.adata.obsm["exposures"]),
+        seed=seed,
+        k=k,
+        n_given=n_given,
+        weights_kl=np.array(fk.get("weights_kl")) if fk.get("weights_kl") is not None else np.zeros(0),
+        weights_lhalf=np.array(fk.get("weights_lhalf")) if fk.get("weights_lhalf") is not None else np.zeros(0),
+        **{f"ctor_{a}": b for a, b in ctor.items()},
+    )
+    print(tag, "iterations*freq:", len(model.history["objective_function"]), "final:", model.history["objective_function"][-1])
+
+
+def mvnmf_case(tag, k, seed, **ctor):
+    sal = rl.load_package()
+    adata = _adata()
+    model = sal.models.MvNMF(n_signatures=k, init_method="random", **ctor)
+    model._setup_adata(adata)
+    model._initialize(None, {"seed": seed})
+    W0 = np.array(model.asignatures.X)
+    H0 = np.array(model.adata.obsm["exposures"])
+    model.fit(_adata(), init_kwargs={"seed": seed})
+    np.savez_compressed(
+        os.path.join(OUT, f"{tag}.npz"),
+        W0=W0,
+        H0=H0,
+        history=np.array(model.history["objective_function"]),
+        W=np.array(model.asignatures.X),
+        H=np.array(model.adata.obsm["exposures"]),
+        gamma=model._gamma,
+        seed=seed,
+        k=k,
+        **{f"ctor_{a}": b for a, b in ctor.items()},
+    )
+    print(tag, "history:", len(model.history["objective_function"]), "final:", model.history["objective_function"][-1], "gamma", model._gamma)
+
+
+def main():
+    if not rl.available():
+        raise SystemExit("live reference not mounted; nothing to do")
+    os.makedirs(OUT, exist_ok=True)
+    rng = np.random.default_rng(7)
+    D = 192
+    # C1: KLNMF k=5 on PCAWG breast SBS, defaults (runs to convergence, ~7k iterations)
+    klnmf_case("klnmf_pcawg_k5_seed0", 5, 0)
+    # weighted / l-half / given-signature variants, bounded length
+    klnmf_case(
+        "klnmf_pcawg_k4_weights",
+        4,
+        1,
+        fitting_kwargs={"weights_kl": rng.uniform(0.5, 2.0, D), "weights_lhalf": rng.uniform(0.0, 4.0, D)},
+        min_iterations=300,
+        max_iterations=300,
+    )
+    klnmf_case("klnmf_pcawg_k6_given2", 6, 2, n_given=2, min_iterations=400, max_iterations=400)
+    # C2: MvNMF k=10 on the same data, lam = delta = 1
+    mvnmf_case("mvnmf_pcawg_k10_seed0", 10, 0, min_iterations=600, max_iterations=600)
+    mvnmf_case("mvnmf_pcawg_k3_lam50", 3, 3, lam=50.0, delta=0.5, min_iterations=300, max_iterations=300)
+
+
+if __name__ == "__main__":
+    main()

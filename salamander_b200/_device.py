@@ -1,0 +1,195 @@
+"""
+Thin Python wrapper over the C ABI: one ``Workspace`` per (V, D_local, k, dtype) problem.
+
+PyTorch owns device memory and streams (plumbing); every numerical step is a call into
+libsalamander_b200.so through ctypes with raw device pointers.  No fallback exists: a
+missing library or a CPU tensor raises.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import (  # noqa: F401  (re-exported for callers)
+    PASS_HSUM,
+    PASS_OBJECTIVE,
+    PASS_POISSON,
+    PASS_SAMPLEWISE,
+    PASS_UPDATE_H,
+    PASS_WNUM,
+)
+
+_DTYPES = {torch.float32: _lib.SAL_F32, torch.float64: _lib.SAL_F64}
+
+
+def resolve_dtype(dtype) -> torch.dtype:
+    if isinstance(dtype, torch.dtype):
+        out = dtype
+    else:
+        out = {"float64": torch.float64, "fp64": torch.float64, "float32": torch.float32, "fp32": torch.float32}.get(
+            str(dtype)
+        )
+    if out not in _DTYPES:
+        raise ValueError("dtype has to be 'float64' or 'float32'.")
+    return out
+
+
+def resolve_device(device) -> torch.device:
+    if not torch.cuda.is_available():
+        raise _lib.SalamanderB200Error(
+            "salamander_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback."
+        )
+    dev = torch.device("cuda" if device is None else device)
+    if dev.type != "cuda":
+        raise _lib.SalamanderB200Error(f"salamander_b200 runs on CUDA devices only, got '{dev}'.")
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    return dev
+
+
+class Workspace:
+    """Owns a ``sal_handle_t``; methods map 1:1 onto the ABI entry points."""
+
+    def __init__(self, V: int, D_local: int, k: int, dtype: torch.dtype, device: torch.device, math: str = "fma"):
+        self.lib = _lib.load()
+        self.V, self.D, self.k = int(V), int(D_local), int(k)
+        self.dtype, self.device = dtype, device
+        self._h = C.c_void_p()
+        _lib.check(
+            self.lib.sal_create(C.byref(self._h), self.V, self.D, self.k, _DTYPES[dtype], device.index), "sal_create"
+        )
+        self.set_math(math)
+
+    def set_math(self, math: str) -> None:
+        mode = {"fma": _lib.MATH_FMA, "tf32": _lib.MATH_TF32}.get(math)
+        if mode is None:
+            raise ValueError("math has to be 'fma' or 'tf32'.")
+        _lib.check(self.lib.sal_set_math(self._h, mode), "sal_set_math")
+        self.math = math
+
+    def close(self) -> None:
+        if self._h:
+            self.lib.sal_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.sal_launch_count(self._h))
+
+    # -- helpers -----------------------------------------------------------------------------
+    def _ptr(self, t: Optional[torch.Tensor], numel: int, name: str, dtype=None):
+        if t is None:
+            return None
+        want = self.dtype if dtype is None else dtype
+        if not isinstance(t, torch.Tensor) or t.device != self.device:
+            raise ValueError(f"'{name}' has to be a tensor on {self.device}.")
+        if t.dtype != want or not t.is_contiguous() or t.numel() != numel:
+            raise ValueError(f"'{name}' has to be a contiguous {want} tensor with {numel} elements.")
+        return C.c_void_p(t.data_ptr())
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # -- ABI ---------------------------------------------------------------------------------
+    def klnmf_pass(
+        self,
+        X,
+        W,
+        H_in,
+        flags: int,
+        H_out=None,
+        w_kl=None,
+        w_lhalf=None,
+        h_scale=None,
+        Wnum=None,
+        objective=None,
+        per_sample=None,
+        hsum=None,
+    ) -> None:
+        V, D, k = self.V, self.D, self.k
+        _lib.check(
+            self.lib.sal_klnmf_pass(
+                self._h,
+                self._ptr(X, D * V, "X"),
+                self._ptr(W, k * V, "W"),
+                self._ptr(H_in, D * k, "H_in"),
+                self._ptr(H_out, D * k, "H_out"),
+                self._ptr(w_kl, D, "w_kl"),
+                self._ptr(w_lhalf, D, "w_lhalf"),
+                self._ptr(h_scale, k, "h_scale"),
+                int(flags),
+                self._ptr(Wnum, k * V, "Wnum"),
+                self._ptr(objective, 1, "objective", torch.float64),
+                self._ptr(per_sample, D, "per_sample"),
+                self._ptr(hsum, k, "hsum"),
+                self._stream(),
+            ),
+            "sal_klnmf_pass",
+        )
+
+    def w_epilogue(self, W_in, Wnum, n_given: int, clip_given: bool, W_out) -> None:
+        kv = self.k * self.V
+        _lib.check(
+            self.lib.sal_w_epilogue(
+                self._h,
+                self._ptr(W_in, kv, "W_in"),
+                self._ptr(Wnum, kv, "Wnum"),
+                int(n_given),
+                int(bool(clip_given)),
+                self._ptr(W_out, kv, "W_out"),
+                self._stream(),
+            ),
+            "sal_w_epilogue",
+        )
+
+    def mvnmf_logdet(self, W, delta: float, out) -> None:
+        _lib.check(
+            self.lib.sal_mvnmf_logdet(
+                self._h, self._ptr(W, self.k * self.V, "W"), float(delta), self._ptr(out, 1, "out", torch.float64), self._stream()
+            ),
+            "sal_mvnmf_logdet",
+        )
+
+    def mvnmf_w_unconstrained(self, W, N, hsum, lam: float, delta: float, n_given: int, W_unc) -> None:
+        kv = self.k * self.V
+        _lib.check(
+            self.lib.sal_mvnmf_w_unconstrained(
+                self._h,
+                self._ptr(W, kv, "W"),
+                self._ptr(N, kv, "N"),
+                self._ptr(hsum, self.k, "hsum"),
+                float(lam),
+                float(delta),
+                int(n_given),
+                self._ptr(W_unc, kv, "W_unc"),
+                self._stream(),
+            ),
+            "sal_mvnmf_w_unconstrained",
+        )
+
+    def mvnmf_trial(self, W, W_unc, gamma_blend: float, delta: float, W_trial, h_scale, logdet_out) -> None:
+        kv = self.k * self.V
+        _lib.check(
+            self.lib.sal_mvnmf_trial(
+                self._h,
+                self._ptr(W, kv, "W"),
+                self._ptr(W_unc, kv, "W_unc"),
+                float(gamma_blend),
+                float(delta),
+                self._ptr(W_trial, kv, "W_trial"),
+                self._ptr(h_scale, self.k, "h_scale"),
+                self._ptr(logdet_out, 1, "logdet_out", torch.float64),
+                self._stream(),
+            ),
+            "sal_mvnmf_trial",
+        )

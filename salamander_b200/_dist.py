@@ -1,0 +1,59 @@
+"""
+Sample-sharded data parallelism: one process per GPU, contiguous row blocks
+of ``adata.X``; H and every per-sample quantity stay local; only the V x k W numerator
+(+ scalar objective, + k row sums for MvNMF) is summed across ranks each iteration.
+
+These helpers are pure ``torch.distributed`` plumbing and work with any backend (NCCL on the
+GPUs, gloo in the CPU tests of the host logic).
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def world() -> tuple[int, int]:
+    """(rank, world_size); (0, 1) when torch.distributed is not initialised."""
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_bounds(n_samples: int, world_size: int, rank: int) -> tuple[int, int]:
+    """Contiguous, nearly equal row block [lo, hi) of rank ``rank``; the first ``n % world`` ranks get one extra."""
+    base, extra = divmod(int(n_samples), int(world_size))
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def allreduce_sum_(t: torch.Tensor) -> torch.Tensor:
+    """In-place sum over ranks (no-op for a single process).  NCCL's result is identical on all ranks."""
+    if world()[1] > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t
+
+
+def gather_rows(local: torch.Tensor, n_total: int) -> torch.Tensor:
+    """All-gather row blocks laid out by ``shard_bounds`` into the full (n_total, ...) tensor on every rank."""
+    rank, ws = world()
+    if ws == 1:
+        return local
+    counts = [shard_bounds(n_total, ws, r) for r in range(ws)]
+    max_rows = max(hi - lo for lo, hi in counts)
+    pad = torch.zeros((max_rows,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    bufs = [torch.empty_like(pad) for _ in range(ws)]
+    dist.all_gather(bufs, pad)
+    return torch.cat([b[: hi - lo] for b, (lo, hi) in zip(bufs, counts)], dim=0)
+
+
+def broadcast_numpy(arr: np.ndarray, device: torch.device, src: int = 0) -> np.ndarray:
+    """Make rank ``src``'s host array the value on every rank (keeps replicas bit-identical after host init)."""
+    rank, ws = world()
+    if ws == 1:
+        return arr
+    t = torch.from_numpy(np.ascontiguousarray(arr)).to(device)
+    dist.broadcast(t, src=src)
+    return t.cpu().numpy()

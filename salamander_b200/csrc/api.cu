@@ -1,0 +1,142 @@
+// C ABI of libsalamander_b200.so -- argument checking, workspace ownership, dispatch.
+// Declarations and the reference sites each entry point replaces: include/salamander_b200.h
+#include <stdarg.h>
+#include <string.h>
+
+#include "sal_common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void sal_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" {
+
+const char* sal_last_error(void) { return g_err; }
+int sal_version(void) { return 100; }
+
+int sal_create(sal_handle_t* out, int V, int64_t D_local, int k, int dtype, int device) {
+    SAL_CHECK_ARG(out != nullptr, "out handle is null");
+    SAL_CHECK_ARG(V >= 1 && k >= 1 && D_local >= 0, "V, k must be >= 1 and D >= 0");
+    SAL_CHECK_ARG(dtype == SAL_F32 || dtype == SAL_F64, "dtype must be SAL_F32 or SAL_F64");
+    if (V > SAL_VMAX || k > SAL_KMAX) {
+        sal_set_error("unsupported shape: V=%d (max %d), k=%d (max %d)", V, SAL_VMAX, k, SAL_KMAX);
+        return SAL_EUNSUPPORTED;
+    }
+    SAL_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    SAL_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        sal_set_error("libsalamander_b200 is built for sm_100a only; device %d is sm_%d%d", device, prop.major,
+                      prop.minor);
+        return SAL_EUNSUPPORTED;
+    }
+    sal_ctx* c = new sal_ctx();
+    memset(c, 0, sizeof(*c));
+    c->V = V, c->k = k, c->KP = sal_kpad(k), c->dtype = dtype, c->device = device, c->D = D_local;
+    c->math = SAL_MATH_FMA;
+    c->n_sm = prop.multiProcessorCount;
+    c->grid_pass = c->n_sm * (dtype == SAL_F32 ? 2 : 1);
+    const size_t es = dtype == SAL_F32 ? 4 : 8;
+    cudaError_t e = cudaMalloc(&c->partial_wnum, (size_t)c->grid_pass * SAL_KMAX * SAL_VMAX * es);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&c->partial_obj, (size_t)c->grid_pass * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&c->partial_hsum, (size_t)c->grid_pass * SAL_KMAX * sizeof(double));
+    if (e != cudaSuccess) {
+        sal_set_error("cudaMalloc of the workspace failed: %s", cudaGetErrorString(e));
+        cudaFree(c->partial_wnum), cudaFree(c->partial_obj), cudaFree(c->partial_hsum);
+        delete c;
+        return (int)e;
+    }
+    *out = c;
+    return 0;
+}
+
+int sal_destroy(sal_handle_t h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    cudaFree(h->partial_wnum), cudaFree(h->partial_obj), cudaFree(h->partial_hsum);
+    if (h->tc_ws) cudaFree(h->tc_ws);
+    delete h;
+    return 0;
+}
+
+int sal_set_math(sal_handle_t h, int math_mode) {
+    SAL_CHECK_ARG(h != nullptr, "handle is null");
+    SAL_CHECK_ARG(math_mode == SAL_MATH_FMA || math_mode == SAL_MATH_TF32, "unknown math mode");
+    if (math_mode == SAL_MATH_TF32 && h->dtype != SAL_F32) {
+        sal_set_error("SAL_MATH_TF32 needs an fp32 handle");
+        return SAL_EINVAL;
+    }
+    h->math = math_mode;
+    return 0;
+}
+
+int64_t sal_launch_count(sal_handle_t h) { return h ? h->launches : -1; }
+
+int sal_klnmf_pass(sal_handle_t h, const void* X, const void* W, const void* H_in, void* H_out,
+                   const void* w_kl, const void* w_lhalf, const void* h_scale, int flags, void* Wnum,
+                   double* objective, void* per_sample, void* hsum, void* stream) {
+    SAL_CHECK_ARG(h != nullptr, "handle is null");
+    SAL_CHECK_ARG(X && W && H_in, "X, W, H_in must be non-null");
+    SAL_CHECK_ARG(flags != 0, "flags == 0: nothing to do");
+    SAL_CHECK_ARG(!(flags & SAL_PASS_UPDATE_H) || H_out, "UPDATE_H needs H_out");
+    SAL_CHECK_ARG(!(flags & SAL_PASS_WNUM) || Wnum, "WNUM needs Wnum");
+    SAL_CHECK_ARG(!(flags & (SAL_PASS_OBJECTIVE | SAL_PASS_POISSON)) || objective, "OBJECTIVE needs objective");
+    SAL_CHECK_ARG(!((flags & SAL_PASS_OBJECTIVE) && (flags & SAL_PASS_POISSON)), "OBJECTIVE and POISSON are exclusive");
+    SAL_CHECK_ARG(!((flags & SAL_PASS_SAMPLEWISE) && (flags & SAL_PASS_POISSON)), "SAMPLEWISE and POISSON are exclusive");
+    SAL_CHECK_ARG(!(flags & SAL_PASS_SAMPLEWISE) || per_sample, "SAMPLEWISE needs per_sample");
+    SAL_CHECK_ARG(!(flags & SAL_PASS_HSUM) || hsum, "HSUM needs hsum");
+    SAL_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (h->D == 0) {  // empty shard: outputs are exact zeros
+        const size_t es = h->dtype == SAL_F32 ? 4 : 8;
+        if (flags & SAL_PASS_WNUM) SAL_CUDA(cudaMemsetAsync(Wnum, 0, (size_t)h->k * h->V * es, st));
+        if (flags & (SAL_PASS_OBJECTIVE | SAL_PASS_POISSON)) SAL_CUDA(cudaMemsetAsync(objective, 0, sizeof(double), st));
+        if (flags & SAL_PASS_HSUM) SAL_CUDA(cudaMemsetAsync(hsum, 0, (size_t)h->k * es, st));
+        return 0;
+    }
+    PassArgs a;
+    a.X = X, a.W = W, a.H_in = H_in, a.w_kl = w_kl, a.w_lhalf = w_lhalf, a.h_scale = h_scale;
+    a.H_out = H_out, a.Wnum = Wnum, a.per_sample = per_sample, a.hsum = hsum, a.objective = objective;
+    a.flags = flags;
+    if (h->math == SAL_MATH_TF32) return sal_launch_pass_tf32(h, a, st);
+    return sal_launch_pass_fma(h, a, st);
+}
+
+int sal_w_epilogue(sal_handle_t h, const void* W_in, const void* Wnum, int n_given, int clip_given,
+                   void* W_out, void* stream) {
+    SAL_CHECK_ARG(h != nullptr, "handle is null");
+    SAL_CHECK_ARG(W_in && W_out, "W_in, W_out must be non-null");
+    SAL_CHECK_ARG(n_given >= 0 && n_given <= h->k, "n_given out of range");
+    SAL_CHECK_ARG(n_given == h->k || Wnum, "Wnum must be non-null");
+    SAL_CUDA(cudaSetDevice(h->device));
+    return sal_launch_w_epilogue(h, W_in, Wnum, n_given, clip_given, W_out, (cudaStream_t)stream);
+}
+
+int sal_mvnmf_logdet(sal_handle_t h, const void* W, double delta, double* out, void* stream) {
+    SAL_CHECK_ARG(h && W && out, "null argument");
+    SAL_CUDA(cudaSetDevice(h->device));
+    return sal_launch_mvnmf_logdet(h, W, delta, out, (cudaStream_t)stream);
+}
+
+int sal_mvnmf_w_unconstrained(sal_handle_t h, const void* W, const void* N, const void* hsum, double lam,
+                              double delta, int n_given, void* W_unc, void* stream) {
+    SAL_CHECK_ARG(h && W && N && hsum && W_unc, "null argument");
+    SAL_CHECK_ARG(n_given >= 0 && n_given <= h->k, "n_given out of range");
+    SAL_CUDA(cudaSetDevice(h->device));
+    return sal_launch_mvnmf_w_unc(h, W, N, hsum, lam, delta, n_given, W_unc, (cudaStream_t)stream);
+}
+
+int sal_mvnmf_trial(sal_handle_t h, const void* W, const void* W_unc, double gamma_blend, double delta,
+                    void* W_trial, void* h_scale, double* logdet_out, void* stream) {
+    SAL_CHECK_ARG(h && W && W_unc && W_trial && h_scale && logdet_out, "null argument");
+    SAL_CUDA(cudaSetDevice(h->device));
+    return sal_launch_mvnmf_trial(h, W, W_unc, gamma_blend, delta, W_trial, h_scale, logdet_out,
+                                  (cudaStream_t)stream);
+}
+
+}  // extern "C"

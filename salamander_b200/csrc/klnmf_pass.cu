@@ -1,0 +1,425 @@
+// Fused KL-NMF pass, CUDA-core FMA flavour (exact fp32 / fp64 arithmetic).
+//
+// One launch streams the resident count matrix X [D][V] once.  Per sample d it rebuilds
+// (WH)[:,d] from W (pinned in shared memory) and H[d][:] (registers), forms the quotient
+// A = X/(WH), and accumulates -- depending on flags --
+//     H_out[d][:]  = clip(H * W^T A)            update_H / update_WH   _utils_klnmf.py:258-278,343-361
+//     Wnum[k][v]  += wkl_d A[v,d] H[k,d]         update_W / update_WH   _utils_klnmf.py:207-212,328-338
+//     objective   += wkl_d KL(x_d || W h_d)      kl_divergence          _utils_klnmf.py:37-55
+// (WH) and A never touch HBM.  Algorithmic traffic: V*D + 2*k*D reals per launch.
+//
+// Work decomposition (192 threads = 6 warps per CTA, persistent grid):
+//   stage : cooperative coalesced copy of a tile of TS samples (X rows, H rows) to shared memory
+//   phase1: thread <-> sample.  h[KP], hn[KP] in registers; W rows are broadcast 128-bit LDS.
+//           The quotient tile overwrites the X tile in shared memory.
+//   phase2: thread <-> (feature v, half of the signatures).  Accumulates sum_s A[s][v] * H[s][k]
+//           over the tile in registers that persist across all tiles of the CTA.
+//   end   : per-CTA partial numerators / objective go to a scratch buffer; a second tiny kernel
+//           sums them in a FIXED order (deterministic, rank-independent).
+#include "sal_common.cuh"
+
+namespace {
+
+constexpr int NT = 192;
+constexpr int VP = SAL_VMAX;
+
+template <typename T>
+struct Cfg;
+template <>
+struct Cfg<float> {
+    static constexpr int TS = 192, XP = 100, HPAD = 4, VEC = 4, OCC = 2;
+};
+template <>
+struct Cfg<double> {
+    static constexpr int TS = 96, XP = 98, HPAD = 2, VEC = 2, OCC = 1;
+};
+
+template <typename T, int N>
+struct alignas(16) Vec {
+    T v[N];
+};
+
+template <typename T>
+struct PassParams {
+    const T *X, *W, *H_in, *w_kl, *w_lhalf, *h_scale;
+    T *H_out, *partial_wnum, *per_sample;
+    double *partial_obj, *partial_hsum;
+    int64_t D;
+    int V, k, flags, vec_x, vec_h;
+};
+
+__device__ __forceinline__ float sal_div(float a, float b) { return __fdividef(a, b); }
+__device__ __forceinline__ double sal_div(double a, double b) { return a / b; }
+__device__ __forceinline__ float sal_log(float a) { return logf(a); }
+__device__ __forceinline__ double sal_log(double a) { return log(a); }
+__device__ __forceinline__ float sal_sqrt(float a) { return sqrtf(a); }
+__device__ __forceinline__ double sal_sqrt(double a) { return sqrt(a); }
+__device__ __forceinline__ float sal_fma(float a, float b, float c) { return fmaf(a, b, c); }
+__device__ __forceinline__ double sal_fma(double a, double b, double c) { return fma(a, b, c); }
+
+__device__ __forceinline__ double block_sum_192(double x, double* s_red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = x;
+    __syncthreads();
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < NT / 32; ++w) t += s_red[w];
+    return t;
+}
+
+template <typename T, int KP>
+__global__ void __launch_bounds__(NT, Cfg<T>::OCC) klnmf_pass_kernel(PassParams<T> p) {
+    using C = Cfg<T>;
+    constexpr int TS = C::TS, XP = C::XP, HP = KP + C::HPAD, VEC = C::VEC, KH = KP / 2;
+    using V16 = Vec<T, VEC>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* sW = reinterpret_cast<T*>(smem_raw);  // [VP][KP]   sW[v][j] = W[j][v]
+    T* sH = sW + VP * KP;                    // [TS][HP]
+    T* sX = sH + TS * HP;                    // [TS][XP]   counts, overwritten by the quotient
+    __shared__ double s_red[NT / 32];
+
+    const int tid = threadIdx.x;
+    const int V = p.V, k = p.k;
+    const T eps = (T)SAL_EPS_F32;
+    const bool do_h = p.flags & SAL_PASS_UPDATE_H, do_w = p.flags & SAL_PASS_WNUM;
+    const bool do_kl = p.flags & (SAL_PASS_OBJECTIVE | SAL_PASS_SAMPLEWISE);
+    const bool do_pois = p.flags & SAL_PASS_POISSON;
+    const bool do_hsum = p.flags & SAL_PASS_HSUM;
+
+    for (int i = tid; i < VP * KP; i += NT) {
+        const int v = i / KP, j = i - v * KP;
+        sW[i] = (v < V && j < k) ? p.W[(size_t)j * V + v] : (T)0;
+    }
+
+    const int pv = tid % VP, kh = tid / VP;  // phase-2 identity
+    T acc[KH];
+    T hs_acc[KH];
+#pragma unroll
+    for (int j = 0; j < KH; ++j) acc[j] = (T)0, hs_acc[j] = (T)0;
+    double obj_acc = 0.0;
+
+    const int64_t n_tiles = (p.D + TS - 1) / TS;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t d0 = tile * TS;
+        const int n_valid = (int)min((int64_t)TS, p.D - d0);
+        __syncthreads();  // previous tile's phase 2 done (and sW ready on the first trip)
+
+        // ---- stage H tile: sH[s][j] = H_in[d0+s][j] (optionally scaled+clipped), zero padded
+        {
+            const T* Hg = p.H_in + (size_t)d0 * k;
+            for (int i = tid; i < TS * KP; i += NT) {
+                const int s = i / KP, j = i - s * KP;
+                T val = (T)0;
+                if (s < n_valid && j < k) {
+                    val = Hg[s * k + j];
+                    if (p.h_scale) val = max(val * p.h_scale[j], eps);
+                }
+                sH[s * HP + j] = val;
+            }
+        }
+        // ---- stage X tile (coalesced; 128-bit when rows are 16-byte aligned)
+        {
+            const T* Xg = p.X + (size_t)d0 * V;
+            if (p.vec_x) {
+                const int vpr = V / VEC;  // vectors per row
+                const V16* Xv = reinterpret_cast<const V16*>(Xg);
+                for (int i = tid; i < n_valid * vpr; i += NT) {
+                    const int s = i / vpr, c = i - s * vpr;
+                    *reinterpret_cast<V16*>(sX + s * XP + c * VEC) = Xv[i];
+                }
+            } else {
+                for (int i = tid; i < n_valid * V; i += NT) {
+                    const int s = i / V, v = i - s * V;
+                    sX[s * XP + v] = Xg[i];
+                }
+                const int vr = (V + VEC - 1) / VEC * VEC;
+                if (vr != V)
+                    for (int i = tid; i < n_valid * (vr - V); i += NT) {
+                        const int s = i / (vr - V), v = V + (i - s * (vr - V));
+                        sX[s * XP + v] = (T)0;
+                    }
+            }
+        }
+        __syncthreads();
+
+        // ---- phase 1: one sample per thread
+        T hn[KP];
+        if (tid < TS) {
+            const int s = tid;
+            const int64_t d = d0 + s;
+            T* xrow = sX + s * XP;
+            if (s < n_valid) {
+                T h[KP];
+#pragma unroll
+                for (int j = 0; j < KP; j += VEC) {
+                    const V16 t = *reinterpret_cast<const V16*>(sH + s * HP + j);
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) h[j + e] = t.v[e], hn[j + e] = (T)0;
+                }
+                const T wk = p.w_kl ? p.w_kl[d] : (T)1;
+                T kl = (T)0;
+                for (int v0 = 0; v0 < V; v0 += VEC) {
+                    const V16 x = *reinterpret_cast<const V16*>(xrow + v0);
+                    V16 r;
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) {
+                        const int v = v0 + e;
+                        T w[KP];
+#pragma unroll
+                        for (int j = 0; j < KP; j += VEC) {
+                            const V16 t = *reinterpret_cast<const V16*>(sW + v * KP + j);
+#pragma unroll
+                            for (int q = 0; q < VEC; ++q) w[j + q] = t.v[q];
+                        }
+                        T wh0 = (T)0, wh1 = (T)0;
+#pragma unroll
+                        for (int j = 0; j < KP; j += 2) {
+                            wh0 = sal_fma(w[j], h[j], wh0);
+                            wh1 = sal_fma(w[j + 1], h[j + 1], wh1);
+                        }
+                        const T wh = wh0 + wh1;
+                        const T xv = x.v[e];
+                        const bool in = v < V;
+                        const T rr = in ? sal_div(xv, wh) : (T)0;
+#pragma unroll
+                        for (int j = 0; j < KP; ++j) hn[j] = sal_fma(w[j], rr, hn[j]);
+                        r.v[e] = rr * wk;
+                        if (do_kl && in) {
+                            if (xv != (T)0) kl += xv * sal_log(rr) - xv;
+                            kl += wh;
+                        }
+                        if (do_pois && in) {
+                            if (wh != (T)0) kl += xv * sal_log(wh);
+                            kl -= wh;
+                        }
+                    }
+                    *reinterpret_cast<V16*>(xrow + v0) = r;
+                }
+                if (p.flags & SAL_PASS_SAMPLEWISE) p.per_sample[d] = kl;
+                if (p.flags & (SAL_PASS_OBJECTIVE | SAL_PASS_POISSON)) {
+                    double o = (double)kl * (double)wk;
+                    if (p.w_lhalf && !do_pois) {
+                        T sq = (T)0;
+#pragma unroll
+                        for (int j = 0; j < KP; ++j) sq += sal_sqrt(h[j]);
+                        o += (double)p.w_lhalf[d] * (double)sq;
+                    }
+                    obj_acc += o;
+                }
+                if (do_h) {
+                    if (p.h_scale) {
+#pragma unroll
+                        for (int j = 0; j < KP; ++j) hn[j] = h[j];
+                    } else if (!p.w_lhalf) {
+#pragma unroll
+                        for (int j = 0; j < KP; ++j) hn[j] = max(h[j] * hn[j], eps);
+                    } else {
+                        const T lam = p.w_lhalf[d];
+                        const T wsq = p.w_kl ? wk * wk : (T)1;
+#pragma unroll
+                        for (int j = 0; j < KP; ++j) {
+                            T t = (T)4 * h[j] * hn[j];
+                            if (p.w_kl) t *= wsq;
+                            const T disc = (T)0.25 * lam * lam + t;
+                            const T root = lam / (T)2 - sal_sqrt(disc);
+                            T o = (T)0.25 * root * root;
+                            if (p.w_kl) o = o / wsq;
+                            hn[j] = max(o, eps);
+                        }
+                    }
+                    T* og = p.H_out + (size_t)d * k;
+                    if (p.vec_h) {
+#pragma unroll
+                        for (int j = 0; j < KP; j += VEC)
+                            if (j < k) {
+                                V16 t;
+#pragma unroll
+                                for (int e = 0; e < VEC; ++e) t.v[e] = hn[j + e];
+                                *reinterpret_cast<V16*>(og + j) = t;
+                            }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < KP; ++j)
+                            if (j < k) og[j] = hn[j];
+                    }
+                }
+            } else {
+                const int vr = (V + VEC - 1) / VEC * VEC;
+                for (int v0 = 0; v0 < vr; ++v0) xrow[v0] = (T)0;
+            }
+        }
+        __syncthreads();
+
+        // ---- phase 2: numerator tile  acc[j] += A[s][v] * H[s][kh*KH + j]
+        if ((do_w || do_hsum) && pv < V) {
+            const T* hbase = sH + kh * KH;
+#pragma unroll 4
+            for (int s = 0; s < TS; ++s) {
+                const T r = sX[s * XP + pv];
+                T hv[KH];
+#pragma unroll
+                for (int j = 0; j < KH; j += VEC) {
+                    const V16 t = *reinterpret_cast<const V16*>(hbase + s * HP + j);
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) hv[j + e] = t.v[e];
+                }
+#pragma unroll
+                for (int j = 0; j < KH; ++j) acc[j] = sal_fma(r, hv[j], acc[j]);
+                if (do_hsum && pv == 0) {
+#pragma unroll
+                    for (int j = 0; j < KH; ++j) hs_acc[j] += hv[j];
+                }
+            }
+        }
+    }
+
+    // ---- per-CTA partials (every launched CTA owns >= 1 tile, so all slots are written)
+    if (do_w && pv < V) {
+#pragma unroll
+        for (int j = 0; j < KH; ++j)
+            p.partial_wnum[((size_t)blockIdx.x * KP + kh * KH + j) * VP + pv] = acc[j];
+    }
+    if (do_hsum && pv == 0) {
+#pragma unroll
+        for (int j = 0; j < KH; ++j) p.partial_hsum[(size_t)blockIdx.x * SAL_KMAX + kh * KH + j] = (double)hs_acc[j];
+    }
+    if (p.flags & (SAL_PASS_OBJECTIVE | SAL_PASS_POISSON)) {
+        const double t = block_sum_192(obj_acc, s_red);
+        if (tid == 0) p.partial_obj[blockIdx.x] = t;
+    }
+}
+
+// Fixed-order reduction of the per-CTA partials (deterministic).
+template <typename T>
+__global__ void __launch_bounds__(128) klnmf_reduce_kernel(const T* partial_wnum, const double* partial_obj,
+                                                           const double* partial_hsum, int n_part, int KP,
+                                                           int k, int V, int flags, T* Wnum, double* objective,
+                                                           T* hsum) {
+    const int n_w = (flags & SAL_PASS_WNUM) ? k * V : 0;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_w) {
+        const int j = i / V, v = i - j * V;
+        double s = 0.0;
+        const T* src = partial_wnum + (size_t)j * VP + v;
+#pragma unroll 8
+        for (int b = 0; b < n_part; ++b) s += (double)src[(size_t)b * KP * VP];
+        Wnum[i] = (T)s;
+    }
+    if (blockIdx.x == gridDim.x - 1) {
+        if ((flags & (SAL_PASS_OBJECTIVE | SAL_PASS_POISSON)) && threadIdx.x < 32) {
+            double s = 0.0;
+            for (int b = threadIdx.x; b < n_part; b += 32) s += partial_obj[b];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (threadIdx.x == 0) *objective = s;
+        }
+        if ((flags & SAL_PASS_HSUM) && threadIdx.x >= 64 && threadIdx.x - 64 < k) {
+            const int j = threadIdx.x - 64;
+            double s = 0.0;
+            for (int b = 0; b < n_part; ++b) s += partial_hsum[(size_t)b * SAL_KMAX + j];
+            hsum[j] = (T)s;
+        }
+    }
+}
+
+// W epilogue: one CTA per signature.
+template <typename T>
+__global__ void __launch_bounds__(128) w_epilogue_kernel(const T* W_in, const T* Wnum, int V, int n_given,
+                                                         int clip_given, T* W_out) {
+    __shared__ double s_red[4];
+    const int j = blockIdx.x, v = threadIdx.x;
+    const bool in = v < V;
+    const double w = in ? (double)W_in[(size_t)j * V + v] : 0.0;
+    double val = in ? w * (double)Wnum[(size_t)j * V + v] : 0.0;
+    double s = val;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((v & 31) == 0) s_red[v >> 5] = s;
+    __syncthreads();
+    s = s_red[0] + s_red[1] + s_red[2] + s_red[3];
+    if (!in) return;
+    double out = val / s;
+    if (j < n_given) out = w;
+    if (clip_given || j >= n_given) out = fmax(out, (double)SAL_EPS_F32);
+    W_out[(size_t)j * V + v] = (T)out;
+}
+
+template <typename T, int KP>
+size_t pass_smem_bytes() {
+    using C = Cfg<T>;
+    return sizeof(T) * ((size_t)VP * KP + (size_t)C::TS * (KP + C::HPAD) + (size_t)C::TS * C::XP);
+}
+
+template <typename T, int KP>
+int launch_pass_t(sal_ctx* c, const PassArgs& a, cudaStream_t st) {
+    using C = Cfg<T>;
+    static bool attr_set[16] = {false};
+    const size_t smem = pass_smem_bytes<T, KP>();
+    if (!attr_set[c->device & 15]) {
+        SAL_CUDA(cudaFuncSetAttribute(klnmf_pass_kernel<T, KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[c->device & 15] = true;
+    }
+    PassParams<T> p;
+    p.X = (const T*)a.X, p.W = (const T*)a.W, p.H_in = (const T*)a.H_in;
+    p.w_kl = (const T*)a.w_kl, p.w_lhalf = (const T*)a.w_lhalf, p.h_scale = (const T*)a.h_scale;
+    p.H_out = (T*)a.H_out, p.partial_wnum = (T*)c->partial_wnum, p.per_sample = (T*)a.per_sample;
+    p.partial_obj = c->partial_obj, p.partial_hsum = c->partial_hsum;
+    p.D = c->D, p.V = c->V, p.k = c->k, p.flags = a.flags;
+    p.vec_x = (c->V % C::VEC == 0) && (((uintptr_t)a.X) % 16 == 0);
+    p.vec_h = (c->k % C::VEC == 0) && (((uintptr_t)a.H_out) % 16 == 0);
+    const int64_t n_tiles = (c->D + C::TS - 1) / C::TS;
+    const int grid = (int)(n_tiles < c->grid_pass ? n_tiles : c->grid_pass);
+    klnmf_pass_kernel<T, KP><<<grid, NT, smem, st>>>(p);
+    SAL_CUDA(cudaGetLastError());
+    c->launches++;
+    if (a.flags & (SAL_PASS_WNUM | SAL_PASS_OBJECTIVE | SAL_PASS_POISSON | SAL_PASS_HSUM)) {
+        const int n_w = (a.flags & SAL_PASS_WNUM) ? c->k * c->V : 0;
+        const int rb = (n_w + 127) / 128 + 1;
+        klnmf_reduce_kernel<T><<<rb, 128, 0, st>>>((const T*)c->partial_wnum, c->partial_obj, c->partial_hsum, grid,
+                                                  KP, c->k, c->V, a.flags, (T*)a.Wnum, a.objective, (T*)a.hsum);
+        SAL_CUDA(cudaGetLastError());
+        c->launches++;
+    }
+    return 0;
+}
+
+template <typename T>
+int launch_pass_k(sal_ctx* c, const PassArgs& a, cudaStream_t st) {
+    switch (c->KP) {
+        case 8: return launch_pass_t<T, 8>(c, a, st);
+        case 16: return launch_pass_t<T, 16>(c, a, st);
+        case 24: return launch_pass_t<T, 24>(c, a, st);
+        default: return launch_pass_t<T, 32>(c, a, st);
+    }
+}
+
+}  // namespace
+
+int sal_launch_pass_fma(sal_ctx* c, const PassArgs& a, cudaStream_t st) {
+    return c->dtype == SAL_F32 ? launch_pass_k<float>(c, a, st) : launch_pass_k<double>(c, a, st);
+}
+
+int sal_pass_smem_bytes(int dtype, int KP) {
+    if (dtype == SAL_F32) return (int)pass_smem_bytes<float, 32>() - (32 - KP) * 4 * (VP + Cfg<float>::TS);
+    return (int)pass_smem_bytes<double, 32>() - (32 - KP) * 8 * (VP + Cfg<double>::TS);
+}
+
+int sal_launch_w_epilogue(sal_ctx* c, const void* W_in, const void* Wnum, int n_given, int clip_given,
+                          void* W_out, cudaStream_t st) {
+    const size_t bytes = (size_t)c->k * c->V * (c->dtype == SAL_F32 ? 4 : 8);
+    if (n_given >= c->k) {
+        if (W_out != W_in) SAL_CUDA(cudaMemcpyAsync(W_out, W_in, bytes, cudaMemcpyDeviceToDevice, st));
+        return 0;
+    }
+    if (c->dtype == SAL_F32)
+        w_epilogue_kernel<float><<<c->k, 128, 0, st>>>((const float*)W_in, (const float*)Wnum, c->V, n_given,
+                                                      clip_given, (float*)W_out);
+    else
+        w_epilogue_kernel<double><<<c->k, 128, 0, st>>>((const double*)W_in, (const double*)Wnum, c->V, n_given,
+                                                       clip_given, (double*)W_out);
+    SAL_CUDA(cudaGetLastError());
+    c->launches++;
+    return 0;
+}

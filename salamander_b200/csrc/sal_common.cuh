@@ -1,0 +1,63 @@
+// Shared declarations of libsalamander_b200 (sm_100a).  See include/salamander_b200.h for the ABI.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/salamander_b200.h"
+
+#define SAL_VMAX 96   // features per sample handled by the kernels (SBS-96 / ID-83 / SV-32)
+#define SAL_KMAX 32   // signatures handled by the kernels
+#define SAL_EPS_F32 1.1920928955078125e-07  // np.finfo(np.float32).eps, the reference's clip constant
+
+struct sal_ctx {
+    int V, k, KP, dtype, device, math;
+    int64_t D;
+    int n_sm;
+    int grid_pass;         // persistent grid of the fused pass
+    void* partial_wnum;    // [grid_pass][KP][SAL_VMAX] real
+    double* partial_obj;   // [grid_pass]
+    double* partial_hsum;  // [grid_pass][SAL_KMAX]
+    void* tc_ws;           // tensor-core path workspace (may be null)
+    int64_t launches;
+};
+
+void sal_set_error(const char* fmt, ...);
+
+#define SAL_CUDA(call)                                                                       \
+    do {                                                                                     \
+        cudaError_t e__ = (call);                                                            \
+        if (e__ != cudaSuccess) {                                                            \
+            sal_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return (int)e__;                                                                 \
+        }                                                                                    \
+    } while (0)
+
+#define SAL_CHECK_ARG(cond, msg)            \
+    do {                                    \
+        if (!(cond)) {                      \
+            sal_set_error("invalid argument: %s", msg); \
+            return SAL_EINVAL;              \
+        }                                   \
+    } while (0)
+
+static inline int sal_kpad(int k) { return k <= 8 ? 8 : k <= 16 ? 16 : k <= 24 ? 24 : 32; }
+
+// ---- launchers implemented in the .cu files -------------------------------------------------
+struct PassArgs {
+    const void *X, *W, *H_in, *w_kl, *w_lhalf, *h_scale;
+    void *H_out, *Wnum, *per_sample, *hsum;
+    double* objective;
+    int flags;
+};
+int sal_launch_pass_fma(sal_ctx* c, const PassArgs& a, cudaStream_t st);
+int sal_launch_pass_tf32(sal_ctx* c, const PassArgs& a, cudaStream_t st);  // tcgen05 path (fp32 only)
+int sal_pass_smem_bytes(int dtype, int KP);
+int sal_launch_w_epilogue(sal_ctx* c, const void* W_in, const void* Wnum, int n_given, int clip_given,
+                          void* W_out, cudaStream_t st);
+int sal_launch_mvnmf_logdet(sal_ctx* c, const void* W, double delta, double* out, cudaStream_t st);
+int sal_launch_mvnmf_w_unc(sal_ctx* c, const void* W, const void* N, const void* hsum, double lam,
+                           double delta, int n_given, void* W_unc, cudaStream_t st);
+int sal_launch_mvnmf_trial(sal_ctx* c, const void* W, const void* W_unc, double gamma, double delta,
+                           void* W_trial, void* h_scale, double* logdet_out, cudaStream_t st);

@@ -1,0 +1,205 @@
+"""
+``SignatureNMF``: constructor, ``fit`` loop and the abstract seam of all models.
+
+Same public surface as reference models/signature_nmf.py:138-185, 237-385 -- constructor
+kwargs, ``fit(adata, given_parameters, init_kwargs, fitting_kwargs, history, verbose,
+verbosity_freq)``, results inside the AnnData objects, ``history['objective_function']`` --
+with two keyword-only additions: ``device`` and ``dtype`` ('float64' parity mode, 'float32'
+fast mode).  Between ``_to_device`` and ``_to_host`` all model state lives in HBM and every
+numerical step is a CUDA kernel of libsalamander_b200 (there is no CPU path).
+Plot wrappers and dimensionality-reduction helpers are out of scope.
+"""
+
+from __future__ import annotations
+
+from abc import ABC, abstractmethod
+from typing import Any, Literal
+
+import numpy as np
+import pandas as pd
+
+from .._anndata import AnnData
+from .._device import resolve_device, resolve_dtype
+from ..initialization.methods import _INIT_METHODS
+from ..utils import EPSILON, type_checker, value_checker
+
+
+class SignatureNMF(ABC):
+    def __init__(
+        self,
+        n_signatures: int = 1,
+        init_method: str = "nndsvd",
+        min_iterations: int = 500,
+        max_iterations: int = 10000,
+        conv_test_freq: int = 10,
+        tol: float = 1e-7,
+        *,
+        device=None,
+        dtype="float64",
+        math: str = "fma",
+    ):
+        value_checker("init_method", init_method, _INIT_METHODS)
+        value_checker("math", math, ("fma", "tf32"))
+        self.n_signatures = n_signatures
+        self.init_method = init_method
+        self.min_iterations = min_iterations
+        self.max_iterations = max_iterations
+        self.conv_test_freq = conv_test_freq
+        self.tol = tol
+        self.device = device
+        self.dtype = resolve_dtype(dtype)
+        self.math = math
+
+        # data / fitting dependent attributes (reference signature_nmf.py:182-185)
+        self.adata = AnnData()
+        self.asignatures = AnnData()
+        self.history: dict[str, Any] = {}
+
+        self._dev = None  # device-resident state while fitting
+        self._in_fit = False
+        self.n_iterations = 0
+
+    # ---- accessors (reference signature_nmf.py:187-235) ----------------------------------
+    @property
+    def mutation_types(self) -> list[str]:
+        return list(self.adata.var_names)
+
+    @property
+    def signature_names(self) -> list[str]:
+        return list(self.asignatures.obs_names)
+
+    @property
+    def sample_names(self) -> list[str]:
+        return list(self.adata.obs_names)
+
+    @property
+    def signatures(self) -> pd.DataFrame:
+        """Signatures as an (n_features, n_signatures) frame, i.e. W."""
+        return pd.DataFrame(np.asarray(self.asignatures.X).T, index=self.mutation_types, columns=self.signature_names)
+
+    @property
+    def exposures(self) -> pd.DataFrame:
+        """Exposures as an (n_samples, n_signatures) frame, i.e. H^T."""
+        assert "exposures" in self.adata.obsm, "Accessing the exposures requires fitting the NMF model."
+        return pd.DataFrame(self.adata.obsm["exposures"], index=self.sample_names, columns=self.signature_names)
+
+    @abstractmethod
+    def compute_reconstruction_errors(self) -> None:
+        """Write per-sample reconstruction errors to ``adata.obs['reconstruction_error']``."""
+
+    @property
+    def reconstruction_error(self) -> float:
+        if "reconstruction_error" not in self.adata.obs:
+            self.compute_reconstruction_errors()
+        return float(np.sum(self.adata.obs["reconstruction_error"]))
+
+    @property
+    @abstractmethod
+    def objective(self) -> Literal["minimize", "maximize"]:
+        ...
+
+    @abstractmethod
+    def objective_function(self) -> float:
+        ...
+
+    # ---- the seam (reference signature_nmf.py:269-313) -------------------------------------
+    def _setup_adata(self, adata: AnnData) -> None:
+        """Type check, then clip the counts to EPSILON *on the caller's object* (reference :269-281)."""
+        type_checker("adata", adata, AnnData)
+        self.adata = adata
+        self.adata.X = np.asarray(self.adata.X).clip(EPSILON)
+
+    @abstractmethod
+    def _initialize(self, given_parameters=None, init_kwargs=None) -> None:
+        ...
+
+    @abstractmethod
+    def _setup_fitting_parameters(self, fitting_kwargs=None) -> None:
+        ...
+
+    @abstractmethod
+    def _update_parameters(self, given_parameters=None) -> None:
+        ...
+
+    # ---- device residency ------------------------------------------------------------------
+    @abstractmethod
+    def _to_device(self) -> None:
+        """Upload X (this rank's rows), parameters and fitting weights; create the workspace."""
+
+    @abstractmethod
+    def _to_host(self) -> None:
+        """Write the parameters back into the AnnData objects as float64 host arrays."""
+
+    def _release_device(self) -> None:
+        if self._dev is not None:
+            self._dev.close()
+            self._dev = None
+
+    def _resolved_device(self):
+        return resolve_device(self.device)
+
+    class _Resident:
+        """``with self._resident():`` -- run a block with state in HBM; outside ``fit`` this uploads before
+        and downloads after, which is what lets single updates be called the way the reference's tests do."""
+
+        def __init__(self, model):
+            self.m = model
+            self.owner = False
+
+        def __enter__(self):
+            if self.m._dev is None:
+                self.m._to_device()
+                self.owner = True
+            return self.m._dev
+
+        def __exit__(self, exc_type, exc, tb):
+            if self.owner:
+                try:
+                    if exc_type is None:
+                        self.m._to_host()
+                finally:
+                    self.m._release_device()
+            return False
+
+    def _resident(self):
+        return SignatureNMF._Resident(self)
+
+    # ---- fit (reference signature_nmf.py:315-385) ------------------------------------------
+    def fit(
+        self,
+        adata: AnnData,
+        given_parameters: dict[str, Any] | None = None,
+        init_kwargs: dict[str, Any] | None = None,
+        fitting_kwargs: dict[str, Any] | None = None,
+        history: bool = True,
+        verbose: Literal[0, 1] = 0,
+        verbosity_freq: int = 1000,
+    ) -> "SignatureNMF":
+        self._setup_adata(adata)
+        self._initialize(given_parameters, init_kwargs)
+        self._setup_fitting_parameters(fitting_kwargs)
+
+        with self._resident():
+            self._in_fit = True
+            try:
+                of_values = [self.objective_function()]
+                n_iteration = 0
+                converged = False
+                while not converged:
+                    n_iteration += 1
+                    if verbose and n_iteration % verbosity_freq == 0:
+                        print(f"iteration: {n_iteration}; objective: {of_values[-1]:.2f}")
+                    self._update_parameters(given_parameters)
+                    if n_iteration % self.conv_test_freq == 0:
+                        prev = of_values[-1]
+                        of_values.append(self.objective_function())
+                        rel_change = np.abs(prev - of_values[-1]) / np.abs(prev)
+                        converged = bool(rel_change < self.tol and n_iteration >= self.min_iterations)
+                    converged |= n_iteration >= self.max_iterations
+                self.n_iterations = n_iteration
+            finally:
+                self._in_fit = False
+
+        if history:
+            self.history["objective_function"] = of_values[1:]
+        return self

@@ -1,0 +1,96 @@
+"""
+``StandardNMF``: models parameterised by a signature matrix W and an exposure matrix H
+(reference models/standard_nmf.py:18-58).  Holds the device-resident state shared by
+KLNMF and MvNMF and the sample sharding across ranks.
+"""
+
+from __future__ import annotations
+
+from typing import Any
+
+import numpy as np
+import torch
+
+from .. import _dist
+from .._device import PASS_SAMPLEWISE, Workspace
+from ..initialization.initialize import initialize_standard_nmf
+from .signature_nmf import SignatureNMF
+
+
+class StandardState:
+    """X [D_local][V], W [k][V], H [D_local][k] in HBM plus scratch; D_local = this rank's row block."""
+
+    def __init__(self, model: "StandardNMF"):
+        dev = model._resolved_device()
+        dt = model.dtype
+        X_host = np.asarray(model.adata.X)
+        W_host = np.asarray(model.asignatures.X, dtype=np.float64)
+        H_host = np.asarray(model.adata.obsm["exposures"], dtype=np.float64)
+        self.D_total, self.V = X_host.shape
+        self.k = W_host.shape[0]
+        self.rank, self.world = _dist.world()
+        self.lo, self.hi = _dist.shard_bounds(self.D_total, self.world, self.rank)
+        if self.world > 1:  # replicas must start bit-identical whatever the host RNG did
+            W_host = _dist.broadcast_numpy(W_host, dev)
+            H_host = _dist.broadcast_numpy(H_host, dev)
+        self.device, self.dtype = dev, dt
+        D = self.hi - self.lo
+        self.X = torch.as_tensor(np.ascontiguousarray(X_host[self.lo : self.hi]), dtype=dt).to(dev).contiguous()
+        self.W = torch.as_tensor(np.ascontiguousarray(W_host), dtype=dt).to(dev).contiguous()
+        self.H = torch.as_tensor(np.ascontiguousarray(H_host[self.lo : self.hi]), dtype=dt).to(dev).contiguous()
+        self.Wnum = torch.zeros((self.k, self.V), dtype=dt, device=dev)
+        self.obj = torch.zeros(1, dtype=torch.float64, device=dev)
+        self.ws = Workspace(self.V, D, self.k, dt, dev, math=model.math)
+        self.weights: dict[str, Any] = {}
+
+    def shard(self, per_sample) -> torch.Tensor | None:
+        """Upload this rank's slice of a per-sample host vector (or None)."""
+        if per_sample is None:
+            return None
+        arr = np.ascontiguousarray(np.asarray(per_sample, dtype=np.float64)[self.lo : self.hi])
+        return torch.as_tensor(arr, dtype=self.dtype).to(self.device).contiguous()
+
+    def objective_value(self) -> float:
+        """Sum the device scalar over ranks and bring it to the host (one sync)."""
+        _dist.allreduce_sum_(self.obj)
+        return float(self.obj.item())
+
+    def close(self) -> None:
+        self.ws.close()
+
+
+class StandardNMF(SignatureNMF):
+    def _initialize(self, given_parameters=None, init_kwargs=None) -> None:
+        """Initialise signatures and exposures; given signatures are kept fixed (reference :32-58)."""
+        init_kwargs = {} if init_kwargs is None else init_kwargs.copy()
+        self.asignatures = initialize_standard_nmf(
+            self.adata, self.n_signatures, self.init_method, given_parameters, **init_kwargs
+        )
+
+    def _to_device(self) -> None:
+        self._dev = StandardState(self)
+        self._upload_fitting_parameters()
+
+    def _upload_fitting_parameters(self) -> None:
+        """Hook for per-sample weights etc."""
+
+    def _to_host(self) -> None:
+        st = self._dev
+        self.asignatures.X = st.W.to(torch.float64).cpu().numpy()
+        H_full = _dist.gather_rows(st.H, st.D_total)
+        self.adata.obsm["exposures"] = H_full.to(torch.float64).cpu().numpy()
+
+    def compute_reconstruction_errors(self) -> None:
+        """Unweighted per-sample KL divergences -> ``adata.obs['reconstruction_error']``
+        (reference klnmf.py:54-62, mvnmf.py:139-147 -> _utils_klnmf.py:58-97)."""
+        with self._resident() as st:
+            out = torch.empty(st.hi - st.lo, dtype=st.dtype, device=st.device)
+            st.ws.klnmf_pass(st.X, st.W, st.H, PASS_SAMPLEWISE, per_sample=out)
+            full = _dist.gather_rows(out, st.D_total)
+            self.adata.obs["reconstruction_error"] = full.to(torch.float64).cpu().numpy()
+
+    @staticmethod
+    def _n_given(given_parameters) -> int:
+        if given_parameters and "asignatures" in given_parameters:
+            return given_parameters["asignatures"].n_obs
+        return 0

@@ -1,0 +1,210 @@
+"""
+GPU parity at the model level (public API: constructor + fit(adata) + single updates).
+
+* mirrors reference tests/test_klnmf.py:58-91 and tests/test_mvnmf.py:57-90 on the
+  reference's golden fixtures;
+* full trajectories from the LIVE reference (tests/golden/trajectories, made by
+  oracle/make_golden.py): float64 objective history within 1e-9 relative; float32 final KL
+  within 1e-4 relative and signature cosine >= 0.9999 (the north-star tolerances).
+"""
+
+import os
+import pickle
+
+import numpy as np
+import pandas as pd
+import pytest
+from conftest import GOLDEN, ROOT, golden_path
+
+import salamander_b200 as sal
+from salamander_b200 import AnnData
+
+pytestmark = pytest.mark.gpu
+
+TRAJ = os.path.join(GOLDEN, "trajectories")
+
+
+def counts_adata(*parts):
+    counts = pd.read_csv(golden_path(*parts), index_col=0)
+    return AnnData(counts.T)
+
+
+def pcawg_adata():
+    counts = pd.read_csv(os.path.join(ROOT, "salamander_b200", "data", "pcawg_breast_sbs.csv"), index_col=0)
+    return AnnData(counts.T)
+
+
+@pytest.fixture(params=[1, 2])
+def k(request):
+    return request.param
+
+
+@pytest.fixture(params=["float64", "float32"])
+def dtype(request):
+    return request.param
+
+
+def _model_init(cls, path, k, dtype, **kw):
+    adata = counts_adata(path, "counts.csv")
+    W_init = np.load(golden_path(path, f"W_init_nsigs{k}.npy"))
+    H_init = np.load(golden_path(path, f"H_init_nsigs{k}.npy"))
+    model = cls(n_signatures=k, dtype=dtype, **kw)
+    model.adata = adata
+    asig = AnnData(W_init.T)
+    asig.var_names = adata.var_names
+    model.asignatures = asig
+    model.adata.obsm["exposures"] = H_init.T
+    return model
+
+
+# ---- KLNMF (reference tests/test_klnmf.py) -------------------------------------------------
+
+
+def test_klnmf_objective_function(k, dtype):
+    model = _model_init(sal.models.KLNMF, "models/klnmf", k, dtype)
+    model._setup_fitting_parameters(None)
+    assert np.allclose(model.objective_function(), np.load(golden_path("models/klnmf", f"objective_init_nsigs{k}.npy")))
+
+
+def test_klnmf_update_parameters(k, dtype):
+    model = _model_init(sal.models.KLNMF, "models/klnmf", k, dtype)
+    model._setup_fitting_parameters(None)
+    model._update_parameters()
+    with open(golden_path("models/klnmf", f"WH_updated_joint_nsigs{k}.pkl"), "rb") as f:
+        W_updated, H_updated = pickle.load(f)
+    assert np.allclose(model.asignatures.X, W_updated.T)
+    assert np.allclose(model.adata.obsm["exposures"], H_updated.T)
+
+
+@pytest.mark.parametrize("cls", ["KLNMF", "MvNMF"])
+def test_given_signatures(k, dtype, cls):
+    adata = counts_adata("models/klnmf", "counts.csv")
+    for n_given in range(1, k + 1):
+        given = adata[:n_given, :].copy()
+        given.X = given.X / np.sum(given.X, axis=1, keepdims=True)
+        model = getattr(sal.models, cls)(n_signatures=k, min_iterations=3, max_iterations=3, dtype=dtype)
+        model.fit(adata.copy(), given_parameters={"asignatures": given})
+        assert np.allclose(given.X, model.asignatures.X[:n_given, :])
+        assert list(model.asignatures.obs_names[:n_given]) == list(given.obs_names)
+
+
+def test_fit_errors():
+    adata = counts_adata("models/klnmf", "counts.csv")
+    with pytest.raises(ValueError):
+        sal.models.KLNMF(init_method="bogus")
+    with pytest.raises(TypeError):
+        sal.models.KLNMF().fit(np.zeros((3, 3)))
+    with pytest.raises(ValueError):
+        sal.models.KLNMF(n_signatures=2).fit(adata.copy(), fitting_kwargs={"weights": 1.0})
+    with pytest.raises(ValueError):
+        sal.models.KLNMF(n_signatures=2).fit(adata.copy(), fitting_kwargs={"weights_kl": -np.ones(adata.n_obs)})
+    with pytest.raises(ValueError):
+        sal.models.KLNMF(n_signatures=2).fit(adata.copy(), given_parameters={"signatures": 1})
+
+
+# ---- MvNMF (reference tests/test_mvnmf.py) -------------------------------------------------
+
+
+def test_mvnmf_objective_function(k, dtype):
+    model = _model_init(sal.models.MvNMF, "models/mvnmf", k, dtype)
+    assert np.allclose(model.objective_function(), np.load(golden_path("models/mvnmf", f"objective_init_nsigs{k}.npy")))
+
+
+def test_mvnmf_update_W(k, dtype):
+    model = _model_init(sal.models.MvNMF, "models/mvnmf", k, dtype)
+    model._gamma = 1.0
+    model._update_W()
+    assert np.allclose(model.asignatures.X, np.load(golden_path("models/mvnmf", f"W_updated_nsigs{k}.npy")).T, rtol=1e-5 if dtype == "float64" else 1e-4)
+
+
+def test_mvnmf_update_H(k, dtype):
+    model = _model_init(sal.models.MvNMF, "models/mvnmf", k, dtype)
+    model._update_H()
+    assert np.allclose(model.adata.obsm["exposures"], np.load(golden_path("models/mvnmf", f"H_updated_nsigs{k}.npy")).T)
+
+
+# ---- trajectories of the live reference ----------------------------------------------------
+
+
+def _ctor(z, name, default):
+    key = f"ctor_{name}"
+    return z[key].item() if key in z.files else default
+
+
+def _cosine(A, B):
+    return np.sum(A * B, axis=1) / (np.linalg.norm(A, axis=1) * np.linalg.norm(B, axis=1))
+
+
+@pytest.mark.parametrize("tag", ["klnmf_pcawg_k5_seed0", "klnmf_pcawg_k4_weights", "klnmf_pcawg_k6_given2"])
+def test_klnmf_trajectory(tag, dtype):
+    z = np.load(os.path.join(TRAJ, f"{tag}.npz"))
+    adata = pcawg_adata()
+    kk, n_given = int(z["k"]), int(z["n_given"])
+    given = None
+    if n_given:
+        g = pcawg_adata()[:n_given, :].copy()
+        g.X = g.X / g.X.sum(axis=1, keepdims=True)
+        given = {"asignatures": g}
+    fk = {}
+    if z["weights_kl"].size:
+        fk["weights_kl"] = z["weights_kl"]
+    if z["weights_lhalf"].size:
+        fk["weights_lhalf"] = z["weights_lhalf"]
+    model = sal.models.KLNMF(
+        n_signatures=kk,
+        init_method="random",
+        min_iterations=_ctor(z, "min_iterations", 500),
+        max_iterations=_ctor(z, "max_iterations", 10000),
+        dtype=dtype,
+    )
+    model.fit(adata, given_parameters=given, init_kwargs={"seed": int(z["seed"])}, fitting_kwargs=fk or None)
+    hist = np.array(model.history["objective_function"])
+    ref = z["history"]
+    if dtype == "float64":
+        assert len(hist) == len(ref)
+        assert np.allclose(hist, ref, rtol=1e-9, atol=0)
+        assert np.allclose(model.asignatures.X, z["W"], rtol=1e-6, atol=1e-12)
+        assert np.allclose(model.adata.obsm["exposures"], z["H"], rtol=1e-6, atol=1e-9)
+    else:
+        assert abs(hist[-1] - ref[-1]) / abs(ref[-1]) < 1e-4
+        assert _cosine(model.asignatures.X, z["W"]).min() >= 0.9999
+    # the API contract of the reference: results live in the AnnData objects as float64 host arrays
+    assert model.asignatures.X.dtype == np.float64 and model.asignatures.X.shape == (kk, 96)
+    assert model.adata.obsm["exposures"].shape == (192, kk)
+    assert model.signatures.shape == (96, kk) and model.exposures.shape == (192, kk)
+
+
+@pytest.mark.parametrize("tag", ["mvnmf_pcawg_k10_seed0", "mvnmf_pcawg_k3_lam50"])
+def test_mvnmf_trajectory(tag, dtype):
+    z = np.load(os.path.join(TRAJ, f"{tag}.npz"))
+    model = sal.models.MvNMF(
+        n_signatures=int(z["k"]),
+        init_method="random",
+        lam=_ctor(z, "lam", 1.0),
+        delta=_ctor(z, "delta", 1.0),
+        min_iterations=_ctor(z, "min_iterations", 500),
+        max_iterations=_ctor(z, "max_iterations", 10000),
+        dtype=dtype,
+    )
+    model.fit(pcawg_adata(), init_kwargs={"seed": int(z["seed"])})
+    hist = np.array(model.history["objective_function"])
+    ref = z["history"]
+    if dtype == "float64":
+        assert np.allclose(hist, ref, rtol=1e-9, atol=0)
+        assert np.isclose(model._gamma, float(z["gamma"]))
+        assert np.allclose(model.asignatures.X, z["W"], rtol=1e-6, atol=1e-12)
+    else:
+        assert abs(hist[-1] - ref[-1]) / abs(ref[-1]) < 1e-4
+        assert _cosine(model.asignatures.X, z["W"]).min() >= 0.9999
+
+
+def test_reconstruction_error(dtype):
+    from oracle import EPSILON, klnmf
+
+    adata = pcawg_adata()
+    model = sal.models.KLNMF(n_signatures=3, init_method="random", min_iterations=20, max_iterations=20, dtype=dtype)
+    model.fit(adata, init_kwargs={"seed": 4})
+    ref = klnmf.samplewise_kl_divergence(adata.X.T, model.asignatures.X.T, adata.obsm["exposures"].T)
+    model.compute_reconstruction_errors()
+    assert np.allclose(adata.obs["reconstruction_error"].values, ref, rtol=1e-9 if dtype == "float64" else 2e-3, atol=1e-2 if dtype == "float32" else 0)
+    assert np.isclose(model.reconstruction_error, ref.sum(), rtol=1e-5)
