@@ -96,6 +96,13 @@ int sal_klnmf_pass(sal_handle_t h, const void* X, const void* W, const void* H_i
 int sal_w_epilogue(sal_handle_t h, const void* W_in, const void* Wnum, int n_given, int clip_given,
                    void* W_out, void* stream);
 
+/*
+ * In-place clip of the count matrix to EPSILON = 2^-23 (the reference does this on the host before every
+ * fit: SignatureNMF._setup_adata, models/signature_nmf.py:280-281).  n = number of elements of X;
+ * *n_changed (device int64, must be zeroed by the caller) receives how many entries were raised.
+ */
+int sal_clip_counts(sal_handle_t h, void* X, int64_t n, long long* n_changed, void* stream);
+
 /* ---- MvNMF single-CTA k x k steps (models/mvnmf.py) -------------------------------- */
 
 /* out[0] = ln det(W^T W + delta I)   (volume_logdet, mvnmf.py:19-24; LU with pivoting) */

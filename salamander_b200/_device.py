@@ -152,6 +152,19 @@ class Workspace:
             "sal_w_epilogue",
         )
 
+    def clip_counts(self, X, n_changed) -> None:
+        """X <- max(X, EPSILON) in place; ``n_changed`` (zeroed int64 device scalar) counts raised entries."""
+        _lib.check(
+            self.lib.sal_clip_counts(
+                self._h,
+                self._ptr(X, X.numel(), "X"),
+                int(X.numel()),
+                self._ptr(n_changed, 1, "n_changed", torch.int64),
+                self._stream(),
+            ),
+            "sal_clip_counts",
+        )
+
     def mvnmf_logdet(self, W, delta: float, out) -> None:
         _lib.check(
             self.lib.sal_mvnmf_logdet(

@@ -30,6 +30,7 @@ SYMBOLS = {
     "sal_launch_count": (_i64, [_vp]),
     "sal_klnmf_pass": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "sal_w_epilogue": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),
+    "sal_clip_counts": (_i, [_vp, _vp, _i64, _vp, _vp]),
     "sal_mvnmf_logdet": (_i, [_vp, _vp, _d, _vp, _vp]),
     "sal_mvnmf_w_unconstrained": (_i, [_vp, _vp, _vp, _vp, _d, _d, _i, _vp, _vp]),
     "sal_mvnmf_trial": (_i, [_vp, _vp, _vp, _d, _d, _vp, _vp, _vp, _vp]),

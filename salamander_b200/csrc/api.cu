@@ -81,14 +81,14 @@ int sal_klnmf_pass(sal_handle_t h, const void* X, const void* W, const void* H_i
                    const void* w_kl, const void* w_lhalf, const void* h_scale, int flags, void* Wnum,
                    double* objective, void* per_sample, void* hsum, void* stream) {
     SAL_CHECK_ARG(h != nullptr, "handle is null");
-    SAL_CHECK_ARG(X && W && H_in, "X, W, H_in must be non-null");
+    SAL_CHECK_ARG(W && (h->D == 0 || (X && H_in)), "X, W, H_in must be non-null");
     SAL_CHECK_ARG(flags != 0, "flags == 0: nothing to do");
-    SAL_CHECK_ARG(!(flags & SAL_PASS_UPDATE_H) || H_out, "UPDATE_H needs H_out");
+    SAL_CHECK_ARG(!(flags & SAL_PASS_UPDATE_H) || H_out || h->D == 0, "UPDATE_H needs H_out");
     SAL_CHECK_ARG(!(flags & SAL_PASS_WNUM) || Wnum, "WNUM needs Wnum");
     SAL_CHECK_ARG(!(flags & (SAL_PASS_OBJECTIVE | SAL_PASS_POISSON)) || objective, "OBJECTIVE needs objective");
     SAL_CHECK_ARG(!((flags & SAL_PASS_OBJECTIVE) && (flags & SAL_PASS_POISSON)), "OBJECTIVE and POISSON are exclusive");
     SAL_CHECK_ARG(!((flags & SAL_PASS_SAMPLEWISE) && (flags & SAL_PASS_POISSON)), "SAMPLEWISE and POISSON are exclusive");
-    SAL_CHECK_ARG(!(flags & SAL_PASS_SAMPLEWISE) || per_sample, "SAMPLEWISE needs per_sample");
+    SAL_CHECK_ARG(!(flags & SAL_PASS_SAMPLEWISE) || per_sample || h->D == 0, "SAMPLEWISE needs per_sample");
     SAL_CHECK_ARG(!(flags & SAL_PASS_HSUM) || hsum, "HSUM needs hsum");
     SAL_CUDA(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
@@ -115,6 +115,14 @@ int sal_w_epilogue(sal_handle_t h, const void* W_in, const void* Wnum, int n_giv
     SAL_CHECK_ARG(n_given == h->k || Wnum, "Wnum must be non-null");
     SAL_CUDA(cudaSetDevice(h->device));
     return sal_launch_w_epilogue(h, W_in, Wnum, n_given, clip_given, W_out, (cudaStream_t)stream);
+}
+
+int sal_clip_counts(sal_handle_t h, void* X, int64_t n, long long* n_changed, void* stream) {
+    SAL_CHECK_ARG(h != nullptr, "handle is null");
+    SAL_CHECK_ARG(n >= 0 && (n == 0 || (X && n_changed)), "X / n_changed must be non-null");
+    if (n == 0) return 0;
+    SAL_CUDA(cudaSetDevice(h->device));
+    return sal_launch_clip_counts(h, X, n, n_changed, (cudaStream_t)stream);
 }
 
 int sal_mvnmf_logdet(sal_handle_t h, const void* W, double delta, double* out, void* stream) {

@@ -346,6 +346,24 @@ __global__ void __launch_bounds__(128) w_epilogue_kernel(const T* W_in, const T*
     W_out[(size_t)j * V + v] = (T)out;
 }
 
+// X <- max(X, eps) in place, counting the entries that changed (grid-stride, one atomic per CTA).
+template <typename T>
+__global__ void __launch_bounds__(256) clip_counts_kernel(T* X, int64_t n, unsigned long long* n_changed) {
+    __shared__ unsigned int s_cnt;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    const T eps = (T)SAL_EPS_F32;
+    unsigned int cnt = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const T x = X[i];
+        if (x < eps) X[i] = eps, ++cnt;
+    }
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&s_cnt, cnt);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_cnt) atomicAdd(n_changed, (unsigned long long)s_cnt);
+}
+
 template <typename T, int KP>
 size_t pass_smem_bytes() {
     using C = Cfg<T>;
@@ -419,6 +437,18 @@ int sal_launch_w_epilogue(sal_ctx* c, const void* W_in, const void* Wnum, int n_
     else
         w_epilogue_kernel<double><<<c->k, 128, 0, st>>>((const double*)W_in, (const double*)Wnum, c->V, n_given,
                                                        clip_given, (double*)W_out);
+    SAL_CUDA(cudaGetLastError());
+    c->launches++;
+    return 0;
+}
+
+int sal_launch_clip_counts(sal_ctx* c, void* X, int64_t n, long long* n_changed, cudaStream_t st) {
+    const int64_t want = (n + 255) / 256;
+    const int grid = (int)(want < (int64_t)c->n_sm * 8 ? want : (int64_t)c->n_sm * 8);
+    if (c->dtype == SAL_F32)
+        clip_counts_kernel<float><<<grid, 256, 0, st>>>((float*)X, n, (unsigned long long*)n_changed);
+    else
+        clip_counts_kernel<double><<<grid, 256, 0, st>>>((double*)X, n, (unsigned long long*)n_changed);
     SAL_CUDA(cudaGetLastError());
     c->launches++;
     return 0;

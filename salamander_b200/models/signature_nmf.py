@@ -25,6 +25,8 @@ from ..utils import EPSILON, type_checker, value_checker
 
 
 class SignatureNMF(ABC):
+    _DEVICE_CLIP_MIN_SIZE = 1 << 22
+
     def __init__(
         self,
         n_signatures: int = 1,
@@ -37,6 +39,7 @@ class SignatureNMF(ABC):
         device=None,
         dtype="float64",
         math: str = "fma",
+        shard_input: bool = True,
     ):
         value_checker("init_method", init_method, _INIT_METHODS)
         value_checker("math", math, ("fma", "tf32"))
@@ -49,6 +52,10 @@ class SignatureNMF(ABC):
         self.device = device
         self.dtype = resolve_dtype(dtype)
         self.math = math
+        # multi-GPU (torch.distributed initialised): True = ``adata`` holds the whole matrix on every rank and
+        # each rank takes its contiguous row block; False = ``adata`` already holds only this rank's rows.
+        self.shard_input = bool(shard_input)
+        self.transfer_bytes = {"h2d": 0, "d2h": 0}  # host<->device bytes of the last fit / update
 
         # data / fitting dependent attributes (reference signature_nmf.py:182-185)
         self.adata = AnnData()
@@ -56,6 +63,7 @@ class SignatureNMF(ABC):
         self.history: dict[str, Any] = {}
 
         self._dev = None  # device-resident state while fitting
+        self._clip_on_device = False
         self._in_fit = False
         self.n_iterations = 0
 
@@ -107,7 +115,14 @@ class SignatureNMF(ABC):
         """Type check, then clip the counts to EPSILON *on the caller's object* (reference :269-281)."""
         type_checker("adata", adata, AnnData)
         self.adata = adata
-        self.adata.X = np.asarray(self.adata.X).clip(EPSILON)
+        X = np.asarray(self.adata.X)
+        if X.dtype in (np.float32, np.float64) and X.size >= self._DEVICE_CLIP_MIN_SIZE:
+            # large floating matrices are clipped on the device right after the upload (sal_clip_counts) and
+            # the host copy is only rewritten if an entry actually changed -- same observable result
+            self._clip_on_device = True
+        else:
+            self._clip_on_device = False
+            self.adata.X = X.clip(EPSILON)
 
     @abstractmethod
     def _initialize(self, given_parameters=None, init_kwargs=None) -> None:

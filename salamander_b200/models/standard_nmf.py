@@ -23,32 +23,67 @@ class StandardState:
     def __init__(self, model: "StandardNMF"):
         dev = model._resolved_device()
         dt = model.dtype
+        model.transfer_bytes = {"h2d": 0, "d2h": 0}
+        self.model = model
+        self.device, self.dtype = dev, dt
         X_host = np.asarray(model.adata.X)
         W_host = np.asarray(model.asignatures.X, dtype=np.float64)
-        H_host = np.asarray(model.adata.obsm["exposures"], dtype=np.float64)
-        self.D_total, self.V = X_host.shape
+        H_host = np.asarray(model.adata.obsm["exposures"])
         self.k = W_host.shape[0]
         self.rank, self.world = _dist.world()
-        self.lo, self.hi = _dist.shard_bounds(self.D_total, self.world, self.rank)
-        if self.world > 1:  # replicas must start bit-identical whatever the host RNG did
-            W_host = _dist.broadcast_numpy(W_host, dev)
-            H_host = _dist.broadcast_numpy(H_host, dev)
-        self.device, self.dtype = dev, dt
+        if model.shard_input:
+            self.D_total, self.V = X_host.shape
+            self.lo, self.hi = _dist.shard_bounds(self.D_total, self.world, self.rank)
+            if self.world > 1:  # replicas must start bit-identical whatever the host RNG did
+                W_host = _dist.broadcast_numpy(W_host, dev)
+                H_host = _dist.broadcast_numpy(H_host, dev)
+        else:  # adata already holds this rank's rows only
+            self.V = X_host.shape[1]
+            self.lo, self.hi = 0, X_host.shape[0]
+            self.D_total = self.hi
+            if self.world > 1:
+                W_host = _dist.broadcast_numpy(W_host, dev)
         D = self.hi - self.lo
-        self.X = torch.as_tensor(np.ascontiguousarray(X_host[self.lo : self.hi]), dtype=dt).to(dev).contiguous()
-        self.W = torch.as_tensor(np.ascontiguousarray(W_host), dtype=dt).to(dev).contiguous()
-        self.H = torch.as_tensor(np.ascontiguousarray(H_host[self.lo : self.hi]), dtype=dt).to(dev).contiguous()
+        self.ws = Workspace(self.V, D, self.k, dt, dev, math=model.math)
+        self.X = self.upload(X_host[self.lo : self.hi])
+        if model._clip_on_device:
+            changed = torch.zeros(1, dtype=torch.int64, device=dev)
+            self.ws.clip_counts(self.X, changed)
+            if int(changed.item()) > 0:  # reference signature_nmf.py:281 rebinds adata.X to the clipped matrix
+                clipped = self.download(self.X)
+                if model.shard_input and self.world > 1:
+                    clipped = _dist.gather_rows(self.X, self.D_total).to(torch.float64).cpu().numpy()
+                model.adata.X = clipped
+            model._clip_on_device = False
+        self.W = self.upload(W_host)
+        self.H = self.upload(H_host[self.lo : self.hi])
         self.Wnum = torch.zeros((self.k, self.V), dtype=dt, device=dev)
         self.obj = torch.zeros(1, dtype=torch.float64, device=dev)
-        self.ws = Workspace(self.V, D, self.k, dt, dev, math=model.math)
         self.weights: dict[str, Any] = {}
+
+    def upload(self, host) -> torch.Tensor:
+        """Host array -> contiguous device tensor of the model dtype (async DMA when the array is pinned)."""
+        t = torch.from_numpy(np.ascontiguousarray(host))
+        self.model.transfer_bytes["h2d"] += t.numel() * t.element_size()
+        return t.to(self.device, non_blocking=True).to(self.dtype).contiguous()
+
+    def download(self, t: torch.Tensor) -> np.ndarray:
+        """Device tensor -> float64 host array (the dtype the reference leaves in the AnnData objects)."""
+        out = t.to(torch.float64).cpu().numpy()
+        self.model.transfer_bytes["d2h"] += out.nbytes
+        return out
 
     def shard(self, per_sample) -> torch.Tensor | None:
         """Upload this rank's slice of a per-sample host vector (or None)."""
         if per_sample is None:
             return None
-        arr = np.ascontiguousarray(np.asarray(per_sample, dtype=np.float64)[self.lo : self.hi])
-        return torch.as_tensor(arr, dtype=self.dtype).to(self.device).contiguous()
+        return self.upload(np.asarray(per_sample, dtype=np.float64)[self.lo : self.hi])
+
+    def rows_to_host(self, local: torch.Tensor) -> np.ndarray:
+        """Per-sample device rows -> host array covering ``adata``'s rows (all-gather when the model sharded them)."""
+        if self.model.shard_input and self.world > 1:
+            local = _dist.gather_rows(local, self.D_total)
+        return self.download(local)
 
     def objective_value(self) -> float:
         """Sum the device scalar over ranks and bring it to the host (one sync)."""
@@ -76,9 +111,8 @@ class StandardNMF(SignatureNMF):
 
     def _to_host(self) -> None:
         st = self._dev
-        self.asignatures.X = st.W.to(torch.float64).cpu().numpy()
-        H_full = _dist.gather_rows(st.H, st.D_total)
-        self.adata.obsm["exposures"] = H_full.to(torch.float64).cpu().numpy()
+        self.asignatures.X = st.download(st.W)
+        self.adata.obsm["exposures"] = st.rows_to_host(st.H)
 
     def compute_reconstruction_errors(self) -> None:
         """Unweighted per-sample KL divergences -> ``adata.obs['reconstruction_error']``
@@ -86,8 +120,7 @@ class StandardNMF(SignatureNMF):
         with self._resident() as st:
             out = torch.empty(st.hi - st.lo, dtype=st.dtype, device=st.device)
             st.ws.klnmf_pass(st.X, st.W, st.H, PASS_SAMPLEWISE, per_sample=out)
-            full = _dist.gather_rows(out, st.D_total)
-            self.adata.obs["reconstruction_error"] = full.to(torch.float64).cpu().numpy()
+            self.adata.obs["reconstruction_error"] = np.array(st.rows_to_host(out))
 
     @staticmethod
     def _n_given(given_parameters) -> int:

@@ -1,0 +1,143 @@
+"""
+CPU-only checks of the host side: the C-ABI library loads and exports every symbol the header
+declares (no compute calls without a GPU), the product path refuses to run without CUDA, the
+threaded CPU port used as bench.py's reference arm equals the oracle, the synthetic workload
+does not depend on the rank count, and the sample-sharding helpers work under a 2-process gloo
+group (the N > 1 path of SURVEY.md 8(e)).
+"""
+
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+from conftest import ROOT
+
+from oracle import EPSILON, klnmf
+from oracle.klnmf_mt import HostKLNMF
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__ as entry
+
+    entry.build()
+    from salamander_b200 import _lib
+
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "salamander_b200.h")).read()
+    declared = set(re.findall(r"\b(sal_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations found in the header"
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.sal_version() >= 100
+
+
+def test_no_cpu_fallback():
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is visible")
+    import salamander_b200 as sal
+    from salamander_b200._lib import SalamanderB200Error
+
+    adata = sal.AnnData(np.random.default_rng(0).poisson(5.0, size=(12, 96)).astype(float))
+    with pytest.raises(SalamanderB200Error):
+        sal.models.KLNMF(n_signatures=2, init_method="random").fit(adata)
+    with pytest.raises(SalamanderB200Error):
+        sal.models.MvNMF(n_signatures=2, init_method="random").fit(adata)
+
+
+def test_package_does_not_import_oracle():
+    code = "import sys, salamander_b200, salamander_b200.models; assert not any(m.split('.')[0] == 'oracle' for m in sys.modules)"
+    subprocess.run([sys.executable, "-c", code], check=True, cwd=ROOT)
+
+
+def test_threaded_port_equals_oracle():
+    rng = np.random.default_rng(3)
+    V, D, k = 96, 5000, 7
+    W = rng.dirichlet(np.ones(V), size=k)  # [k][V]
+    H = rng.gamma(1.0, 100.0, size=(D, k))
+    X = rng.poisson(H @ W).astype(float).clip(EPSILON)
+    host = HostKLNMF(X, n_threads=3, chunk=777)
+    Wr, Hr = klnmf.update_WH(X.T, W.T, H.T)
+    kl_r = klnmf.kl_divergence(X.T, W.T, H.T)
+    assert np.isclose(host.kl_divergence(W, H), kl_r, rtol=1e-12)
+    Wn, Hn = host.update_WH(W, H.copy())
+    assert np.allclose(Wn, Wr.T, rtol=1e-11) and np.allclose(Hn, Hr.T, rtol=1e-11)
+    Wg, _ = host.update_WH(W, H.copy(), n_given_signatures=2)
+    assert np.allclose(Wg, klnmf.update_WH(X.T, W.T, H.T, None, None, 2)[0].T, rtol=1e-11)
+    host.close()
+
+
+def test_synthetic_workload_is_rank_independent():
+    import bench
+
+    full = bench.synth_rows(0, 130_000, 20)
+    assert full.dtype == np.float32 and full.min() >= np.float32(EPSILON)
+    lo, hi = bench.shard_bounds(130_000, 3, 1)
+    part = bench.synth_rows(lo, hi, 20)
+    assert np.array_equal(part, full[lo:hi])
+    W0, H0 = bench.init_rows(full, 0, 20)
+    W1, H1 = bench.init_rows(part, lo, 20)
+    assert np.array_equal(W0, W1) and np.array_equal(H1, H0[lo:hi])
+    assert np.allclose(W0.sum(axis=1), 1.0, atol=1e-4)
+    # column totals in the range of PCAWG breast SBS burdens
+    assert 2000 < np.median(full.sum(axis=1)) < 12000
+
+
+_GLOO_WORKER = r"""
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["SAL_ROOT"])
+from salamander_b200 import _dist
+dist.init_process_group("gloo")
+rank, world = _dist.world()
+assert world == 2
+n = 11
+lo, hi = _dist.shard_bounds(n, world, rank)
+full = torch.arange(n * 3, dtype=torch.float64).reshape(n, 3)
+got = _dist.gather_rows(full[lo:hi].clone(), n)
+assert torch.equal(got, full), (rank, got)
+t = torch.full((4,), float(rank + 1))
+_dist.allreduce_sum_(t)
+assert torch.equal(t, torch.full((4,), 3.0))
+arr = np.full((2, 2), float(rank))
+out = _dist.broadcast_numpy(arr, torch.device("cpu"))
+assert np.array_equal(out, np.zeros((2, 2)))
+# sample-sharded W numerator: the sum of the shards' partial numerators equals the unsharded one
+rng = np.random.default_rng(0)
+X = rng.poisson(20.0, size=(n, 5)).astype(float) + 1e-3
+W = rng.dirichlet(np.ones(5), size=2); H = rng.gamma(2.0, 5.0, size=(n, 2))
+num = torch.from_numpy(H[lo:hi].T @ (X[lo:hi] / (H[lo:hi] @ W)))
+_dist.allreduce_sum_(num)
+assert np.allclose(num.numpy(), H.T @ (X / (H @ W)), rtol=1e-12)
+dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_sharding_helpers_gloo_world2(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER)
+    env = dict(os.environ, SAL_ROOT=ROOT, MASTER_ADDR="127.0.0.1")
+    cmd = [
+        sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+        "--master-addr", "127.0.0.1", "--master-port", "29731", str(script),
+    ]
+    res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=240)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert res.stdout.count("ok") == 2
+
+
+def test_shard_bounds_cover_everything():
+    from salamander_b200._dist import shard_bounds
+
+    for n in (0, 1, 7, 8, 1_000_000):
+        for world in (1, 2, 3, 8):
+            edges = [shard_bounds(n, world, r) for r in range(world)]
+            assert edges[0][0] == 0 and edges[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(edges, edges[1:]))
+            sizes = [hi - lo for lo, hi in edges]
+            assert max(sizes) - min(sizes) <= 1
