@@ -36,7 +36,9 @@ enum { SAL_F32 = 0, SAL_F64 = 1 };
 /* arithmetic used for the three thin contractions of the fused pass (fp32 handles only) */
 enum {
     SAL_MATH_FMA = 0,  /* CUDA-core FMA in the handle's dtype (exact fp32 / fp64)          */
-    SAL_MATH_TF32 = 1  /* tcgen05 kind::tf32 tensor-core contractions, fp32 accumulation   */
+    SAL_MATH_TF32 = 1  /* tcgen05 kind::tf32 tensor-core contractions, fp32 accumulation:
+                          used by sal_klnmf_pass when V == 96, k % 4 == 0, no weights / h_scale and flags within
+                          UPDATE_H | WNUM | OBJECTIVE; every other call runs the exact FMA kernels (still on the GPU) */
 };
 
 enum {
@@ -62,6 +64,9 @@ int sal_version(void);
 int sal_create(sal_handle_t* out, int V, int64_t D_local, int k, int dtype, int device);
 int sal_destroy(sal_handle_t h);
 int sal_set_math(sal_handle_t h, int math_mode);
+/* Diagnostics of the tensor-core pass: when buf != NULL (device, >= 128*96 + 128*32 floats) CTA 0 dumps the
+ * quotient tile R[128][96] and Hn[128][32] of its first tile.  Pass NULL to switch off. */
+int sal_set_debug_buffer(sal_handle_t h, void* buf);
 /* number of kernels this handle has launched since creation (bench.py "gpu_launches") */
 int64_t sal_launch_count(sal_handle_t h);
 

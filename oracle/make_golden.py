@@ -110,6 +110,9 @@ def main():
         max_iterations=300,
     )
     klnmf_case("klnmf_pcawg_k6_given2", 6, 2, n_given=2, min_iterations=400, max_iterations=400)
+    # k % 4 == 0, unweighted: the shapes the tcgen05 (tf32) flavour of the pass covers
+    klnmf_case("klnmf_pcawg_k8_seed5", 8, 5)
+    klnmf_case("klnmf_pcawg_k4_seed6", 4, 6, min_iterations=1000, max_iterations=1000)
     # C2: MvNMF k=10 on the same data, lam = delta = 1
     mvnmf_case("mvnmf_pcawg_k10_seed0", 10, 0, min_iterations=600, max_iterations=600)
     mvnmf_case("mvnmf_pcawg_k3_lam50", 3, 3, lam=50.0, delta=0.5, min_iterations=300, max_iterations=300)

@@ -71,6 +71,12 @@ class Workspace:
         _lib.check(self.lib.sal_set_math(self._h, mode), "sal_set_math")
         self.math = math
 
+    def set_debug_buffer(self, buf) -> None:
+        """Diagnostics of the tensor-core pass (sal_set_debug_buffer); ``None`` switches them off."""
+        ptr = None if buf is None else C.c_void_p(buf.data_ptr())
+        _lib.check(self.lib.sal_set_debug_buffer(self._h, ptr), "sal_set_debug_buffer")
+        self._dbg = buf  # keep the tensor alive while the library holds its address
+
     def close(self) -> None:
         if self._h:
             self.lib.sal_destroy(self._h)

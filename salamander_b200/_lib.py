@@ -28,6 +28,7 @@ SYMBOLS = {
     "sal_destroy": (_i, [_vp]),
     "sal_set_math": (_i, [_vp, _i]),
     "sal_launch_count": (_i64, [_vp]),
+    "sal_set_debug_buffer": (_i, [_vp, _vp]),
     "sal_klnmf_pass": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "sal_w_epilogue": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),
     "sal_clip_counts": (_i, [_vp, _vp, _i64, _vp, _vp]),

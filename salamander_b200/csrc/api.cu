@@ -59,7 +59,6 @@ int sal_destroy(sal_handle_t h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
     cudaFree(h->partial_wnum), cudaFree(h->partial_obj), cudaFree(h->partial_hsum);
-    if (h->tc_ws) cudaFree(h->tc_ws);
     delete h;
     return 0;
 }
@@ -76,6 +75,12 @@ int sal_set_math(sal_handle_t h, int math_mode) {
 }
 
 int64_t sal_launch_count(sal_handle_t h) { return h ? h->launches : -1; }
+
+int sal_set_debug_buffer(sal_handle_t h, void* buf) {
+    SAL_CHECK_ARG(h != nullptr, "handle is null");
+    h->dbg = buf;
+    return 0;
+}
 
 int sal_klnmf_pass(sal_handle_t h, const void* X, const void* W, const void* H_in, void* H_out,
                    const void* w_kl, const void* w_lhalf, const void* h_scale, int flags, void* Wnum,
@@ -103,7 +108,7 @@ int sal_klnmf_pass(sal_handle_t h, const void* X, const void* W, const void* H_i
     a.X = X, a.W = W, a.H_in = H_in, a.w_kl = w_kl, a.w_lhalf = w_lhalf, a.h_scale = h_scale;
     a.H_out = H_out, a.Wnum = Wnum, a.per_sample = per_sample, a.hsum = hsum, a.objective = objective;
     a.flags = flags;
-    if (h->math == SAL_MATH_TF32) return sal_launch_pass_tf32(h, a, st);
+    if (h->math == SAL_MATH_TF32 && sal_pass_tf32_supported(h, a)) return sal_launch_pass_tf32(h, a, st);
     return sal_launch_pass_fma(h, a, st);
 }
 

@@ -392,14 +392,7 @@ int launch_pass_t(sal_ctx* c, const PassArgs& a, cudaStream_t st) {
     klnmf_pass_kernel<T, KP><<<grid, NT, smem, st>>>(p);
     SAL_CUDA(cudaGetLastError());
     c->launches++;
-    if (a.flags & (SAL_PASS_WNUM | SAL_PASS_OBJECTIVE | SAL_PASS_POISSON | SAL_PASS_HSUM)) {
-        const int n_w = (a.flags & SAL_PASS_WNUM) ? c->k * c->V : 0;
-        const int rb = (n_w + 127) / 128 + 1;
-        klnmf_reduce_kernel<T><<<rb, 128, 0, st>>>((const T*)c->partial_wnum, c->partial_obj, c->partial_hsum, grid,
-                                                  KP, c->k, c->V, a.flags, (T*)a.Wnum, a.objective, (T*)a.hsum);
-        SAL_CUDA(cudaGetLastError());
-        c->launches++;
-    }
+    if (int e = sal_launch_pass_reduce(c, a, grid, st)) return e;
     return 0;
 }
 
@@ -414,6 +407,23 @@ int launch_pass_k(sal_ctx* c, const PassArgs& a, cudaStream_t st) {
 }
 
 }  // namespace
+
+// Fixed-order sum of the per-CTA partials left by either flavour of the pass (n_part = its grid size).
+int sal_launch_pass_reduce(sal_ctx* c, const PassArgs& a, int n_part, cudaStream_t st) {
+    if (!(a.flags & (SAL_PASS_WNUM | SAL_PASS_OBJECTIVE | SAL_PASS_POISSON | SAL_PASS_HSUM))) return 0;
+    const int n_w = (a.flags & SAL_PASS_WNUM) ? c->k * c->V : 0;
+    const int rb = (n_w + 127) / 128 + 1;
+    if (c->dtype == SAL_F32)
+        klnmf_reduce_kernel<float><<<rb, 128, 0, st>>>((const float*)c->partial_wnum, c->partial_obj, c->partial_hsum, n_part,
+                                                      c->KP, c->k, c->V, a.flags, (float*)a.Wnum, a.objective, (float*)a.hsum);
+    else
+        klnmf_reduce_kernel<double><<<rb, 128, 0, st>>>((const double*)c->partial_wnum, c->partial_obj, c->partial_hsum,
+                                                       n_part, c->KP, c->k, c->V, a.flags, (double*)a.Wnum, a.objective,
+                                                       (double*)a.hsum);
+    SAL_CUDA(cudaGetLastError());
+    c->launches++;
+    return 0;
+}
 
 int sal_launch_pass_fma(sal_ctx* c, const PassArgs& a, cudaStream_t st) {
     return c->dtype == SAL_F32 ? launch_pass_k<float>(c, a, st) : launch_pass_k<double>(c, a, st);

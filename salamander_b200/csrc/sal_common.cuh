@@ -19,7 +19,7 @@ struct sal_ctx {
     void* partial_wnum;    // [grid_pass][KP][SAL_VMAX] real
     double* partial_obj;   // [grid_pass]
     double* partial_hsum;  // [grid_pass][SAL_KMAX]
-    void* tc_ws;           // tensor-core path workspace (may be null)
+    void* dbg;             // optional diagnostics buffer of the tensor-core pass (sal_set_debug_buffer)
     int64_t launches;
 };
 
@@ -53,6 +53,8 @@ struct PassArgs {
 };
 int sal_launch_pass_fma(sal_ctx* c, const PassArgs& a, cudaStream_t st);
 int sal_launch_pass_tf32(sal_ctx* c, const PassArgs& a, cudaStream_t st);  // tcgen05 path (fp32 only)
+bool sal_pass_tf32_supported(const sal_ctx* c, const PassArgs& a);         // shapes / flags the tcgen05 path covers
+int sal_launch_pass_reduce(sal_ctx* c, const PassArgs& a, int n_part, cudaStream_t st);
 int sal_pass_smem_bytes(int dtype, int KP);
 int sal_launch_w_epilogue(sal_ctx* c, const void* W_in, const void* Wnum, int n_given, int clip_given,
                           void* W_out, cudaStream_t st);

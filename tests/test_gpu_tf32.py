@@ -1,0 +1,144 @@
+"""
+GPU parity of the tensor-core (tcgen05 kind::tf32) flavour of the fused pass, through the C ABI.
+
+tf32 operands carry 11 significant bits (round to nearest), accumulation is fp32: single updates are
+compared with a float64 torch restatement of the same formulas at rtol 4e-3; whole fits are held to
+the north-star fp32 criteria (final KL within 1e-4 relative, signature cosine >= 0.9999) against
+trajectories of the LIVE reference (tests/golden/trajectories).  The first test reads the kernel's
+diagnostic dump so a wrong descriptor shows up as "which GEMM is wrong" instead of a bad number.
+"""
+
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+import torch
+from conftest import GOLDEN, ROOT
+
+import salamander_b200 as sal
+from salamander_b200 import AnnData
+from salamander_b200._device import PASS_OBJECTIVE, PASS_UPDATE_H, PASS_WNUM, Workspace
+
+pytestmark = pytest.mark.gpu
+EPS = float(np.finfo(np.float32).eps)
+RTOL = 4e-3
+
+
+def _problem(D, k, seed, dev):
+    gen = torch.Generator(device=dev).manual_seed(seed)
+    W = torch.rand((k, 96), generator=gen, device=dev, dtype=torch.float64) + 0.01
+    W /= W.sum(1, keepdim=True)
+    H = torch.rand((D, k), generator=gen, device=dev, dtype=torch.float64) * 400 + 1.0
+    X = torch.poisson(H @ W, generator=gen).clamp_min(EPS)
+    return X, W, H
+
+
+def _run(X, W, H, flags, debug=False):
+    dev = X.device
+    D, k = H.shape
+    ws = Workspace(96, D, k, torch.float32, dev, math="tf32")
+    Xf, Wf, Hf = X.float().contiguous(), W.float().contiguous(), H.float().contiguous()
+    Hout = torch.full_like(Hf, -1.0)
+    Wnum = torch.full_like(Wf, -1.0)
+    obj = torch.zeros(1, dtype=torch.float64, device=dev)
+    dbg = None
+    if debug:
+        dbg = torch.zeros(128 * 96 + 128 * 32, dtype=torch.float32, device=dev)
+        ws.set_debug_buffer(dbg)
+    ws.klnmf_pass(Xf, Wf, Hf, flags, H_out=Hout, Wnum=Wnum, objective=obj)
+    torch.cuda.synchronize()
+    ws.set_debug_buffer(None)
+    ws.close()
+    return Hout.double(), Wnum.double(), float(obj.item()), dbg
+
+
+def _relerr(a, b):
+    return float(((a - b).abs() / b.abs().clamp_min(1e-30)).max())
+
+
+def test_stage_by_stage_first_tile():
+    dev = torch.device("cuda:0")
+    X, W, H = _problem(300, 20, 1, dev)
+    Hout, Wnum, _, dbg = _run(X, W, H, PASS_UPDATE_H | PASS_WNUM, debug=True)
+    R_ref = X / (H @ W)
+    R = dbg[: 128 * 96].reshape(128, 96).double()
+    Hn = dbg[128 * 96 :].reshape(128, 32).double()[:, :20]
+    e_r = _relerr(R, R_ref[:128])
+    e_hn = _relerr(Hn, R_ref[:128] @ W.T)
+    e_h = _relerr(Hout, (H * (R_ref @ W.T)).clamp_min(EPS))
+    e_w = _relerr(Wnum, H.T @ R_ref)
+    print(f"tf32 stage errors: R {e_r:.2e} (G1 + divide)  Hn {e_hn:.2e} (G2)  H_out {e_h:.2e}  Wnum {e_w:.2e} (G3)")
+    assert e_r < RTOL, f"G1 / quotient wrong: {e_r}"
+    assert e_hn < RTOL, f"G2 wrong: {e_hn}"
+    assert e_h < RTOL, f"H update wrong: {e_h}"
+    assert e_w < RTOL, f"G3 / numerator wrong: {e_w}"
+
+
+@pytest.mark.parametrize("D,k", [(1, 4), (127, 8), (128, 12), (129, 16), (1000, 20), (4097, 24), (777, 28), (50_000, 32), (200_003, 20)])
+def test_pass_matches_float64(D, k):
+    dev = torch.device("cuda:0")
+    X, W, H = _problem(D, k, 100 + k, dev)
+    R = X / (H @ W)
+    kl_ref = float((X * torch.log(R) - X + H @ W).sum())
+    Hout, Wnum, obj, _ = _run(X, W, H, PASS_UPDATE_H | PASS_WNUM | PASS_OBJECTIVE)
+    assert _relerr(Hout, (H * (R @ W.T)).clamp_min(EPS)) < RTOL
+    assert _relerr(Wnum, H.T @ R) < RTOL
+    assert abs(obj - kl_ref) / abs(kl_ref) < RTOL
+    # each flag alone
+    Hout2, _, _, _ = _run(X, W, H, PASS_UPDATE_H)
+    assert torch.equal(Hout2, Hout)
+    _, Wnum2, _, _ = _run(X, W, H, PASS_WNUM)
+    assert torch.equal(Wnum2, Wnum)
+    # objective-only passes use the error-compensated 3 x tf32 product: fp32-grade accuracy for the convergence test
+    _, _, obj2, _ = _run(X, W, H, PASS_OBJECTIVE)
+    assert abs(obj2 - kl_ref) / abs(kl_ref) < 2e-6
+
+
+def test_deterministic_and_in_place():
+    dev = torch.device("cuda:0")
+    X, W, H = _problem(70_001, 20, 7, dev)
+    a = _run(X, W, H, PASS_UPDATE_H | PASS_WNUM)
+    b = _run(X, W, H, PASS_UPDATE_H | PASS_WNUM)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    # H_out aliasing H_in (how the models call it)
+    ws = Workspace(96, 70_001, 20, torch.float32, dev, math="tf32")
+    Hf = H.float().contiguous()
+    Wnum = torch.empty((20, 96), dtype=torch.float32, device=dev)
+    ws.klnmf_pass(X.float().contiguous(), W.float().contiguous(), Hf, PASS_UPDATE_H | PASS_WNUM, H_out=Hf, Wnum=Wnum)
+    torch.cuda.synchronize()
+    assert torch.equal(Hf.double(), a[0]) and torch.equal(Wnum.double(), a[1])
+    ws.close()
+
+
+def test_unsupported_shapes_use_the_exact_kernels():
+    """k % 4 != 0, V != 96 or weights: the call still succeeds (exact FMA kernels) -- never a CPU fallback."""
+    dev = torch.device("cuda:0")
+    X, W, H = _problem(500, 5, 3, dev)
+    Hout, Wnum, _, _ = _run(X, W, H, PASS_UPDATE_H | PASS_WNUM)
+    R = X / (H @ W)
+    assert _relerr(Hout, (H * (R @ W.T)).clamp_min(EPS)) < 3e-5
+    assert _relerr(Wnum, H.T @ R) < 3e-5
+
+
+def _pcawg():
+    counts = pd.read_csv(os.path.join(ROOT, "salamander_b200", "data", "pcawg_breast_sbs.csv"), index_col=0)
+    return AnnData(counts.T)
+
+
+@pytest.mark.parametrize("tag", ["klnmf_pcawg_k8_seed5", "klnmf_pcawg_k4_seed6"])
+def test_fit_meets_fp32_criteria(tag):
+    z = np.load(os.path.join(GOLDEN, "trajectories", f"{tag}.npz"))
+    kw = {}
+    for name in ("min_iterations", "max_iterations"):
+        if f"ctor_{name}" in z.files:
+            kw[name] = int(z[f"ctor_{name}"])
+    model = sal.models.KLNMF(n_signatures=int(z["k"]), init_method="random", dtype="float32", math="tf32", **kw)
+    model.fit(_pcawg(), init_kwargs={"seed": int(z["seed"])})
+    hist, ref = np.array(model.history["objective_function"]), z["history"]
+    A, B = model.asignatures.X, z["W"]
+    cos = np.sum(A * B, axis=1) / (np.linalg.norm(A, axis=1) * np.linalg.norm(B, axis=1))
+    print(f"{tag}: final KL {hist[-1]:.6f} vs reference {ref[-1]:.6f} (rel {abs(hist[-1] - ref[-1]) / ref[-1]:.2e}), "
+          f"{len(hist)} vs {len(ref)} checkpoints, min cosine {cos.min():.7f}")
+    assert abs(hist[-1] - ref[-1]) / abs(ref[-1]) < 1e-4
+    assert cos.min() >= 0.9999
