@@ -64,8 +64,9 @@ int sal_version(void);
 int sal_create(sal_handle_t* out, int V, int64_t D_local, int k, int dtype, int device);
 int sal_destroy(sal_handle_t h);
 int sal_set_math(sal_handle_t h, int math_mode);
-/* Diagnostics of the tensor-core pass: when buf != NULL (device, >= 128*96 + 128*32 floats) CTA 0 dumps the
- * quotient tile R[128][96] and Hn[128][32] of its first tile.  Pass NULL to switch off. */
+/* Diagnostics of the tensor-core pass: when buf != NULL (device, >= 32768 floats) CTA 0 dumps the quotient tile
+ * R[128][96] and Hn[128][32] of its first tile, then a clock64 timeline [role 4][tile 48][phase 8] (uint32) of
+ * its warp roles.  Pass NULL to switch off. */
 int sal_set_debug_buffer(sal_handle_t h, void* buf);
 /* number of kernels this handle has launched since creation (bench.py "gpu_launches") */
 int64_t sal_launch_count(sal_handle_t h);

@@ -5,11 +5,17 @@
 // per-sample weights.  The three thin contractions of one 128-sample tile run on the 5th-gen tensor
 // cores; X is streamed from HBM exactly once by TMA and the quotient never leaves the SM:
 //
-//   G1  WH[s,f]   = sum_j H[s,j] W[j,f]        A = sH  (smem, K-major)      B = sW1 (smem, K-major)
+//   G1  WH[s,f]   = sum_j H[s,j] W[j,f]        A = H   (TMEM, "TS" form)    B = sW1 (smem, K-major)
 //   E1  R[s,f]    = X[s,f] / WH[s,f]           thread s = TMEM lane s; R overwrites X in smem AND WH in TMEM
 //   G2  Hn[s,j]   = sum_f R[s,f] W[j,f]        A = R   (TMEM, "TS" form)    B = sW2 (smem, K-major)
 //   G3  Wn[f,j]  += sum_s R[s,f] H[s,j]        A = R   (smem, MN-major)     B = sHT (smem, K-major)
 //   E2  H_out[s,j] = max(H[s,j] Hn[s,j], eps)
+//
+// tf32 recipe (scripts/tf32_precision_experiment.py): WH feeds a division and decides whether the
+// fit's 1e-7 convergence test sees noise, so G1 is error compensated -- h = hi + lo, w = hi + lo,
+// WH = hi*hi + lo*hi + hi*lo (3 x tf32, ~2^-22).  In G2 the signatures, whose rounding error would be the same
+// for every sample and every iteration, are split too (R*Whi + R*Wlo); R itself and G3 use plain tf32, their
+// rounding noise averages out over the 96 features / all samples.
 //
 // Wn (96 x k) accumulates in TMEM over all tiles of the CTA and is written once as a per-CTA partial;
 // the deterministic fixed-order reduction kernel of klnmf_pass.cu finishes the job.
@@ -18,7 +24,7 @@
 //   X / R stage : 3 TMA boxes [128 samples][32 features] fp32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.  The very same
 //                 bytes are the MN-major SWIZZLE_128B_BASE32B A operand of G3 (M = feature, K = sample) -- the only
 //                 MN-major layout tcgen05 accepts for 32-bit operands -- so R is written in place over X.
-//   sH, sW1, sW2, sHT : canonical no-swizzle K-major "core matrices" (8 rows x 16 B, 128 B contiguous),
+//   sW1, sW2, sHT : canonical no-swizzle K-major "core matrices" (8 rows x 16 B, 128 B contiguous),
 //                 written by the threads with round-to-nearest tf32 conversion.
 //
 // Warp roles (384 threads, 1 CTA / SM, persistent over tiles):  warp 0 TMA producer, warp 1 MMA issuer,
@@ -36,38 +42,46 @@ constexpr int BOX_BYTES = TILE * 128;           // 16 KB
 constexpr int XSTAGE_BYTES = NBOX * BOX_BYTES;  // 48 KB
 constexpr int NTHREADS = 384;
 constexpr int N2 = 32;                          // UMMA N of G2 / G3 (k zero-padded to 32)
+constexpr int SMEM_LIMIT = 232448;              // 227 KB opt-in limit per CTA
 
-// TMEM columns (512 allocated): two WH/R buffers, two Hn buffers, the persistent numerator
-constexpr uint32_t TM_WH0 = 0, TM_WH1 = 96, TM_HN0 = 192, TM_HN1 = 224, TM_WN = 256, TM_COLS = 512;
+// TMEM columns (512 allocated): WH / R x2, Hn x2, the persistent numerator, H operand (hi, lo) x2
+constexpr uint32_t TM_WH0 = 0, TM_WH1 = 96, TM_HN0 = 192, TM_HN1 = 224, TM_WN = 256;
+constexpr uint32_t TM_H0 = 288, TM_H1 = 352, TM_HLO = 32, TM_COLS = 512;
 
 // strides of the thread-written operands (bytes)
-constexpr int SH_LBO = 2048, SH_SBO = 128;    // sH  [kc][sample/8][8][16B]   A of G1 (M = sample, K = signature)
 constexpr int SW1_LBO = 1536, SW1_SBO = 128;  // sW1 [kc][feature/8][8][16B]  B of G1 (N = feature, K = signature)
-constexpr int SW2_SBO = 128;                  // sW2 [fc][sig/8][8][16B]      B of G2 (N = signature, K = feature); LBO = Lay::SW2_LBO
+constexpr int SW2_SBO = 128;                  // sW2 [fc][sig/8][8][16B]      B of G2 (N = signature, K = feature)
 constexpr int SHT_LBO = 528, SHT_SBO = 128;   // sHT [sc][sig/8][8][16B](+16) B of G3 (N = signature, K = sample)
+constexpr int SHT_BYTES = 32 * SHT_LBO;
 
-template <int KP8>
-struct Lay {
-    static constexpr int S = KP8 <= 24 ? 3 : 2;  // X / H stages
-    static constexpr int HRAW = TILE * KP8 * 4;  // raw H tile as TMA delivers it ([128][k] dense rows)
-    // only ceil(k/8) signature groups of sW2 are stored; G2 runs with N = 32 and the groups beyond them read the
-    // following bytes (finite garbage that only reaches output columns >= k, which nobody reads)
-    static constexpr int SW2_LBO = (KP8 / 8) * 128;
-    static constexpr int OFF_X = 0;
-    static constexpr int OFF_HRAW = OFF_X + S * XSTAGE_BYTES;
-    static constexpr int OFF_SW1 = OFF_HRAW + S * HRAW;
-    static constexpr int OFF_SW2 = OFF_SW1 + (KP8 / 4) * SW1_LBO;
-    static constexpr int OFF_SH = OFF_SW2 + 24 * SW2_LBO;
-    static constexpr int OFF_SHT = OFF_SH + (KP8 / 4) * SH_LBO;
-    static constexpr int OFF_BAR = OFF_SHT + 32 * SHT_LBO;
-    static constexpr int N_BAR = 2 * S + 9;
-    static constexpr int OFF_MISC = OFF_BAR + N_BAR * 8;
-    static constexpr int TOTAL = OFF_MISC + 128;
-    static constexpr int DYN_BYTES = TOTAL;
-    // the G3 A operand spans 4 boxes (M = 128 features, 96 real): the bytes after the last stage must exist
-    static_assert(S * HRAW + (KP8 / 4) * SW1_LBO + 24 * SW2_LBO + (KP8 / 4) * SH_LBO >= BOX_BYTES, "need 16 KB after the last X stage");
-    static_assert(DYN_BYTES <= 232448, "shared memory budget");
+// Shared-memory plan for k signatures (KP8 = k rounded up to 8).  Only ceil(k/8) signature groups of sW2 are
+// stored: G2 runs with N = 32 and the groups beyond them read the following bytes, finite garbage that only
+// reaches output columns >= k which nobody reads.  The same holds for the 4th (non-existent) feature box of
+// the G3 A operand: it reads the bytes after the stage, so at least 16 KB must follow the last stage.
+struct Plan {
+    int S;  // X / H stages
+    int hraw, sw1, sw2, sw2_lbo;
+    int off_hraw, off_w1hi, off_w1lo, off_w2hi, off_w2lo, off_sht, off_bar, off_misc, total;
 };
+__host__ __device__ inline Plan make_plan(int k, int KP8) {
+    Plan q;
+    q.hraw = (TILE * k * 4 + 127) & ~127;
+    q.sw1 = (KP8 / 4) * SW1_LBO;
+    q.sw2_lbo = (KP8 / 8) * 128;
+    q.sw2 = 24 * q.sw2_lbo;
+    const int fixed = 2 * q.sw1 + 2 * q.sw2 + SHT_BYTES + 24 * 8 + 128;
+    q.S = (3 * (XSTAGE_BYTES + q.hraw) + fixed <= SMEM_LIMIT) ? 3 : 2;
+    q.off_hraw = q.S * XSTAGE_BYTES;
+    q.off_w1hi = q.off_hraw + q.S * q.hraw;
+    q.off_w1lo = q.off_w1hi + q.sw1;
+    q.off_w2hi = q.off_w1lo + q.sw1;
+    q.off_w2lo = q.off_w2hi + q.sw2;
+    q.off_sht = q.off_w2lo + q.sw2;
+    q.off_bar = q.off_sht + SHT_BYTES;
+    q.off_misc = q.off_bar + 24 * 8;
+    q.total = q.off_misc + 128;
+    return q;
+}
 
 struct TcParams {
     const float* W;
@@ -119,6 +133,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         : "memory");
 }
 
+// one lane of a converged warp (the address arithmetic around it stays warp-uniform, i.e. in uniform registers)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred)::"memory");
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
@@ -192,11 +212,17 @@ __device__ __forceinline__ float rcp_approx(float x) {
 // the same banks in one wavefront).
 template <bool DO_R, bool DO_KL>
 __device__ __forceinline__ void quotient_box(uint32_t (&v)[32], uint32_t rowbase, int s, uint32_t sw, float& kl) {
+    // the loads of chunk m + 1 are issued before chunk m is divided and stored (LDS latency off the critical path)
+    float4 va = lds128(rowbase + ((uint32_t)(0 ^ (s & 3)) << 5) + sw * 16);
+    float4 vb = lds128(rowbase + ((uint32_t)(0 ^ (s & 3)) << 5) + (sw ^ 1) * 16);
 #pragma unroll
     for (int m = 0; m < 4; ++m) {
         const uint32_t a32 = rowbase + ((uint32_t)(m ^ (s & 3)) << 5);
-        const float4 va = lds128(a32 + sw * 16), vb = lds128(a32 + (sw ^ 1) * 16);
         const float4 xlo = sw ? vb : va, xhi = sw ? va : vb;
+        if (m < 3) {
+            const uint32_t n32 = rowbase + ((uint32_t)((m + 1) ^ (s & 3)) << 5);
+            va = lds128(n32 + sw * 16), vb = lds128(n32 + (sw ^ 1) * 16);
+        }
         const float xv[8] = {xlo.x, xlo.y, xlo.z, xlo.w, xhi.x, xhi.y, xhi.z, xhi.w};
         float rr[8];
 #pragma unroll
@@ -230,29 +256,37 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn, int b_
            ((uint32_t)(M >> 4) << 24);
 }
 
+// Diagnostics timeline (only when a debug buffer is set): CTA 0 stamps clock64 per role / tile / phase.
+constexpr int DBG_TL_OFF = TILE * VT + TILE * 32, DBG_TL_TILES = 48, DBG_TL_SLOTS = 8;
+__device__ __forceinline__ void stamp(float* dbg, bool on, int role, int tile, int slot) {
+    if (on && tile < DBG_TL_TILES)
+        reinterpret_cast<unsigned int*>(dbg)[DBG_TL_OFF + (role * DBG_TL_TILES + tile) * DBG_TL_SLOTS + slot] = (unsigned int)clock64();
+}
+
+// tcgen05.st of 8 consecutive columns
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%8], {%0, %1, %2, %3, %4, %5, %6, %7};" ::SAL_W8(v, 0), "r"(taddr) : "memory");
+}
+
 template <int KP8, bool DO_R, bool DO_KL>
 __global__ void __launch_bounds__(NTHREADS, 1)
 klnmf_pass_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapH, TcParams p) {
-    using L = Lay<KP8>;
-    constexpr int S = L::S;
     extern __shared__ __align__(1024) unsigned char smem_dyn[];
     const uint32_t base = smem_u32(smem_dyn);
-    unsigned char* gbase = smem_dyn;
     if (base & 1023u) __trap();  // the swizzled TMA boxes need 1024-byte alignment
-    const uint32_t sX = base + L::OFF_X, sHraw = base + L::OFF_HRAW, sW1 = base + L::OFF_SW1, sW2 = base + L::OFF_SW2;
-    const uint32_t sH = base + L::OFF_SH, sHT = base + L::OFF_SHT, bars = base + L::OFF_BAR;
-    // barriers
-    const uint32_t bar_full = bars, bar_empty = bars + 8 * S, bar_hready = bars + 16 * S;
-    const uint32_t bar_whfull = bar_hready + 8, bar_rready = bar_whfull + 16, bar_hnfull = bar_rready + 16;
-    const uint32_t bar_shtfree = bar_hnfull + 16, bar_done = bar_shtfree + 8;
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + L::OFF_MISC);
-    double* s_red = reinterpret_cast<double*>(gbase + L::OFF_MISC + 16);  // [8]
+    const int k = p.k;
+    const Plan q = make_plan(k, KP8);
+    const int S = q.S;
+    const uint32_t sX = base, sHraw = base + q.off_hraw, sW1hi = base + q.off_w1hi, sW1lo = base + q.off_w1lo;
+    const uint32_t sW2hi = base + q.off_w2hi, sW2lo = base + q.off_w2lo, sHT = base + q.off_sht, bars = base + q.off_bar;
+    // barriers: full[3] empty[3] hready[2] whfull[2] rready[2] hnfull[2] shtfree done
+    const uint32_t bar_full = bars, bar_empty = bars + 24, bar_hready = bars + 48, bar_whfull = bars + 64;
+    const uint32_t bar_rready = bars + 80, bar_hnfull = bars + 96, bar_shtfree = bars + 112, bar_done = bars + 120;
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_dyn + q.off_misc);
+    double* s_red = reinterpret_cast<double*>(smem_dyn + q.off_misc + 16);  // [8]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int k = p.k;
     const bool do_h = p.flags & SAL_PASS_UPDATE_H, do_w = p.flags & SAL_PASS_WNUM;
-    constexpr bool do_r = DO_R;  // quotient needed by G2 / G3 (UPDATE_H or WNUM requested)
-    constexpr bool do_kl = DO_KL;
     const int n_my = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // tiles of this CTA (>= 1)
 
     // ---- one-time setup --------------------------------------------------------------------------
@@ -261,9 +295,9 @@ klnmf_pass_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapH) : "memory");
     }
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < S; ++i) mbar_init(bar_full + 8 * i, 1), mbar_init(bar_empty + 8 * i, 1);
-        mbar_init(bar_hready, 128);
+        for (int i = 0; i < 3; ++i) mbar_init(bar_full + 8 * i, 1), mbar_init(bar_empty + 8 * i, 1);
         for (int i = 0; i < 2; ++i) {
+            mbar_init(bar_hready + 8 * i, 128);
             mbar_init(bar_whfull + 8 * i, 1);
             mbar_init(bar_rready + 8 * i, 128);
             mbar_init(bar_hnfull + 8 * i, 1);
@@ -278,27 +312,20 @@ klnmf_pass_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    // W operands (tf32, round to nearest), zero padding for signatures >= k; sHT zero fill
+    // W operands as tf32 hi + lo (round to nearest), zero padding for signatures >= k; sHT zero fill
     for (int i = tid; i < KP8 * VT; i += NTHREADS) {
         const int j = i / VT, f = i - j * VT;
-        const float w = j < k ? tf32_rn(p.W[(size_t)j * VT + f]) : 0.f;
-        sts32(sW1 + (j >> 2) * SW1_LBO + (f >> 3) * SW1_SBO + (f & 7) * 16 + (j & 3) * 4, w);
+        const float w = j < k ? p.W[(size_t)j * VT + f] : 0.f;
+        const float hi = tf32_rn(w), lo = tf32_rn(w - hi);
+        const uint32_t o1 = (j >> 2) * SW1_LBO + (f >> 3) * SW1_SBO + (f & 7) * 16 + (j & 3) * 4;
+        sts32(sW1hi + o1, hi), sts32(sW1lo + o1, lo);
+        if (DO_R) {
+            const uint32_t o2 = (f >> 2) * q.sw2_lbo + (j >> 3) * SW2_SBO + (j & 7) * 16 + (f & 3) * 4;
+            sts32(sW2hi + o2, hi), sts32(sW2lo + o2, lo);
+        }
     }
-    // Objective-only passes feed the convergence test (reference signature_nmf.py:373-378, tol 1e-7), so their WH is
-    // formed with the error-compensated split  w = hi + lo, h = hi + lo,  WH ~ hi*hi + lo*hi + hi*lo  (3 x tf32, ~2^-22):
-    // the lo parts live where sW2 / sHT would be (unused without G2 / G3).
-    constexpr bool split = !DO_R;
-    const uint32_t sW1lo = sW2, sHlo = sHT;
-    for (int i = tid; i < KP8 * VT; i += NTHREADS) {
-        const int j = i / VT, f = i - j * VT;
-        const float wf = j < k ? p.W[(size_t)j * VT + f] : 0.f;
-        if (split)
-            sts32(sW1lo + (j >> 2) * SW1_LBO + (f >> 3) * SW1_SBO + (f & 7) * 16 + (j & 3) * 4, tf32_rn(wf - tf32_rn(wf)));
-        else
-            sts32(sW2 + (f >> 2) * L::SW2_LBO + (j >> 3) * SW2_SBO + (j & 7) * 16 + (f & 3) * 4, tf32_rn(wf));
-    }
-    if (!split)
-        for (int i = tid; i < 32 * SHT_LBO / 4; i += NTHREADS) sts32(sHT + 4 * i, 0.f);
+    if (DO_R)
+        for (int i = tid; i < SHT_BYTES / 4; i += NTHREADS) sts32(sHT + 4 * i, 0.f);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -306,6 +333,7 @@ klnmf_pass_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
     const uint32_t tmem = *tmem_slot;
 
     double obj_acc = 0.0;
+    const bool tl = p.dbg != nullptr && blockIdx.x == 0;  // diagnostics timeline
 
     if (warp == 0) {
         // ================= TMA producer =================
@@ -315,104 +343,125 @@ klnmf_pass_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
                 const int st = i % S;
                 const int d0 = ((int)blockIdx.x + i * (int)gridDim.x) * TILE;
                 mbar_wait(bar_empty + 8 * st, ((i / S) & 1) ^ 1);
+                stamp(p.dbg, tl, 3, i, 0);
                 mbar_arrive_expect_tx(bar_full + 8 * st, tx);
                 for (int c = 0; c < NBOX; ++c) tma_load_2d(sX + st * XSTAGE_BYTES + c * BOX_BYTES, &mapX, bar_full + 8 * st, c * 32, d0);
-                tma_load_2d(sHraw + st * L::HRAW, &mapH, bar_full + 8 * st, 0, d0);
+                tma_load_2d(sHraw + st * q.hraw, &mapH, bar_full + 8 * st, 0, d0);
             }
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0) {
-            constexpr uint32_t ID1 = make_idesc(128, VT, 0, 0);
-            constexpr uint32_t ID2 = make_idesc(128, N2, 0, 0);
-            constexpr uint32_t ID3 = make_idesc(128, N2, 1, 0);
-            auto issue_g1 = [&](int i) {
-                mbar_wait(bar_hready, i & 1);
-                tc_fence_after();
-                const uint32_t d = tmem + ((i & 1) ? TM_WH1 : TM_WH0);
+        // The whole warp runs the loop (descriptor arithmetic stays in uniform registers); one elected lane issues.
+        constexpr uint32_t ID1 = make_idesc(128, VT, 0, 0);
+        constexpr uint32_t ID2 = make_idesc(128, N2, 0, 0);
+        constexpr uint32_t ID3 = make_idesc(128, N2, 1, 0);
+        const uint64_t dW1hi = make_desc(sW1hi, SW1_LBO, SW1_SBO, LAYOUT_NONE), dW1lo = make_desc(sW1lo, SW1_LBO, SW1_SBO, LAYOUT_NONE);
+        const uint64_t dW2hi = make_desc(sW2hi, q.sw2_lbo, SW2_SBO, LAYOUT_NONE), dW2lo = make_desc(sW2lo, q.sw2_lbo, SW2_SBO, LAYOUT_NONE);
+        const uint64_t dHT = make_desc(sHT, SHT_LBO, SHT_SBO, LAYOUT_NONE);
+        const uint64_t dX0 = make_desc(sX, BOX_BYTES, 512, LAYOUT_128B_BASE32B);
+        const uint32_t w2step = (uint32_t)(2 * q.sw2_lbo) >> 4;
+        auto issue_g1 = [&](int i) {
+            const int b = i & 1;
+            mbar_wait(bar_hready + 8 * b, (i >> 1) & 1);
+            stamp(p.dbg, tl && lane == 0, 2, i, 0);
+            tc_fence_after();
+            const uint32_t d = tmem + (b ? TM_WH1 : TM_WH0), th = tmem + (b ? TM_H1 : TM_H0);
+            if (elect_one()) {
 #pragma unroll
-                for (int ks = 0; ks < KP8 / 8; ++ks)
-                    mma_ss(d, make_desc(sH + ks * 2 * SH_LBO, SH_LBO, SH_SBO, LAYOUT_NONE),
-                           make_desc(sW1 + ks * 2 * SW1_LBO, SW1_LBO, SW1_SBO, LAYOUT_NONE), ID1, ks > 0);
-                if (split) {
-#pragma unroll
-                    for (int ks = 0; ks < KP8 / 8; ++ks) {
-                        mma_ss(d, make_desc(sHlo + ks * 2 * SH_LBO, SH_LBO, SH_SBO, LAYOUT_NONE),
-                               make_desc(sW1 + ks * 2 * SW1_LBO, SW1_LBO, SW1_SBO, LAYOUT_NONE), ID1, 1);
-                        mma_ss(d, make_desc(sH + ks * 2 * SH_LBO, SH_LBO, SH_SBO, LAYOUT_NONE),
-                               make_desc(sW1lo + ks * 2 * SW1_LBO, SW1_LBO, SW1_SBO, LAYOUT_NONE), ID1, 1);
-                    }
+                for (int ks = 0; ks < KP8 / 8; ++ks) {
+                    const uint64_t bhi = dW1hi + (uint64_t)((ks * 2 * SW1_LBO) >> 4), blo = dW1lo + (uint64_t)((ks * 2 * SW1_LBO) >> 4);
+                    mma_ts(d, th + ks * 8, bhi, ID1, ks > 0);      // hi * hi
+                    mma_ts(d, th + TM_HLO + ks * 8, bhi, ID1, 1);  // lo * hi
+                    mma_ts(d, th + ks * 8, blo, ID1, 1);           // hi * lo
                 }
-                tc_commit(bar_whfull + 8 * (i & 1));
-            };
-            issue_g1(0);
-            for (int i = 0; i < n_my; ++i) {
-                if (i + 1 < n_my) issue_g1(i + 1);
-                const int st = i % S, b = i & 1;
-                mbar_wait(bar_rready + 8 * b, (i >> 1) & 1);
-                tc_fence_after();
-                if (do_r) {
-                    const uint32_t tR = tmem + (b ? TM_WH1 : TM_WH0), tHn = tmem + (b ? TM_HN1 : TM_HN0);
+                tc_commit(bar_whfull + 8 * b);
+            }
+            __syncwarp();
+            stamp(p.dbg, tl && lane == 0, 2, i, 2);
+        };
+        issue_g1(0);
+        for (int i = 0; i < n_my; ++i) {
+            if (i + 1 < n_my) issue_g1(i + 1);
+            const int st = i % S, b = i & 1;
+            mbar_wait(bar_rready + 8 * b, (i >> 1) & 1);
+            stamp(p.dbg, tl && lane == 0, 2, i, 1);
+            tc_fence_after();
+            if (DO_R) {
+                const uint32_t tR = tmem + (b ? TM_WH1 : TM_WH0), tHn = tmem + (b ? TM_HN1 : TM_HN0);
+                const uint64_t dX = dX0 + (uint64_t)((uint32_t)(st * XSTAGE_BYTES) >> 4);
+                if (elect_one()) {
+                    if (do_h) {
 #pragma unroll
-                    for (int ks = 0; ks < VT / 8; ++ks)
-                        mma_ts(tHn, tR + ks * 8, make_desc(sW2 + ks * 2 * L::SW2_LBO, L::SW2_LBO, SW2_SBO, LAYOUT_NONE), ID2, ks > 0);
-                    tc_commit(bar_hnfull + 8 * b);
-                    const uint32_t xs = sX + st * XSTAGE_BYTES;
+                        for (int ks = 0; ks < VT / 8; ++ks) {
+                            mma_ts(tHn, tR + ks * 8, dW2hi + (uint64_t)(ks * w2step), ID2, ks > 0);
+                            mma_ts(tHn, tR + ks * 8, dW2lo + (uint64_t)(ks * w2step), ID2, 1);
+                        }
+                        tc_commit(bar_hnfull + 8 * b);
+                    }
+                    if (do_w) {
 #pragma unroll
-                    for (int ks = 0; ks < TILE / 8; ++ks)
-                        mma_ss(tmem + TM_WN, make_desc(xs + ks * 1024, BOX_BYTES, 512, LAYOUT_128B_BASE32B),
-                               make_desc(sHT + ks * 2 * SHT_LBO, SHT_LBO, SHT_SBO, LAYOUT_NONE), ID3, (i > 0 || ks > 0));
+                        for (int ks = 0; ks < TILE / 8; ++ks)
+                            mma_ss(tmem + TM_WN, dX + (uint64_t)(ks * (1024 >> 4)), dHT + (uint64_t)(ks * ((2 * SHT_LBO) >> 4)), ID3,
+                                   (i > 0 || ks > 0));
+                    }
                     tc_commit(bar_empty + 8 * st);
                     tc_commit(bar_shtfree);
-                } else {  // objective only: nothing reads the stage after E1
-                    mbar_arrive(bar_empty + 8 * st);
-                    mbar_arrive(bar_shtfree);
                 }
+                __syncwarp();
+                stamp(p.dbg, tl && lane == 0, 2, i, 3);
+            } else if (lane == 0) {  // objective only: nothing reads the stage after E1
+                mbar_arrive(bar_empty + 8 * st);
+                mbar_arrive(bar_shtfree);
             }
-            tc_commit(bar_done);
-            mbar_wait(bar_done, 0);  // every MMA has retired before the CTA tears TMEM down
         }
+        if (elect_one()) tc_commit(bar_done);
+        __syncwarp();
+        mbar_wait(bar_done, 0);  // every MMA has retired before the CTA tears TMEM down
     } else if (warp >= 4) {
         // ================= epilogue warpgroups =================
-        const int g = (warp - 4) >> 2, q = warp & 3;
-        const int s = q * 32 + lane;  // sample row of the tile = TMEM lane
-        const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+        const int g = (warp - 4) >> 2, qw = warp & 3;
+        const int s = qw * 32 + lane;  // sample row of the tile = TMEM lane
+        const uint32_t lane_off = (uint32_t)(qw * 32) << 16;
         const uint32_t sw = (s >> 2) & 1;
         const float eps = (float)SAL_EPS_F32;
         for (int i = g; i < n_my; i += 2) {
             const int st = i % S, b = i & 1;
             const int64_t d0 = (int64_t)((int)blockIdx.x + i * (int)gridDim.x) * TILE;
             const bool valid = d0 + s < p.D;
+            const bool tlw = tl && lane == 0 && qw == 0;
+            stamp(p.dbg, tlw, g, i, 0);
             mbar_wait(bar_full + 8 * st, (i / S) & 1);
-            // exposures of this sample (rows beyond D are zero-filled by TMA)
+            stamp(p.dbg, tlw, g, i, 1);
+            // exposures of this sample (rows beyond D are zero-filled by TMA) -> registers and, as tf32 hi / lo,
+            // the TMEM A operand of G1.  Buffer b was last read by G1(i - 2), which finished before E1(i - 2) began.
             float h[KP8];
             {
-                const uint32_t hrow = sHraw + st * L::HRAW + s * (k * 4);
+                const uint32_t hrow = sHraw + st * q.hraw + s * (k * 4);
+                const uint32_t th = tmem + lane_off + (b ? TM_H1 : TM_H0);
 #pragma unroll
-                for (int j = 0; j < KP8; j += 4) {
-                    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (j < k) t = lds128(hrow + j * 4);
-                    h[j] = t.x, h[j + 1] = t.y, h[j + 2] = t.z, h[j + 3] = t.w;
+                for (int j = 0; j < KP8; j += 8) {
+                    float4 t0 = make_float4(0.f, 0.f, 0.f, 0.f), t1 = t0;
+                    if (j < k) t0 = lds128(hrow + j * 4);
+                    if (j + 4 < k) t1 = lds128(hrow + j * 4 + 16);
+                    h[j] = t0.x, h[j + 1] = t0.y, h[j + 2] = t0.z, h[j + 3] = t0.w;
+                    h[j + 4] = t1.x, h[j + 5] = t1.y, h[j + 6] = t1.z, h[j + 7] = t1.w;
+                    uint32_t hi[8], lo[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        hi[e] = tf32_bits(h[j + e]);
+                        lo[e] = tf32_bits(h[j + e] - __uint_as_float(hi[e]));
+                    }
+                    tmem_st8(th + j, hi);
+                    tmem_st8(th + TM_HLO + j, lo);
                 }
             }
-            if (i > 0) mbar_wait(bar_whfull + 8 * ((i - 1) & 1), ((i - 1) >> 1) & 1);  // G1(i-1) has read sH
-#pragma unroll
-            for (int kc = 0; kc < KP8 / 4; ++kc)
-                sts128(sH + kc * SH_LBO + (s >> 3) * SH_SBO + (s & 7) * 16,
-                       make_float4(tf32_rn(h[4 * kc]), tf32_rn(h[4 * kc + 1]), tf32_rn(h[4 * kc + 2]), tf32_rn(h[4 * kc + 3])));
-            if (split) {
-#pragma unroll
-                for (int kc = 0; kc < KP8 / 4; ++kc) {
-                    float4 lo;
-                    lo.x = tf32_rn(h[4 * kc] - tf32_rn(h[4 * kc])), lo.y = tf32_rn(h[4 * kc + 1] - tf32_rn(h[4 * kc + 1]));
-                    lo.z = tf32_rn(h[4 * kc + 2] - tf32_rn(h[4 * kc + 2])), lo.w = tf32_rn(h[4 * kc + 3] - tf32_rn(h[4 * kc + 3]));
-                    sts128(sHlo + kc * SH_LBO + (s >> 3) * SH_SBO + (s & 7) * 16, lo);
-                }
-            }
-            fence_proxy_async();
-            mbar_arrive(bar_hready);
+            tc_wait_st();
+            tc_fence_before();
+            mbar_arrive(bar_hready + 8 * b);
+            stamp(p.dbg, tlw, g, i, 2);
 
             mbar_wait(bar_whfull + 8 * b, (i >> 1) & 1);
+            stamp(p.dbg, tlw, g, i, 3);
             tc_fence_after();
             const uint32_t tWH = tmem + lane_off + (b ? TM_WH1 : TM_WH0);
             float kl = 0.f;
@@ -457,9 +506,11 @@ klnmf_pass_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
                     for (int e = 0; e < 32; ++e) p.dbg[(size_t)s * VT + 64 + e] = __uint_as_float(v0[e]);
                 }
             }
-            if (do_kl && valid) obj_acc += (double)kl;
-            if (do_r) {
+            if (DO_KL && valid) obj_acc += (double)kl;
+            stamp(p.dbg, tlw, g, i, 4);
+            if (DO_R) {
                 if (i > 0) mbar_wait(bar_shtfree, (i - 1) & 1);  // G3(i-1) has read sHT
+                stamp(p.dbg, tlw, g, i, 5);
                 const uint32_t tbase = sHT + (s >> 2) * SHT_LBO + (s & 3) * 4;
 #pragma unroll
                 for (int j = 0; j < KP8; ++j)
@@ -470,8 +521,10 @@ klnmf_pass_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
             tc_fence_before();
             mbar_arrive(bar_rready + 8 * b);
 
-            if (do_h) {
+            if (DO_R && do_h) {
+                stamp(p.dbg, tlw, g, i, 6);
                 mbar_wait(bar_hnfull + 8 * b, (i >> 1) & 1);
+                stamp(p.dbg, tlw, g, i, 7);
                 tc_fence_after();
                 uint32_t v[32];
                 tmem_ld32(tmem + lane_off + (b ? TM_HN1 : TM_HN0), v);
@@ -497,10 +550,10 @@ klnmf_pass_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
             }
         }
         // ---- per-CTA numerator partial: TMEM lane = feature, column = signature
-        if (do_w && g == 0) {
+        if (DO_R && do_w && g == 0) {
             mbar_wait(bar_done, 0);
             tc_fence_after();
-            if (q < 3) {
+            if (qw < 3) {
                 uint32_t v[32];
                 tmem_ld32(tmem + lane_off + TM_WN, v);
                 tc_wait_ld();
@@ -511,7 +564,7 @@ klnmf_pass_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
             }
             tc_fence_before();
         }
-        if (do_kl) {
+        if (DO_KL) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) obj_acc += __shfl_xor_sync(0xffffffffu, obj_acc, o);
             if (lane == 0) s_red[warp - 4] = obj_acc;
@@ -520,7 +573,7 @@ klnmf_pass_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
     __syncwarp();
     tc_fence_before();
     __syncthreads();
-    if (do_kl && tid == 0) {
+    if (DO_KL && tid == 0) {
         double t = 0.0;
         for (int w = 0; w < 8; ++w) t += s_red[w];
         p.partial_obj[blockIdx.x] = t;
@@ -572,11 +625,15 @@ int encode_2d(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t rows, 
 
 template <int KP8, bool DO_R, bool DO_KL>
 int launch_tc_v(sal_ctx* c, const PassArgs& a, cudaStream_t st) {
-    using L = Lay<KP8>;
+    const Plan q = make_plan(c->k, KP8);
+    if (q.total > SMEM_LIMIT) {
+        sal_set_error("tensor-core pass: shared-memory plan of %d bytes exceeds the limit", q.total);
+        return SAL_EUNSUPPORTED;
+    }
     static bool attr_set[16] = {false};
     if (!attr_set[c->device & 15]) {
         SAL_CUDA(cudaFuncSetAttribute(klnmf_pass_tc_kernel<KP8, DO_R, DO_KL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      L::DYN_BYTES));
+                                      SMEM_LIMIT));
         attr_set[c->device & 15] = true;
     }
     CUtensorMap mapX, mapH;
@@ -589,7 +646,7 @@ int launch_tc_v(sal_ctx* c, const PassArgs& a, cudaStream_t st) {
     p.D = c->D, p.k = c->k, p.flags = a.flags;
     p.n_tiles = (int)((c->D + TILE - 1) / TILE);
     const int grid = p.n_tiles < c->n_sm ? p.n_tiles : c->n_sm;
-    klnmf_pass_tc_kernel<KP8, DO_R, DO_KL><<<grid, NTHREADS, L::DYN_BYTES, st>>>(mapX, mapH, p);
+    klnmf_pass_tc_kernel<KP8, DO_R, DO_KL><<<grid, NTHREADS, q.total, st>>>(mapX, mapH, p);
     SAL_CUDA(cudaGetLastError());
     c->launches++;
     return sal_launch_pass_reduce(c, a, grid, st);
