@@ -13,9 +13,8 @@
 //
 // tf32 recipe (scripts/tf32_precision_experiment.py): WH feeds a division and decides whether the
 // fit's 1e-7 convergence test sees noise, so G1 is error compensated -- h = hi + lo, w = hi + lo,
-// WH = hi*hi + lo*hi + hi*lo (3 x tf32, ~2^-22).  In G2 the signatures, whose rounding error would be the same
-// for every sample and every iteration, are split too (R*Whi + R*Wlo); R itself and G3 use plain tf32, their
-// rounding noise averages out over the 96 features / all samples.
+// WH = hi*hi + lo*hi + hi*lo (3 x tf32, ~2^-22).  The quotient R and the operands of G2 / G3 are plain tf32
+// (round to nearest): their rounding noise averages out over the 96 features / all samples.
 //
 // Wn (96 x k) accumulates in TMEM over all tiles of the CTA and is written once as a per-CTA partial;
 // the deterministic fixed-order reduction kernel of klnmf_pass.cu finishes the job.
@@ -28,7 +27,8 @@
 //                 written by the threads with round-to-nearest tf32 conversion.
 //
 // Warp roles (384 threads, 1 CTA / SM, persistent over tiles):  warp 0 TMA producer, warp 1 MMA issuer,
-// warp 2 TMEM allocator, warps 4-7 and 8-11 two epilogue warpgroups that alternate tiles.
+// warp 2 TMEM allocator, warp 3 TMA store of the updated exposures (staged in the tile's raw-H slot),
+// warps 4-7 and 8-11 two epilogue warpgroups that alternate tiles.
 #include <cuda.h>  // CUtensorMap types; cuTensorMapEncodeTiled itself is fetched through the runtime (no -lcuda)
 
 #include "sal_common.cuh"
@@ -51,17 +51,17 @@ constexpr uint32_t TM_H0 = 288, TM_H1 = 352, TM_HLO = 32, TM_COLS = 512;
 // strides of the thread-written operands (bytes)
 constexpr int SW1_LBO = 1536, SW1_SBO = 128;  // sW1 [kc][feature/8][8][16B]  B of G1 (N = feature, K = signature)
 constexpr int SW2_SBO = 128;                  // sW2 [fc][sig/8][8][16B]      B of G2 (N = signature, K = feature)
-constexpr int SHT_LBO = 528, SHT_SBO = 128;   // sHT [sc][sig/8][8][16B](+16) B of G3 (N = signature, K = sample)
-constexpr int SHT_BYTES = 32 * SHT_LBO;
+constexpr int SHT_SBO = 128;                  // sHT [sc][sig/8][8][16B](+16) B of G3 (N = signature, K = sample); LBO = Plan::sht_lbo
+constexpr int NH = 4;                         // raw-H slots (load -> P0 -> output staging -> TMA store)
 
 // Shared-memory plan for k signatures (KP8 = k rounded up to 8).  Only ceil(k/8) signature groups of sW2 are
 // stored: G2 runs with N = 32 and the groups beyond them read the following bytes, finite garbage that only
 // reaches output columns >= k which nobody reads.  The same holds for the 4th (non-existent) feature box of
 // the G3 A operand: it reads the bytes after the stage, so at least 16 KB must follow the last stage.
 struct Plan {
-    int S;  // X / H stages
-    int hraw, sw1, sw2, sw2_lbo;
-    int off_hraw, off_w1hi, off_w1lo, off_w2hi, off_w2lo, off_sht, off_bar, off_misc, total;
+    int S;  // X / R stages
+    int hraw, sw1, sw2, sw2_lbo, sht, sht_lbo;
+    int off_hraw, off_w1hi, off_w1lo, off_w2, off_sht, off_bar, off_misc, total;
 };
 __host__ __device__ inline Plan make_plan(int k, int KP8) {
     Plan q;
@@ -69,16 +69,17 @@ __host__ __device__ inline Plan make_plan(int k, int KP8) {
     q.sw1 = (KP8 / 4) * SW1_LBO;
     q.sw2_lbo = (KP8 / 8) * 128;
     q.sw2 = 24 * q.sw2_lbo;
-    const int fixed = 2 * q.sw1 + 2 * q.sw2 + SHT_BYTES + 24 * 8 + 128;
-    q.S = (3 * (XSTAGE_BYTES + q.hraw) + fixed <= SMEM_LIMIT) ? 3 : 2;
+    q.sht_lbo = (KP8 / 8) * 128 + 16;  // + 16: the per-sample scalar stores of a warp hit 32 different banks
+    q.sht = 32 * q.sht_lbo;
+    const int fixed = NH * q.hraw + 2 * q.sw1 + q.sw2 + q.sht + 32 * 8 + 128;
+    q.S = (3 * XSTAGE_BYTES + fixed <= SMEM_LIMIT) ? 3 : 2;
     q.off_hraw = q.S * XSTAGE_BYTES;
-    q.off_w1hi = q.off_hraw + q.S * q.hraw;
+    q.off_w1hi = q.off_hraw + NH * q.hraw;
     q.off_w1lo = q.off_w1hi + q.sw1;
-    q.off_w2hi = q.off_w1lo + q.sw1;
-    q.off_w2lo = q.off_w2hi + q.sw2;
-    q.off_sht = q.off_w2lo + q.sw2;
-    q.off_bar = q.off_sht + SHT_BYTES;
-    q.off_misc = q.off_bar + 24 * 8;
+    q.off_w2 = q.off_w1lo + q.sw1;
+    q.off_sht = q.off_w2 + q.sw2;
+    q.off_bar = q.off_sht + q.sht;
+    q.off_misc = q.off_bar + 32 * 8;
     q.total = q.off_misc + 128;
     return q;
 }
@@ -139,6 +140,15 @@ __device__ __forceinline__ bool elect_one() {
     asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred)::"memory");
     return pred != 0;
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit_and_wait_read() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
@@ -233,7 +243,8 @@ __device__ __forceinline__ void quotient_box(uint32_t (&v)[32], uint32_t rowbase
                 if (xv[e] != 0.f) kl += xv[e] * logf(r) - xv[e];
                 kl += wh;
             }
-            rr[e] = tf32_rn(r);
+            // round-to-nearest tf32 = add half an ulp; the MMA ignores the 13 low mantissa bits, no need to mask them
+            rr[e] = __uint_as_float(__float_as_uint(r) + 0x1000u);
             v[8 * m + e] = __float_as_uint(rr[e]);
         }
         if (DO_R) {
@@ -270,7 +281,8 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8])
 
 template <int KP8, bool DO_R, bool DO_KL>
 __global__ void __launch_bounds__(NTHREADS, 1)
-klnmf_pass_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapH, TcParams p) {
+klnmf_pass_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapH,
+                     const __grid_constant__ CUtensorMap mapHout, TcParams p) {
     extern __shared__ __align__(1024) unsigned char smem_dyn[];
     const uint32_t base = smem_u32(smem_dyn);
     if (base & 1023u) __trap();  // the swizzled TMA boxes need 1024-byte alignment
@@ -278,10 +290,12 @@ klnmf_pass_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
     const Plan q = make_plan(k, KP8);
     const int S = q.S;
     const uint32_t sX = base, sHraw = base + q.off_hraw, sW1hi = base + q.off_w1hi, sW1lo = base + q.off_w1lo;
-    const uint32_t sW2hi = base + q.off_w2hi, sW2lo = base + q.off_w2lo, sHT = base + q.off_sht, bars = base + q.off_bar;
-    // barriers: full[3] empty[3] hready[2] whfull[2] rready[2] hnfull[2] shtfree done
+    const uint32_t sW2 = base + q.off_w2, sHT = base + q.off_sht, bars = base + q.off_bar;
+    const int SHT_LBO = q.sht_lbo;
+    // barriers: full[3] empty[3] hready[2] whfull[2] rready[2] hnfull[2] shtfree done hfull[4] hempty[4] hout[4]
     const uint32_t bar_full = bars, bar_empty = bars + 24, bar_hready = bars + 48, bar_whfull = bars + 64;
     const uint32_t bar_rready = bars + 80, bar_hnfull = bars + 96, bar_shtfree = bars + 112, bar_done = bars + 120;
+    const uint32_t bar_hfull = bars + 128, bar_hempty = bars + 160, bar_hout = bars + 192;
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_dyn + q.off_misc);
     double* s_red = reinterpret_cast<double*>(smem_dyn + q.off_misc + 16);  // [8]
 
@@ -293,6 +307,7 @@ klnmf_pass_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapX) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapH) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapHout) : "memory");
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < 3; ++i) mbar_init(bar_full + 8 * i, 1), mbar_init(bar_empty + 8 * i, 1);
@@ -304,6 +319,7 @@ klnmf_pass_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
         }
         mbar_init(bar_shtfree, 1);
         mbar_init(bar_done, 1);
+        for (int i = 0; i < NH; ++i) mbar_init(bar_hfull + 8 * i, 1), mbar_init(bar_hempty + 8 * i, 1), mbar_init(bar_hout + 8 * i, 128);
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -319,13 +335,10 @@ klnmf_pass_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
         const float hi = tf32_rn(w), lo = tf32_rn(w - hi);
         const uint32_t o1 = (j >> 2) * SW1_LBO + (f >> 3) * SW1_SBO + (f & 7) * 16 + (j & 3) * 4;
         sts32(sW1hi + o1, hi), sts32(sW1lo + o1, lo);
-        if (DO_R) {
-            const uint32_t o2 = (f >> 2) * q.sw2_lbo + (j >> 3) * SW2_SBO + (j & 7) * 16 + (f & 3) * 4;
-            sts32(sW2hi + o2, hi), sts32(sW2lo + o2, lo);
-        }
+        if (DO_R) sts32(sW2 + (f >> 2) * q.sw2_lbo + (j >> 3) * SW2_SBO + (j & 7) * 16 + (f & 3) * 4, hi);
     }
     if (DO_R)
-        for (int i = tid; i < SHT_BYTES / 4; i += NTHREADS) sts32(sHT + 4 * i, 0.f);
+        for (int i = tid; i < q.sht / 4; i += NTHREADS) sts32(sHT + 4 * i, 0.f);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -338,15 +351,16 @@ klnmf_pass_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
     if (warp == 0) {
         // ================= TMA producer =================
         if (lane == 0) {
-            const uint32_t tx = XSTAGE_BYTES + (uint32_t)(TILE * k * 4);
             for (int i = 0; i < n_my; ++i) {
-                const int st = i % S;
+                const int st = i % S, hs = i % NH;
                 const int d0 = ((int)blockIdx.x + i * (int)gridDim.x) * TILE;
+                mbar_wait(bar_hempty + 8 * hs, ((i / NH) & 1) ^ 1);
+                mbar_arrive_expect_tx(bar_hfull + 8 * hs, (uint32_t)(TILE * k * 4));
+                tma_load_2d(sHraw + hs * q.hraw, &mapH, bar_hfull + 8 * hs, 0, d0);
                 mbar_wait(bar_empty + 8 * st, ((i / S) & 1) ^ 1);
                 stamp(p.dbg, tl, 3, i, 0);
-                mbar_arrive_expect_tx(bar_full + 8 * st, tx);
+                mbar_arrive_expect_tx(bar_full + 8 * st, XSTAGE_BYTES);
                 for (int c = 0; c < NBOX; ++c) tma_load_2d(sX + st * XSTAGE_BYTES + c * BOX_BYTES, &mapX, bar_full + 8 * st, c * 32, d0);
-                tma_load_2d(sHraw + st * q.hraw, &mapH, bar_full + 8 * st, 0, d0);
             }
         }
     } else if (warp == 1) {
@@ -356,8 +370,9 @@ klnmf_pass_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
         constexpr uint32_t ID2 = make_idesc(128, N2, 0, 0);
         constexpr uint32_t ID3 = make_idesc(128, N2, 1, 0);
         const uint64_t dW1hi = make_desc(sW1hi, SW1_LBO, SW1_SBO, LAYOUT_NONE), dW1lo = make_desc(sW1lo, SW1_LBO, SW1_SBO, LAYOUT_NONE);
-        const uint64_t dW2hi = make_desc(sW2hi, q.sw2_lbo, SW2_SBO, LAYOUT_NONE), dW2lo = make_desc(sW2lo, q.sw2_lbo, SW2_SBO, LAYOUT_NONE);
+        const uint64_t dW2 = make_desc(sW2, q.sw2_lbo, SW2_SBO, LAYOUT_NONE);
         const uint64_t dHT = make_desc(sHT, SHT_LBO, SHT_SBO, LAYOUT_NONE);
+        const uint32_t htstep = (uint32_t)(2 * SHT_LBO) >> 4;
         const uint64_t dX0 = make_desc(sX, BOX_BYTES, 512, LAYOUT_128B_BASE32B);
         const uint32_t w2step = (uint32_t)(2 * q.sw2_lbo) >> 4;
         auto issue_g1 = [&](int i) {
@@ -390,22 +405,21 @@ klnmf_pass_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
                 const uint32_t tR = tmem + (b ? TM_WH1 : TM_WH0), tHn = tmem + (b ? TM_HN1 : TM_HN0);
                 const uint64_t dX = dX0 + (uint64_t)((uint32_t)(st * XSTAGE_BYTES) >> 4);
                 if (elect_one()) {
-                    if (do_h) {
-#pragma unroll
-                        for (int ks = 0; ks < VT / 8; ++ks) {
-                            mma_ts(tHn, tR + ks * 8, dW2hi + (uint64_t)(ks * w2step), ID2, ks > 0);
-                            mma_ts(tHn, tR + ks * 8, dW2lo + (uint64_t)(ks * w2step), ID2, 1);
-                        }
-                        tc_commit(bar_hnfull + 8 * b);
-                    }
+                    // G3 first: it is the last reader of the X / R stage and of sHT, so the stage goes back to the
+                    // TMA producer as early as possible; G2 (TMEM operand) follows.
                     if (do_w) {
 #pragma unroll
                         for (int ks = 0; ks < TILE / 8; ++ks)
-                            mma_ss(tmem + TM_WN, dX + (uint64_t)(ks * (1024 >> 4)), dHT + (uint64_t)(ks * ((2 * SHT_LBO) >> 4)), ID3,
+                            mma_ss(tmem + TM_WN, dX + (uint64_t)(ks * (1024 >> 4)), dHT + (uint64_t)(ks * htstep), ID3,
                                    (i > 0 || ks > 0));
                     }
                     tc_commit(bar_empty + 8 * st);
                     tc_commit(bar_shtfree);
+                    if (do_h) {
+#pragma unroll
+                        for (int ks = 0; ks < VT / 8; ++ks) mma_ts(tHn, tR + ks * 8, dW2 + (uint64_t)(ks * w2step), ID2, ks > 0);
+                        tc_commit(bar_hnfull + 8 * b);
+                    }
                 }
                 __syncwarp();
                 stamp(p.dbg, tl && lane == 0, 2, i, 3);
@@ -417,6 +431,22 @@ klnmf_pass_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
         if (elect_one()) tc_commit(bar_done);
         __syncwarp();
         mbar_wait(bar_done, 0);  // every MMA has retired before the CTA tears TMEM down
+    } else if (warp == 3) {
+        // ================= exposure store =================
+        // The epilogue leaves the updated exposures of tile i in raw-H slot i % NH; one thread streams them out with
+        // a TMA store (rows beyond D are clipped by the tensor map) and hands the slot back to the producer.
+        if (lane == 0) {
+            for (int i = 0; i < n_my; ++i) {
+                const int hs = i % NH;
+                mbar_wait(bar_hout + 8 * hs, (i / NH) & 1);
+                if (DO_R && do_h) {
+                    tma_store_2d(&mapHout, sHraw + hs * q.hraw, 0, ((int)blockIdx.x + i * (int)gridDim.x) * TILE);
+                    tma_store_commit_and_wait_read();
+                }
+                mbar_arrive(bar_hempty + 8 * hs);
+            }
+            tma_store_wait_all();
+        }
     } else if (warp >= 4) {
         // ================= epilogue warpgroups =================
         const int g = (warp - 4) >> 2, qw = warp & 3;
@@ -424,6 +454,37 @@ klnmf_pass_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
         const uint32_t lane_off = (uint32_t)(qw * 32) << 16;
         const uint32_t sw = (s >> 2) & 1;
         const float eps = (float)SAL_EPS_F32;
+        // P0: exposures of sample s of tile i (rows beyond D are zero-filled by TMA) -> registers and, as tf32
+        // hi / lo, the TMEM A operand of G1.  TMEM buffer (i & 1) was last read by G1(i - 2), which retired before
+        // this warpgroup began E1(i - 2).
+        auto load_h = [&](int i, float (&h)[KP8]) {
+            const int hs = i % NH, b = i & 1;
+            mbar_wait(bar_hfull + 8 * hs, (i / NH) & 1);
+            const uint32_t hrow = sHraw + hs * q.hraw + s * (k * 4);
+            const uint32_t th = tmem + lane_off + (b ? TM_H1 : TM_H0);
+#pragma unroll
+            for (int j = 0; j < KP8; j += 8) {
+                float4 t0 = make_float4(0.f, 0.f, 0.f, 0.f), t1 = t0;
+                if (j < k) t0 = lds128(hrow + j * 4);
+                if (j + 4 < k) t1 = lds128(hrow + j * 4 + 16);
+                h[j] = t0.x, h[j + 1] = t0.y, h[j + 2] = t0.z, h[j + 3] = t0.w;
+                h[j + 4] = t1.x, h[j + 5] = t1.y, h[j + 6] = t1.z, h[j + 7] = t1.w;
+                uint32_t hi[8], lo[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    hi[e] = tf32_bits(h[j + e]);
+                    lo[e] = tf32_bits(h[j + e] - __uint_as_float(hi[e]));
+                }
+                tmem_st8(th + j, hi);
+                tmem_st8(th + TM_HLO + j, lo);
+            }
+            tc_wait_st();
+            tc_fence_before();
+            mbar_arrive(bar_hready + 8 * b);
+        };
+
+        float h[KP8], hn[KP8];
+        if (g < n_my) load_h(g, h);
         for (int i = g; i < n_my; i += 2) {
             const int st = i % S, b = i & 1;
             const int64_t d0 = (int64_t)((int)blockIdx.x + i * (int)gridDim.x) * TILE;
@@ -431,35 +492,6 @@ klnmf_pass_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
             const bool tlw = tl && lane == 0 && qw == 0;
             stamp(p.dbg, tlw, g, i, 0);
             mbar_wait(bar_full + 8 * st, (i / S) & 1);
-            stamp(p.dbg, tlw, g, i, 1);
-            // exposures of this sample (rows beyond D are zero-filled by TMA) -> registers and, as tf32 hi / lo,
-            // the TMEM A operand of G1.  Buffer b was last read by G1(i - 2), which finished before E1(i - 2) began.
-            float h[KP8];
-            {
-                const uint32_t hrow = sHraw + st * q.hraw + s * (k * 4);
-                const uint32_t th = tmem + lane_off + (b ? TM_H1 : TM_H0);
-#pragma unroll
-                for (int j = 0; j < KP8; j += 8) {
-                    float4 t0 = make_float4(0.f, 0.f, 0.f, 0.f), t1 = t0;
-                    if (j < k) t0 = lds128(hrow + j * 4);
-                    if (j + 4 < k) t1 = lds128(hrow + j * 4 + 16);
-                    h[j] = t0.x, h[j + 1] = t0.y, h[j + 2] = t0.z, h[j + 3] = t0.w;
-                    h[j + 4] = t1.x, h[j + 5] = t1.y, h[j + 6] = t1.z, h[j + 7] = t1.w;
-                    uint32_t hi[8], lo[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        hi[e] = tf32_bits(h[j + e]);
-                        lo[e] = tf32_bits(h[j + e] - __uint_as_float(hi[e]));
-                    }
-                    tmem_st8(th + j, hi);
-                    tmem_st8(th + TM_HLO + j, lo);
-                }
-            }
-            tc_wait_st();
-            tc_fence_before();
-            mbar_arrive(bar_hready + 8 * b);
-            stamp(p.dbg, tlw, g, i, 2);
-
             mbar_wait(bar_whfull + 8 * b, (i >> 1) & 1);
             stamp(p.dbg, tlw, g, i, 3);
             tc_fence_after();
@@ -516,13 +548,19 @@ klnmf_pass_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
                 for (int j = 0; j < KP8; ++j)
                     if (j < k) sts32(tbase + (j >> 3) * SHT_SBO + (j & 7) * 16, tf32_rn(h[j]));
                 tc_wait_st();
+                stamp(p.dbg, tlw, g, i, 6);
                 fence_proxy_async();
             }
             tc_fence_before();
             mbar_arrive(bar_rready + 8 * b);
+            stamp(p.dbg, tlw, g, i, 1);
+
+            // the next tile's exposures go to the tensor core now, so that G1(i + 2) runs behind G2(i) / G3(i)
+            // while this warpgroup finishes tile i
+            if (i + 2 < n_my) load_h(i + 2, hn);
+            stamp(p.dbg, tlw, g, i, 2);
 
             if (DO_R && do_h) {
-                stamp(p.dbg, tlw, g, i, 6);
                 mbar_wait(bar_hnfull + 8 * b, (i >> 1) & 1);
                 stamp(p.dbg, tlw, g, i, 7);
                 tc_fence_after();
@@ -533,8 +571,8 @@ klnmf_pass_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
 #pragma unroll
                     for (int e = 0; e < 32; ++e) p.dbg[(size_t)TILE * VT + s * 32 + e] = __uint_as_float(v[e]);
                 }
-                if (valid) {
-                    float* og = p.H_out + (size_t)(d0 + s) * k;
+                {
+                    const uint32_t orow = sHraw + (i % NH) * q.hraw + s * (k * 4);
 #pragma unroll
                     for (int j = 0; j < KP8; j += 4)
                         if (j < k) {
@@ -543,11 +581,15 @@ klnmf_pass_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
                             o.y = fmaxf(h[j + 1] * __uint_as_float(v[j + 1]), eps);
                             o.z = fmaxf(h[j + 2] * __uint_as_float(v[j + 2]), eps);
                             o.w = fmaxf(h[j + 3] * __uint_as_float(v[j + 3]), eps);
-                            *reinterpret_cast<float4*>(og + j) = o;
+                            sts128(orow + j * 4, o);
                         }
+                    fence_proxy_async();
                 }
                 tc_fence_before();
             }
+            mbar_arrive(bar_hout + 8 * (i % NH));  // slot i % NH: staged output ready (or simply no longer needed)
+#pragma unroll
+            for (int j = 0; j < KP8; ++j) h[j] = hn[j];
         }
         // ---- per-CTA numerator partial: TMEM lane = feature, column = signature
         if (DO_R && do_w && g == 0) {
@@ -636,9 +678,11 @@ int launch_tc_v(sal_ctx* c, const PassArgs& a, cudaStream_t st) {
                                       SMEM_LIMIT));
         attr_set[c->device & 15] = true;
     }
-    CUtensorMap mapX, mapH;
+    CUtensorMap mapX, mapH, mapHout;
     if (int e = encode_2d(&mapX, a.X, VT, (uint64_t)c->D, 32, TILE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return e;
     if (int e = encode_2d(&mapH, a.H_in, (uint64_t)c->k, (uint64_t)c->D, (uint32_t)c->k, TILE, CU_TENSOR_MAP_SWIZZLE_NONE)) return e;
+    const void* hout = (a.flags & SAL_PASS_UPDATE_H) ? a.H_out : a.H_in;
+    if (int e = encode_2d(&mapHout, hout, (uint64_t)c->k, (uint64_t)c->D, (uint32_t)c->k, TILE, CU_TENSOR_MAP_SWIZZLE_NONE)) return e;
     TcParams p;
     p.W = (const float*)a.W, p.H_out = (float*)a.H_out;
     p.partial_wnum = (float*)c->partial_wnum, p.partial_obj = c->partial_obj;
@@ -646,7 +690,7 @@ int launch_tc_v(sal_ctx* c, const PassArgs& a, cudaStream_t st) {
     p.D = c->D, p.k = c->k, p.flags = a.flags;
     p.n_tiles = (int)((c->D + TILE - 1) / TILE);
     const int grid = p.n_tiles < c->n_sm ? p.n_tiles : c->n_sm;
-    klnmf_pass_tc_kernel<KP8, DO_R, DO_KL><<<grid, NTHREADS, q.total, st>>>(mapX, mapH, p);
+    klnmf_pass_tc_kernel<KP8, DO_R, DO_KL><<<grid, NTHREADS, q.total, st>>>(mapX, mapH, mapHout, p);
     SAL_CUDA(cudaGetLastError());
     c->launches++;
     return sal_launch_pass_reduce(c, a, grid, st);

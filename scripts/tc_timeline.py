@@ -24,7 +24,7 @@ torch.cuda.synchronize()
 ws.set_debug_buffer(None)
 t = dbg.view(torch.int32).cpu().numpy().astype(np.int64)[128 * 96 + 128 * 32 :][: 4 * 48 * 8].reshape(4, 48, 8) & 0xFFFFFFFF
 t0 = t[3, 0, 0]
-names = ["start", "full", "hready>", "whfull", "E1done", "shtfree", "rready>", "hnfull"]
+names = ["start", "rready>", "P0nxt>", "whfull", "E1done", "shtfree", "sts+wst", "hnfull"]
 print("WG timeline (clk since first TMA issue): tile | " + " ".join(n.rjust(8) for n in names) + " | next-start")
 for i in range(16):
     g = i & 1
@@ -34,4 +34,5 @@ print("MMA: tile | hready-seen  G1-issued  rready-seen  G2G3-issued")
 for i in range(16):
     print(f"   {i:2d} | {t[2, i, 0] - t0:8d} {t[2, i, 2] - t0:8d} {t[2, i, 1] - t0:8d} {t[2, i, 3] - t0:8d}")
 print("TMA: tile | issue")
+print("  ", [int(t[3, i, 0] - t0) for i in range(16, 32)])
 print("  ", [int(t[3, i, 0] - t0) for i in range(16)])
