@@ -36,10 +36,14 @@ enum { SAL_F32 = 0, SAL_F64 = 1 };
 /* arithmetic used for the three thin contractions of the fused pass (fp32 handles only) */
 enum {
     SAL_MATH_FMA = 0,  /* CUDA-core FMA in the handle's dtype (exact fp32 / fp64)          */
-    SAL_MATH_TF32 = 1  /* tcgen05 kind::tf32 tensor-core contractions, fp32 accumulation:
+    SAL_MATH_TF32 = 1, /* tcgen05 kind::tf32 tensor-core contractions, fp32 accumulation:
                           used by sal_klnmf_pass when V == 96, k % 4 == 0, no weights / h_scale and flags within
-                          UPDATE_H | WNUM | OBJECTIVE; every other call runs the exact FMA kernels (still on the GPU) */
+                          UPDATE_H | WNUM | OBJECTIVE and D_local >= SAL_TF32_MIN_SAMPLES (below that the pass is
+                          latency bound and the tf32 noise of the numerator no longer averages out over samples);
+                          every other call runs the exact FMA kernels (still on the GPU)                      */
+    SAL_MATH_TF32_ALWAYS = 2 /* as SAL_MATH_TF32 without the D_local threshold (used by the parity tests)     */
 };
+enum { SAL_TF32_MIN_SAMPLES = 4096 };
 
 enum {
     SAL_EINVAL = -1,      /* null pointer / bad size / bad enum            */
@@ -68,6 +72,11 @@ int sal_set_math(sal_handle_t h, int math_mode);
  * R[128][96] and Hn[128][32] of its first tile, then a clock64 timeline [role 4][tile 48][phase 8] (uint32) of
  * its warp roles.  Pass NULL to switch off. */
 int sal_set_debug_buffer(sal_handle_t h, void* buf);
+/* Kernel timing for benchmarks: when on, every fused-pass kernel launched with UPDATE_H | WNUM is bracketed by CUDA
+ * events on its stream.  sal_get_pass_timing synchronises on them and returns their summed duration and count
+ * since the last call (bench.py "roofline"). */
+int sal_set_timing(sal_handle_t h, int on);
+int sal_get_pass_timing(sal_handle_t h, double* total_ms, int64_t* n_launches);
 /* number of kernels this handle has launched since creation (bench.py "gpu_launches") */
 int64_t sal_launch_count(sal_handle_t h);
 
@@ -92,6 +101,18 @@ int64_t sal_launch_count(sal_handle_t h);
 int sal_klnmf_pass(sal_handle_t h, const void* X, const void* W, const void* H_in, void* H_out,
                    const void* w_kl, const void* w_lhalf, const void* h_scale, int flags,
                    void* Wnum, double* objective, void* per_sample, void* hsum, void* stream);
+
+/*
+ * One whole joint update in two launches (single-GPU fast path): the fused pass with UPDATE_H | WNUM
+ * (| OBJECTIVE of the INCOMING iterate when objective != NULL), then the fixed-order reduction of the per-CTA
+ * partials with the W epilogue of sal_w_epilogue fused into it.
+ *   replaces  update_WH  models/_utils_klnmf.py:281-361  (clip_given = 1)  and, with separate calls, nothing else.
+ * W_out must not alias W_in (H is updated with the OLD W, :345).  H_out may alias H_in.  Wnum [k][V] receives the
+ * raw numerator (useful for diagnostics).  n_given == k only updates H and copies W.
+ */
+int sal_klnmf_update(sal_handle_t h, const void* X, const void* W_in, void* W_out, const void* H_in, void* H_out,
+                     const void* w_kl, const void* w_lhalf, int n_given, int clip_given, void* Wnum,
+                     double* objective, void* stream);
 
 /*
  * W epilogue: W_out = clip(colnorm(W_in * Wnum)) with given signatures restored.

@@ -65,11 +65,20 @@ class Workspace:
         self.set_math(math)
 
     def set_math(self, math: str) -> None:
-        mode = {"fma": _lib.MATH_FMA, "tf32": _lib.MATH_TF32}.get(math)
+        mode = {"fma": _lib.MATH_FMA, "tf32": _lib.MATH_TF32, "tf32_always": _lib.MATH_TF32_ALWAYS}.get(math)
         if mode is None:
-            raise ValueError("math has to be 'fma' or 'tf32'.")
+            raise ValueError("math has to be 'fma', 'tf32' or 'tf32_always'.")
         _lib.check(self.lib.sal_set_math(self._h, mode), "sal_set_math")
         self.math = math
+
+    def set_timing(self, on: bool) -> None:
+        _lib.check(self.lib.sal_set_timing(self._h, int(bool(on))), "sal_set_timing")
+
+    def pass_timing(self) -> tuple[float, int]:
+        """(summed milliseconds, count) of the UPDATE_H | WNUM pass kernels since the last call (CUDA events)."""
+        ms, n = C.c_double(0.0), C.c_int64(0)
+        _lib.check(self.lib.sal_get_pass_timing(self._h, C.byref(ms), C.byref(n)), "sal_get_pass_timing")
+        return float(ms.value), int(n.value)
 
     def set_debug_buffer(self, buf) -> None:
         """Diagnostics of the tensor-core pass (sal_set_debug_buffer); ``None`` switches them off."""
@@ -141,6 +150,28 @@ class Workspace:
                 self._stream(),
             ),
             "sal_klnmf_pass",
+        )
+
+    def klnmf_update(self, X, W_in, W_out, H_in, H_out, n_given: int, clip_given: bool, Wnum, w_kl=None, w_lhalf=None, objective=None) -> None:
+        """Joint update in two launches: fused pass, then reduction + W epilogue (sal_klnmf_update)."""
+        V, D, k = self.V, self.D, self.k
+        _lib.check(
+            self.lib.sal_klnmf_update(
+                self._h,
+                self._ptr(X, D * V, "X"),
+                self._ptr(W_in, k * V, "W_in"),
+                self._ptr(W_out, k * V, "W_out"),
+                self._ptr(H_in, D * k, "H_in"),
+                self._ptr(H_out, D * k, "H_out"),
+                self._ptr(w_kl, D, "w_kl"),
+                self._ptr(w_lhalf, D, "w_lhalf"),
+                int(n_given),
+                int(bool(clip_given)),
+                self._ptr(Wnum, k * V, "Wnum"),
+                self._ptr(objective, 1, "objective", torch.float64),
+                self._stream(),
+            ),
+            "sal_klnmf_update",
         )
 
     def w_epilogue(self, W_in, Wnum, n_given: int, clip_given: bool, W_out) -> None:

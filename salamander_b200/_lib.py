@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsalamander_b200.so")
 
 SAL_F32, SAL_F64 = 0, 1
-MATH_FMA, MATH_TF32 = 0, 1
+MATH_FMA, MATH_TF32, MATH_TF32_ALWAYS = 0, 1, 2
 PASS_UPDATE_H, PASS_WNUM, PASS_OBJECTIVE, PASS_SAMPLEWISE, PASS_HSUM, PASS_POISSON = 1, 2, 4, 8, 16, 32
 
 _vp, _i, _i64, _d = C.c_void_p, C.c_int, C.c_int64, C.c_double
@@ -28,8 +28,11 @@ SYMBOLS = {
     "sal_destroy": (_i, [_vp]),
     "sal_set_math": (_i, [_vp, _i]),
     "sal_launch_count": (_i64, [_vp]),
+    "sal_set_timing": (_i, [_vp, _i]),
+    "sal_get_pass_timing": (_i, [_vp, C.POINTER(_d), C.POINTER(_i64)]),
     "sal_set_debug_buffer": (_i, [_vp, _vp]),
     "sal_klnmf_pass": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    "sal_klnmf_update": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "sal_w_epilogue": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),
     "sal_clip_counts": (_i, [_vp, _vp, _i64, _vp, _vp]),
     "sal_mvnmf_logdet": (_i, [_vp, _vp, _d, _vp, _vp]),

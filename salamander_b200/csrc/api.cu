@@ -14,6 +14,27 @@ void sal_set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+static bool timed_flags(int flags) { return (flags & (SAL_PASS_UPDATE_H | SAL_PASS_WNUM)) == (SAL_PASS_UPDATE_H | SAL_PASS_WNUM); }
+
+int sal_timing_begin(sal_ctx* c, int flags, cudaStream_t st) {
+    if (!c->timing || !timed_flags(flags)) return 0;
+    if (!c->ev) c->ev = new std::vector<cudaEvent_t>();
+    while (c->ev->size() < c->ev_used + 2) {
+        cudaEvent_t e;
+        SAL_CUDA(cudaEventCreate(&e));
+        c->ev->push_back(e);
+    }
+    SAL_CUDA(cudaEventRecord((*c->ev)[c->ev_used], st));
+    return 0;
+}
+
+int sal_timing_end(sal_ctx* c, int flags, cudaStream_t st) {
+    if (!c->timing || !timed_flags(flags)) return 0;
+    SAL_CUDA(cudaEventRecord((*c->ev)[c->ev_used + 1], st));
+    c->ev_used += 2;
+    return 0;
+}
+
 extern "C" {
 
 const char* sal_last_error(void) { return g_err; }
@@ -59,14 +80,18 @@ int sal_destroy(sal_handle_t h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
     cudaFree(h->partial_wnum), cudaFree(h->partial_obj), cudaFree(h->partial_hsum);
+    if (h->ev) {
+        for (cudaEvent_t e : *h->ev) cudaEventDestroy(e);
+        delete h->ev;
+    }
     delete h;
     return 0;
 }
 
 int sal_set_math(sal_handle_t h, int math_mode) {
     SAL_CHECK_ARG(h != nullptr, "handle is null");
-    SAL_CHECK_ARG(math_mode == SAL_MATH_FMA || math_mode == SAL_MATH_TF32, "unknown math mode");
-    if (math_mode == SAL_MATH_TF32 && h->dtype != SAL_F32) {
+    SAL_CHECK_ARG(math_mode == SAL_MATH_FMA || math_mode == SAL_MATH_TF32 || math_mode == SAL_MATH_TF32_ALWAYS, "unknown math mode");
+    if (math_mode != SAL_MATH_FMA && h->dtype != SAL_F32) {
         sal_set_error("SAL_MATH_TF32 needs an fp32 handle");
         return SAL_EINVAL;
     }
@@ -75,6 +100,28 @@ int sal_set_math(sal_handle_t h, int math_mode) {
 }
 
 int64_t sal_launch_count(sal_handle_t h) { return h ? h->launches : -1; }
+
+int sal_set_timing(sal_handle_t h, int on) {
+    SAL_CHECK_ARG(h != nullptr, "handle is null");
+    h->timing = on != 0;
+    h->ev_used = 0;
+    return 0;
+}
+
+int sal_get_pass_timing(sal_handle_t h, double* total_ms, int64_t* n_launches) {
+    SAL_CHECK_ARG(h && total_ms && n_launches, "null argument");
+    SAL_CUDA(cudaSetDevice(h->device));
+    double t = 0.0;
+    for (size_t i = 0; i + 1 < h->ev_used; i += 2) {
+        float ms = 0.f;
+        SAL_CUDA(cudaEventSynchronize((*h->ev)[i + 1]));
+        SAL_CUDA(cudaEventElapsedTime(&ms, (*h->ev)[i], (*h->ev)[i + 1]));
+        t += ms;
+    }
+    *total_ms = t, *n_launches = (int64_t)(h->ev_used / 2);
+    h->ev_used = 0;
+    return 0;
+}
 
 int sal_set_debug_buffer(sal_handle_t h, void* buf) {
     SAL_CHECK_ARG(h != nullptr, "handle is null");
@@ -108,7 +155,33 @@ int sal_klnmf_pass(sal_handle_t h, const void* X, const void* W, const void* H_i
     a.X = X, a.W = W, a.H_in = H_in, a.w_kl = w_kl, a.w_lhalf = w_lhalf, a.h_scale = h_scale;
     a.H_out = H_out, a.Wnum = Wnum, a.per_sample = per_sample, a.hsum = hsum, a.objective = objective;
     a.flags = flags;
-    if (h->math == SAL_MATH_TF32 && sal_pass_tf32_supported(h, a)) return sal_launch_pass_tf32(h, a, st);
+    if (h->math != SAL_MATH_FMA && sal_pass_tf32_supported(h, a)) return sal_launch_pass_tf32(h, a, st);
+    return sal_launch_pass_fma(h, a, st);
+}
+
+int sal_klnmf_update(sal_handle_t h, const void* X, const void* W_in, void* W_out, const void* H_in, void* H_out,
+                     const void* w_kl, const void* w_lhalf, int n_given, int clip_given, void* Wnum,
+                     double* objective, void* stream) {
+    SAL_CHECK_ARG(h != nullptr, "handle is null");
+    SAL_CHECK_ARG(W_in && W_out && Wnum && (h->D == 0 || (X && H_in && H_out)), "null argument");
+    SAL_CHECK_ARG(W_in != W_out, "W_out must not alias W_in (the H step reads the old W)");
+    SAL_CHECK_ARG(n_given >= 0 && n_given <= h->k, "n_given out of range");
+    SAL_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t es = h->dtype == SAL_F32 ? 4 : 8;
+    if (h->D == 0) {
+        SAL_CUDA(cudaMemcpyAsync(W_out, W_in, (size_t)h->k * h->V * es, cudaMemcpyDeviceToDevice, st));
+        SAL_CUDA(cudaMemsetAsync(Wnum, 0, (size_t)h->k * h->V * es, st));
+        if (objective) SAL_CUDA(cudaMemsetAsync(objective, 0, sizeof(double), st));
+        return 0;
+    }
+    PassArgs a;
+    a.X = X, a.W = W_in, a.H_in = H_in, a.w_kl = w_kl, a.w_lhalf = w_lhalf, a.h_scale = nullptr;
+    a.H_out = H_out, a.Wnum = Wnum, a.per_sample = nullptr, a.hsum = nullptr, a.objective = objective;
+    a.flags = SAL_PASS_UPDATE_H | (n_given < h->k ? SAL_PASS_WNUM : 0) | (objective ? SAL_PASS_OBJECTIVE : 0);
+    a.fuse_epilogue = n_given < h->k, a.n_given = n_given, a.clip_given = clip_given, a.W_out = W_out;
+    if (n_given >= h->k) SAL_CUDA(cudaMemcpyAsync(W_out, W_in, (size_t)h->k * h->V * es, cudaMemcpyDeviceToDevice, st));
+    if (h->math != SAL_MATH_FMA && sal_pass_tf32_supported(h, a)) return sal_launch_pass_tf32(h, a, st);
     return sal_launch_pass_fma(h, a, st);
 }
 

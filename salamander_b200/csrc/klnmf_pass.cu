@@ -159,7 +159,10 @@ __global__ void __launch_bounds__(NT, Cfg<T>::OCC) klnmf_pass_kernel(PassParams<
                     for (int e = 0; e < VEC; ++e) h[j + e] = t.v[e], hn[j + e] = (T)0;
                 }
                 const T wk = p.w_kl ? p.w_kl[d] : (T)1;
-                T kl = (T)0;
+                // x ln(x/wh) - x + wh is evaluated as fma(x, ln r, wh - x): the cancelling pair (wh - x) is formed first
+                // (exact within a factor of two), so the term keeps ~1e-7 relative accuracy instead of 1e-7 * x; terms are
+                // summed in double.  The fit's convergence test (tol 1e-7, signature_nmf.py:376) sees this number.
+                double kl = 0.0;
                 for (int v0 = 0; v0 < V; v0 += VEC) {
                     const V16 x = *reinterpret_cast<const V16*>(xrow + v0);
                     V16 r;
@@ -186,20 +189,14 @@ __global__ void __launch_bounds__(NT, Cfg<T>::OCC) klnmf_pass_kernel(PassParams<
 #pragma unroll
                         for (int j = 0; j < KP; ++j) hn[j] = sal_fma(w[j], rr, hn[j]);
                         r.v[e] = rr * wk;
-                        if (do_kl && in) {
-                            if (xv != (T)0) kl += xv * sal_log(rr) - xv;
-                            kl += wh;
-                        }
-                        if (do_pois && in) {
-                            if (wh != (T)0) kl += xv * sal_log(wh);
-                            kl -= wh;
-                        }
+                        if (do_kl && in) kl += (double)(xv != (T)0 ? sal_fma(xv, sal_log(rr), wh - xv) : wh);
+                        if (do_pois && in) kl += (double)(wh != (T)0 ? sal_fma(xv, sal_log(wh), -wh) : -wh);
                     }
                     *reinterpret_cast<V16*>(xrow + v0) = r;
                 }
-                if (p.flags & SAL_PASS_SAMPLEWISE) p.per_sample[d] = kl;
+                if (p.flags & SAL_PASS_SAMPLEWISE) p.per_sample[d] = (T)kl;
                 if (p.flags & (SAL_PASS_OBJECTIVE | SAL_PASS_POISSON)) {
-                    double o = (double)kl * (double)wk;
+                    double o = kl * (double)wk;
                     if (p.w_lhalf && !do_pois) {
                         T sq = (T)0;
 #pragma unroll
@@ -291,36 +288,65 @@ __global__ void __launch_bounds__(NT, Cfg<T>::OCC) klnmf_pass_kernel(PassParams<
     }
 }
 
-// Fixed-order reduction of the per-CTA partials (deterministic).
+// Fixed-order reduction of the per-CTA partials (deterministic), optionally followed by the W epilogue.
+//   blocks 0 .. k-1 : signature j.  Thread (part, v) sums the partials b = part, part + 4, ... of Wnum[j][v] in double;
+//                     the four parts are added in order.  With fuse_epilogue the block then applies
+//                     W_out[j] = clip(colnorm(W[j] * Wnum[j])) exactly as w_epilogue_kernel does.
+//   block k         : objective and row sums of H.
+constexpr int FIN_PARTS = 4, FIN_THREADS = FIN_PARTS * VP;
 template <typename T>
-__global__ void __launch_bounds__(128) klnmf_reduce_kernel(const T* partial_wnum, const double* partial_obj,
-                                                           const double* partial_hsum, int n_part, int KP,
-                                                           int k, int V, int flags, T* Wnum, double* objective,
-                                                           T* hsum) {
-    const int n_w = (flags & SAL_PASS_WNUM) ? k * V : 0;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_w) {
-        const int j = i / V, v = i - j * V;
+__global__ void __launch_bounds__(FIN_THREADS) klnmf_finish_kernel(const T* partial_wnum, const double* partial_obj,
+                                                                  const double* partial_hsum, int n_part, int KP, int k,
+                                                                  int V, int flags, T* Wnum, double* objective, T* hsum,
+                                                                  int fuse_epilogue, const T* W_in, T* W_out, int n_given,
+                                                                  int clip_given) {
+    __shared__ double s_part[FIN_PARTS][VP];
+    __shared__ double s_red[VP / 32];
+    const int j = blockIdx.x, tid = threadIdx.x;
+    if (j < k) {
+        if (!(flags & SAL_PASS_WNUM)) return;
+        const int part = tid / VP, v = tid - part * VP;
         double s = 0.0;
-        const T* src = partial_wnum + (size_t)j * VP + v;
-#pragma unroll 8
-        for (int b = 0; b < n_part; ++b) s += (double)src[(size_t)b * KP * VP];
-        Wnum[i] = (T)s;
-    }
-    if (blockIdx.x == gridDim.x - 1) {
-        if ((flags & (SAL_PASS_OBJECTIVE | SAL_PASS_POISSON)) && threadIdx.x < 32) {
-            double s = 0.0;
-            for (int b = threadIdx.x; b < n_part; b += 32) s += partial_obj[b];
+        if (v < V) {
+            const T* src = partial_wnum + (size_t)j * VP + v;
+#pragma unroll 4
+            for (int b = part; b < n_part; b += FIN_PARTS) s += (double)src[(size_t)b * KP * VP];
+        }
+        s_part[part][v] = s;
+        __syncthreads();
+        if (part != 0) return;
+        const bool in = v < V;
+        const double num = (s_part[0][v] + s_part[1][v]) + (s_part[2][v] + s_part[3][v]);
+        if (in) Wnum[(size_t)j * V + v] = (T)num;
+        if (!fuse_epilogue) return;
+        // same arithmetic as w_epilogue_kernel on the value just stored (rounded to T like the unfused path)
+        const double w = in ? (double)W_in[(size_t)j * V + v] : 0.0;
+        const double val = in ? w * (double)(T)num : 0.0;
+        double t = val;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (threadIdx.x == 0) *objective = s;
-        }
-        if ((flags & SAL_PASS_HSUM) && threadIdx.x >= 64 && threadIdx.x - 64 < k) {
-            const int j = threadIdx.x - 64;
-            double s = 0.0;
-            for (int b = 0; b < n_part; ++b) s += partial_hsum[(size_t)b * SAL_KMAX + j];
-            hsum[j] = (T)s;
-        }
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if ((v & 31) == 0) s_red[v >> 5] = t;
+        asm volatile("bar.sync 1, %0;" ::"r"(VP));  // the 96 threads of part 0
+        t = s_red[0] + s_red[1] + s_red[2];
+        if (!in) return;
+        double out = val / t;
+        if (j < n_given) out = w;
+        if (clip_given || j >= n_given) out = fmax(out, (double)SAL_EPS_F32);
+        W_out[(size_t)j * V + v] = (T)out;
+        return;
+    }
+    if ((flags & (SAL_PASS_OBJECTIVE | SAL_PASS_POISSON)) && tid < 32) {
+        double s = 0.0;
+        for (int b = tid; b < n_part; b += 32) s += partial_obj[b];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (tid == 0) *objective = s;
+    }
+    if ((flags & SAL_PASS_HSUM) && tid >= 64 && tid - 64 < k) {
+        const int jj = tid - 64;
+        double s = 0.0;
+        for (int b = 0; b < n_part; ++b) s += partial_hsum[(size_t)b * SAL_KMAX + jj];
+        hsum[jj] = (T)s;
     }
 }
 
@@ -389,8 +415,10 @@ int launch_pass_t(sal_ctx* c, const PassArgs& a, cudaStream_t st) {
     p.vec_h = (c->k % C::VEC == 0) && (((uintptr_t)a.H_out) % 16 == 0);
     const int64_t n_tiles = (c->D + C::TS - 1) / C::TS;
     const int grid = (int)(n_tiles < c->grid_pass ? n_tiles : c->grid_pass);
+    if (int e = sal_timing_begin(c, a.flags, st)) return e;
     klnmf_pass_kernel<T, KP><<<grid, NT, smem, st>>>(p);
     SAL_CUDA(cudaGetLastError());
+    if (int e = sal_timing_end(c, a.flags, st)) return e;
     c->launches++;
     if (int e = sal_launch_pass_reduce(c, a, grid, st)) return e;
     return 0;
@@ -411,15 +439,17 @@ int launch_pass_k(sal_ctx* c, const PassArgs& a, cudaStream_t st) {
 // Fixed-order sum of the per-CTA partials left by either flavour of the pass (n_part = its grid size).
 int sal_launch_pass_reduce(sal_ctx* c, const PassArgs& a, int n_part, cudaStream_t st) {
     if (!(a.flags & (SAL_PASS_WNUM | SAL_PASS_OBJECTIVE | SAL_PASS_POISSON | SAL_PASS_HSUM))) return 0;
-    const int n_w = (a.flags & SAL_PASS_WNUM) ? c->k * c->V : 0;
-    const int rb = (n_w + 127) / 128 + 1;
+    const bool need_tail = a.flags & (SAL_PASS_OBJECTIVE | SAL_PASS_POISSON | SAL_PASS_HSUM);
+    const int grid = c->k + (need_tail ? 1 : 0);
+    const int fuse = a.fuse_epilogue && (a.flags & SAL_PASS_WNUM);
     if (c->dtype == SAL_F32)
-        klnmf_reduce_kernel<float><<<rb, 128, 0, st>>>((const float*)c->partial_wnum, c->partial_obj, c->partial_hsum, n_part,
-                                                      c->KP, c->k, c->V, a.flags, (float*)a.Wnum, a.objective, (float*)a.hsum);
+        klnmf_finish_kernel<float><<<grid, FIN_THREADS, 0, st>>>(
+            (const float*)c->partial_wnum, c->partial_obj, c->partial_hsum, n_part, c->KP, c->k, c->V, a.flags, (float*)a.Wnum,
+            a.objective, (float*)a.hsum, fuse, (const float*)a.W, (float*)a.W_out, a.n_given, a.clip_given);
     else
-        klnmf_reduce_kernel<double><<<rb, 128, 0, st>>>((const double*)c->partial_wnum, c->partial_obj, c->partial_hsum,
-                                                       n_part, c->KP, c->k, c->V, a.flags, (double*)a.Wnum, a.objective,
-                                                       (double*)a.hsum);
+        klnmf_finish_kernel<double><<<grid, FIN_THREADS, 0, st>>>(
+            (const double*)c->partial_wnum, c->partial_obj, c->partial_hsum, n_part, c->KP, c->k, c->V, a.flags, (double*)a.Wnum,
+            a.objective, (double*)a.hsum, fuse, (const double*)a.W, (double*)a.W_out, a.n_given, a.clip_given);
     SAL_CUDA(cudaGetLastError());
     c->launches++;
     return 0;

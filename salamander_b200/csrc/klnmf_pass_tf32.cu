@@ -239,10 +239,7 @@ __device__ __forceinline__ void quotient_box(uint32_t (&v)[32], uint32_t rowbase
         for (int e = 0; e < 8; ++e) {
             const float wh = __uint_as_float(v[8 * m + e]);
             const float r = xv[e] * rcp_approx(wh);
-            if (DO_KL) {
-                if (xv[e] != 0.f) kl += xv[e] * logf(r) - xv[e];
-                kl += wh;
-            }
+            if (DO_KL) kl += xv[e] != 0.f ? fmaf(xv[e], logf(r), wh - xv[e]) : wh;  // cancelling pair (wh - x) first
             // round-to-nearest tf32 = add half an ulp; the MMA ignores the 13 low mantissa bits, no need to mask them
             rr[e] = __uint_as_float(__float_as_uint(r) + 0x1000u);
             v[8 * m + e] = __float_as_uint(rr[e]);
@@ -346,7 +343,7 @@ klnmf_pass_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
     const uint32_t tmem = *tmem_slot;
 
     double obj_acc = 0.0;
-    const bool tl = p.dbg != nullptr && blockIdx.x == 0;  // diagnostics timeline
+    const bool tl = p.dbg != nullptr && blockIdx.x == 1;  // diagnostics timeline (CTA 1: CTA 0 is busy dumping its first tile)
 
     if (warp == 0) {
         // ================= TMA producer =================
@@ -690,8 +687,10 @@ int launch_tc_v(sal_ctx* c, const PassArgs& a, cudaStream_t st) {
     p.D = c->D, p.k = c->k, p.flags = a.flags;
     p.n_tiles = (int)((c->D + TILE - 1) / TILE);
     const int grid = p.n_tiles < c->n_sm ? p.n_tiles : c->n_sm;
+    if (int e = sal_timing_begin(c, a.flags, st)) return e;
     klnmf_pass_tc_kernel<KP8, DO_R, DO_KL><<<grid, NTHREADS, q.total, st>>>(mapX, mapH, mapHout, p);
     SAL_CUDA(cudaGetLastError());
+    if (int e = sal_timing_end(c, a.flags, st)) return e;
     c->launches++;
     return sal_launch_pass_reduce(c, a, grid, st);
 }
@@ -712,6 +711,7 @@ bool sal_pass_tf32_supported(const sal_ctx* c, const PassArgs& a) {
     if ((a.flags & ~allowed) || a.w_kl || a.w_lhalf || a.h_scale) return false;
     if (((uintptr_t)a.X | (uintptr_t)a.H_in | (uintptr_t)a.H_out) & 15) return false;
     if (c->D >= (int64_t)1 << 31) return false;
+    if (c->math != SAL_MATH_TF32_ALWAYS && c->D < SAL_TF32_MIN_SAMPLES) return false;
     return true;
 }
 

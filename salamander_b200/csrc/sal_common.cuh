@@ -5,6 +5,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <vector>
+
 #include "../../include/salamander_b200.h"
 
 #define SAL_VMAX 96   // features per sample handled by the kernels (SBS-96 / ID-83 / SV-32)
@@ -21,7 +23,14 @@ struct sal_ctx {
     double* partial_hsum;  // [grid_pass][SAL_KMAX]
     void* dbg;             // optional diagnostics buffer of the tensor-core pass (sal_set_debug_buffer)
     int64_t launches;
+    int timing;                                       // sal_set_timing
+    std::vector<cudaEvent_t>* ev;                     // event pairs around the UPDATE_H | WNUM pass kernels
+    size_t ev_used;
 };
+
+// bracket a pass kernel with events when timing is on (no-ops otherwise)
+int sal_timing_begin(sal_ctx* c, int flags, cudaStream_t st);
+int sal_timing_end(sal_ctx* c, int flags, cudaStream_t st);
 
 void sal_set_error(const char* fmt, ...);
 
@@ -50,6 +59,9 @@ struct PassArgs {
     void *H_out, *Wnum, *per_sample, *hsum;
     double* objective;
     int flags;
+    // optional W epilogue fused into the reduction of the partials (sal_klnmf_update)
+    int fuse_epilogue = 0, n_given = 0, clip_given = 0;
+    void* W_out = nullptr;
 };
 int sal_launch_pass_fma(sal_ctx* c, const PassArgs& a, cudaStream_t st);
 int sal_launch_pass_tf32(sal_ctx* c, const PassArgs& a, cudaStream_t st);  // tcgen05 path (fp32 only)

@@ -53,9 +53,19 @@ class KLNMF(StandardNMF):
             return st.objective_value()
 
     def _update_parameters(self, given_parameters: dict[str, Any] | None = None) -> None:
-        """One joint multiplicative update of W and H (reference klnmf.py:86-106 -> update_WH)."""
+        """One joint multiplicative update of W and H (reference klnmf.py:86-106 -> update_WH).
+
+        Single GPU: two launches (sal_klnmf_update: fused pass, then reduction + W epilogue).  Several GPUs: the pass
+        leaves this rank's numerator, the 96 x k numerators are summed over the ranks and every rank applies the
+        same epilogue."""
         n_given = self._n_given(given_parameters)
         with self._resident() as st:
+            if st.world == 1:
+                st.ws.klnmf_update(
+                    st.X, st.W, st.W_next, st.H, st.H, n_given, True, st.Wnum, w_kl=st.weights["kl"], w_lhalf=st.weights["lhalf"]
+                )
+                st.W, st.W_next = st.W_next, st.W
+                return
             flags = PASS_UPDATE_H | (PASS_WNUM if n_given < st.k else 0)
             st.ws.klnmf_pass(
                 st.X,

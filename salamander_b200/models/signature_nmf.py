@@ -42,7 +42,7 @@ class SignatureNMF(ABC):
         shard_input: bool = True,
     ):
         value_checker("init_method", init_method, _INIT_METHODS)
-        value_checker("math", math, ("fma", "tf32"))
+        value_checker("math", math, ("fma", "tf32", "tf32_always"))
         self.n_signatures = n_signatures
         self.init_method = init_method
         self.min_iterations = min_iterations

@@ -57,6 +57,7 @@ class StandardState:
             model._clip_on_device = False
         self.W = self.upload(W_host)
         self.H = self.upload(H_host[self.lo : self.hi])
+        self.W_next = torch.empty_like(self.W)  # the joint update writes W here (H needs the old W), then they swap
         self.Wnum = torch.zeros((self.k, self.V), dtype=dt, device=dev)
         self.obj = torch.zeros(1, dtype=torch.float64, device=dev)
         self.weights: dict[str, Any] = {}

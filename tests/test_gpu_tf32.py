@@ -37,7 +37,7 @@ def _problem(D, k, seed, dev):
 def _run(X, W, H, flags, debug=False):
     dev = X.device
     D, k = H.shape
-    ws = Workspace(96, D, k, torch.float32, dev, math="tf32")
+    ws = Workspace(96, D, k, torch.float32, dev, math="tf32_always")
     Xf, Wf, Hf = X.float().contiguous(), W.float().contiguous(), H.float().contiguous()
     Hout = torch.full_like(Hf, -1.0)
     Wnum = torch.full_like(Wf, -1.0)
@@ -102,7 +102,7 @@ def test_deterministic_and_in_place():
     b = _run(X, W, H, PASS_UPDATE_H | PASS_WNUM)
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
     # H_out aliasing H_in (how the models call it)
-    ws = Workspace(96, 70_001, 20, torch.float32, dev, math="tf32")
+    ws = Workspace(96, 70_001, 20, torch.float32, dev, math="tf32_always")
     Hf = H.float().contiguous()
     Wnum = torch.empty((20, 96), dtype=torch.float32, device=dev)
     ws.klnmf_pass(X.float().contiguous(), W.float().contiguous(), Hf, PASS_UPDATE_H | PASS_WNUM, H_out=Hf, Wnum=Wnum)
@@ -141,4 +141,30 @@ def test_fit_meets_fp32_criteria(tag):
     print(f"{tag}: final KL {hist[-1]:.6f} vs reference {ref[-1]:.6f} (rel {abs(hist[-1] - ref[-1]) / ref[-1]:.2e}), "
           f"{len(hist)} vs {len(ref)} checkpoints, min cosine {cos.min():.7f}")
     assert abs(hist[-1] - ref[-1]) / abs(ref[-1]) < 1e-4
+    assert cos.min() >= 0.9999
+
+
+def test_large_fit_tf32_matches_float64_fit():
+    """At a sample count where the tensor-core path is actually taken (D >= SAL_TF32_MIN_SAMPLES) a whole fit
+    in tf32 mode is compared with the float64 fit (itself pinned to the live reference at 1e-9) from the same
+    start: same stopping behaviour, final KL within 1e-4 relative, signature cosine >= 0.9999."""
+    import bench
+
+    D, k = 20_000, 8
+    X = bench.synth_rows(0, D, k).astype(np.float64)
+    W0, H0 = bench.init_rows(X, 0, k)
+    fits = {}
+    for dtype, math in (("float64", "fma"), ("float32", "tf32")):
+        model = sal.models.KLNMF(n_signatures=k, init_method="custom", min_iterations=500, max_iterations=4000, dtype=dtype, math=math)
+        model.fit(AnnData(X.copy()), init_kwargs={"signatures_mat": W0.copy(), "exposures_mat": H0.copy()})
+        fits[dtype] = model
+    a, b = fits["float64"], fits["float32"]
+    ha, hb = np.array(a.history["objective_function"]), np.array(b.history["objective_function"])
+    A, B = a.asignatures.X, b.asignatures.X
+    cos = np.sum(A * B, axis=1) / (np.linalg.norm(A, axis=1) * np.linalg.norm(B, axis=1))
+    n = min(len(ha), len(hb))
+    print(f"fp64: {a.n_iterations} iterations, KL {ha[-1]:.4f}; tf32: {b.n_iterations} iterations, KL {hb[-1]:.4f}; "
+          f"max rel gap over the common history {np.max(np.abs(ha[:n] - hb[:n]) / ha[:n]):.2e}; min cosine {cos.min():.7f}")
+    assert np.max(np.abs(ha[:n] - hb[:n]) / ha[:n]) < 1e-4
+    assert abs(ha[-1] - hb[-1]) / ha[-1] < 1e-4
     assert cos.min() >= 0.9999
