@@ -59,6 +59,7 @@ class Workspace:
         self.V, self.D, self.k = int(V), int(D_local), int(k)
         self.dtype, self.device = dtype, device
         self._h = C.c_void_p()
+        self.timing = False
         _lib.check(
             self.lib.sal_create(C.byref(self._h), self.V, self.D, self.k, _DTYPES[dtype], device.index), "sal_create"
         )
@@ -73,6 +74,7 @@ class Workspace:
 
     def set_timing(self, on: bool) -> None:
         _lib.check(self.lib.sal_set_timing(self._h, int(bool(on))), "sal_set_timing")
+        self.timing = bool(on)
 
     def pass_timing(self) -> tuple[float, int]:
         """(summed milliseconds, count) of the UPDATE_H | WNUM pass kernels since the last call (CUDA events)."""

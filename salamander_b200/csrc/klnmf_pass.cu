@@ -289,11 +289,11 @@ __global__ void __launch_bounds__(NT, Cfg<T>::OCC) klnmf_pass_kernel(PassParams<
 }
 
 // Fixed-order reduction of the per-CTA partials (deterministic), optionally followed by the W epilogue.
-//   blocks 0 .. k-1 : signature j.  Thread (part, v) sums the partials b = part, part + 4, ... of Wnum[j][v] in double;
-//                     the four parts are added in order.  With fuse_epilogue the block then applies
+//   blocks 0 .. k-1 : signature j.  Thread (part, v) sums the partials b = part, part + 8, ... of Wnum[j][v] in double;
+//                     the eight parts are added in a fixed order.  With fuse_epilogue the block then applies
 //                     W_out[j] = clip(colnorm(W[j] * Wnum[j])) exactly as w_epilogue_kernel does.
 //   block k         : objective and row sums of H.
-constexpr int FIN_PARTS = 4, FIN_THREADS = FIN_PARTS * VP;
+constexpr int FIN_PARTS = 8, FIN_THREADS = FIN_PARTS * VP;
 template <typename T>
 __global__ void __launch_bounds__(FIN_THREADS) klnmf_finish_kernel(const T* partial_wnum, const double* partial_obj,
                                                                   const double* partial_hsum, int n_part, int KP, int k,
@@ -309,14 +309,15 @@ __global__ void __launch_bounds__(FIN_THREADS) klnmf_finish_kernel(const T* part
         double s = 0.0;
         if (v < V) {
             const T* src = partial_wnum + (size_t)j * VP + v;
-#pragma unroll 4
+#pragma unroll 8
             for (int b = part; b < n_part; b += FIN_PARTS) s += (double)src[(size_t)b * KP * VP];
         }
         s_part[part][v] = s;
         __syncthreads();
         if (part != 0) return;
         const bool in = v < V;
-        const double num = (s_part[0][v] + s_part[1][v]) + (s_part[2][v] + s_part[3][v]);
+        const double num = ((s_part[0][v] + s_part[1][v]) + (s_part[2][v] + s_part[3][v])) +
+                           ((s_part[4][v] + s_part[5][v]) + (s_part[6][v] + s_part[7][v]));
         if (in) Wnum[(size_t)j * V + v] = (T)num;
         if (!fuse_epilogue) return;
         // same arithmetic as w_epilogue_kernel on the value just stored (rounded to T like the unfused path)

@@ -10,6 +10,7 @@ from __future__ import annotations
 from typing import Any, Literal
 
 import numpy as np
+import torch
 
 from .. import _dist
 from .._device import PASS_OBJECTIVE, PASS_UPDATE_H, PASS_WNUM
@@ -34,6 +35,7 @@ class KLNMF(StandardNMF):
         super().__init__(n_signatures, init_method, min_iterations, max_iterations, conv_test_freq, tol, **device_kwargs)
         self.weights_kl = None
         self.weights_lhalf = None
+        self.use_graphs = True  # capture the periods of the fit loop in CUDA graphs (see _fit_loop)
 
     @property
     def objective(self) -> Literal["minimize", "maximize"]:
@@ -80,6 +82,127 @@ class KLNMF(StandardNMF):
             if n_given < st.k:
                 _dist.allreduce_sum_(st.Wnum)
                 st.ws.w_epilogue(st.W, st.Wnum, n_given, True, st.W)
+
+    # ---- device-side fit driver ------------------------------------------------------------------
+    def _one_update(self, st, n_given, W_in, W_out, H_in, H_out, objective=None) -> None:
+        """Joint update (W_in, H_in) -> (W_out, H_out); ``objective`` (device scalar) receives the objective of
+        the INCOMING iterate.  Single GPU: two launches.  Several GPUs: pass, reduction, all-reduce of the 96 x k
+        numerator (and of the objective scalar), W epilogue."""
+        wk, wl = st.weights["kl"], st.weights["lhalf"]
+        if st.world == 1:
+            st.ws.klnmf_update(st.X, W_in, W_out, H_in, H_out, n_given, True, st.Wnum, w_kl=wk, w_lhalf=wl, objective=objective)
+            return
+        flags = PASS_UPDATE_H | (PASS_WNUM if n_given < st.k else 0) | (PASS_OBJECTIVE if objective is not None else 0)
+        st.ws.klnmf_pass(st.X, W_in, H_in, flags, H_out=H_out, w_kl=wk, w_lhalf=wl, Wnum=st.Wnum, objective=objective)
+        if n_given < st.k:
+            _dist.allreduce_sum_(st.Wnum)
+        if objective is not None:
+            _dist.allreduce_sum_(objective)
+        st.ws.w_epilogue(W_in, st.Wnum, n_given, True, W_out)
+
+    def _fit_loop(self, given_parameters, verbose, verbosity_freq):
+        """Same iterates, history and stopping iteration as the reference loop (signature_nmf.py:361-380), run in
+        periods of ``conv_test_freq`` updates:
+
+        * the objective of iteration n is produced by the fused pass of update n + 1 (it streams X anyway), not by a
+          separate pass over X;
+        * the period's updates are speculative: they write into spare buffers, state n stays untouched until the
+          host has seen the objective, and the period is dropped if the convergence test says the fit ended at n;
+        * each period is two CUDA graphs (update n + 1 with the objective read-back | the remaining updates), so the
+          host issues two launches per period and the GPU never waits for Python.
+        """
+        st = self._dev
+        freq, max_it = int(self.conv_test_freq), int(self.max_iterations)
+        if freq < 3:
+            return super()._fit_loop(given_parameters, verbose, verbosity_freq)
+        n_given = self._n_given(given_parameters)
+        # spare buffers, pinned read-back slot and captured graphs live with the device state, so that a second
+        # fit loop on the same state (bench.py: warm-up, then the timed run) replays instead of re-capturing
+        fl = st.fit_loop
+        if not fl or not any(w is st.W for w in fl["Ws"]) or not any(h is st.H for h in fl["Hs"]) or fl["n_given"] != n_given:
+            fl = st.fit_loop = {
+                "Ws": [st.W, st.W_next, torch.empty_like(st.W)],
+                "Hs": [st.H, torch.empty_like(st.H)],
+                "obj_host": torch.zeros(1, dtype=torch.float64).pin_memory(),
+                "graphs": {},
+                "periods": 0,
+                "n_given": n_given,
+            }
+        Ws, Hs, obj_host, graphs = fl["Ws"], fl["Hs"], fl["obj_host"], fl["graphs"]
+        seen = torch.cuda.Event()
+        use_graphs = self.use_graphs and not st.ws.timing
+
+        def plan(wi, hi, L):
+            """Buffer indices of the L updates of a period that starts from (Ws[wi], Hs[hi])."""
+            others = [j for j in range(3) if j != wi]
+            steps, w_prev, h_other = [], wi, 1 - hi
+            for u in range(L):
+                w_out = others[u % 2]
+                steps.append((w_prev, w_out, hi if u == 0 else h_other, h_other))
+                w_prev = w_out
+            return steps, w_prev, h_other
+
+        def run_head(step):
+            self._one_update(st, n_given, Ws[step[0]], Ws[step[1]], Hs[step[2]], Hs[step[3]], objective=st.obj)
+            obj_host.copy_(st.obj, non_blocking=True)
+
+        def run_tail(steps):
+            for step in steps:
+                self._one_update(st, n_given, Ws[step[0]], Ws[step[1]], Hs[step[2]], Hs[step[3]])
+
+        def launch(wi, hi, L, periods_done):
+            steps, w_end, h_end = plan(wi, hi, L)
+            key = (wi, hi, L)
+            if use_graphs and periods_done >= 2 and key not in graphs:
+                # every kernel variant and the NCCL communicator have been exercised by the eager periods
+                torch.cuda.synchronize(st.device)
+                g_head, g_tail = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g_head):
+                    run_head(steps[0])
+                with torch.cuda.graph(g_tail):
+                    run_tail(steps[1:])
+                graphs[key] = (g_head, g_tail)
+            if use_graphs and key in graphs:
+                graphs[key][0].replay()
+                seen.record()
+                graphs[key][1].replay()
+            else:
+                run_head(steps[0])
+                seen.record()
+                run_tail(steps[1:])
+            return w_end, h_end
+
+        of_values: list[float] = []
+        n, periods = 0, fl["periods"]
+        wi = next(j for j, w in enumerate(Ws) if w is st.W)
+        hi = next(j for j, h in enumerate(Hs) if h is st.H)
+        while True:
+            L = min(freq, max_it - n)
+            if L <= 0:  # n == max_iterations, a multiple of conv_test_freq: the reference still evaluates the objective
+                st.W, st.H = Ws[wi], Hs[hi]
+                of_values.append(self.objective_function())
+                break
+            w_end, h_end = launch(wi, hi, L, periods)
+            periods += 1
+            seen.synchronize()
+            of_values.append(float(obj_host.item()))
+            if n > 0:
+                rel_change = np.abs(of_values[-2] - of_values[-1]) / np.abs(of_values[-2])
+                if bool(rel_change < self.tol and n >= self.min_iterations):
+                    break  # the fit ended at iteration n; the speculative period is not adopted
+            wi, hi = w_end, h_end
+            for it in range(n + 1, n + L + 1):
+                if verbose and it % verbosity_freq == 0:
+                    print(f"iteration: {it}; objective: {of_values[-1]:.2f}")
+            n += L
+            if n >= max_it and n % freq != 0:
+                break
+        torch.cuda.current_stream(st.device).synchronize()
+        st.W, st.H = Ws[wi], Hs[hi]
+        st.W_next = Ws[(wi + 1) % 3]
+        fl["periods"] = periods
+        self.launch_stats = {"graphs": 2 * len(graphs), "periods": periods}
+        return of_values, n
 
     def _check_weights(self, weights: np.ndarray, name: str = "weights") -> None:
         """Type, shape and sign of per-sample weights (reference klnmf.py:108-126)."""

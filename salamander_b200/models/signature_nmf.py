@@ -179,6 +179,24 @@ class SignatureNMF(ABC):
     def _resident(self):
         return SignatureNMF._Resident(self)
 
+    def _fit_loop(self, given_parameters, verbose, verbosity_freq) -> tuple[list[float], int]:
+        """The reference's iteration / convergence logic (signature_nmf.py:361-380); returns (of_values, n)."""
+        of_values = [self.objective_function()]
+        n_iteration = 0
+        converged = False
+        while not converged:
+            n_iteration += 1
+            if verbose and n_iteration % verbosity_freq == 0:
+                print(f"iteration: {n_iteration}; objective: {of_values[-1]:.2f}")
+            self._update_parameters(given_parameters)
+            if n_iteration % self.conv_test_freq == 0:
+                prev = of_values[-1]
+                of_values.append(self.objective_function())
+                rel_change = np.abs(prev - of_values[-1]) / np.abs(prev)
+                converged = bool(rel_change < self.tol and n_iteration >= self.min_iterations)
+            converged |= n_iteration >= self.max_iterations
+        return of_values, n_iteration
+
     # ---- fit (reference signature_nmf.py:315-385) ------------------------------------------
     def fit(
         self,
@@ -197,20 +215,7 @@ class SignatureNMF(ABC):
         with self._resident():
             self._in_fit = True
             try:
-                of_values = [self.objective_function()]
-                n_iteration = 0
-                converged = False
-                while not converged:
-                    n_iteration += 1
-                    if verbose and n_iteration % verbosity_freq == 0:
-                        print(f"iteration: {n_iteration}; objective: {of_values[-1]:.2f}")
-                    self._update_parameters(given_parameters)
-                    if n_iteration % self.conv_test_freq == 0:
-                        prev = of_values[-1]
-                        of_values.append(self.objective_function())
-                        rel_change = np.abs(prev - of_values[-1]) / np.abs(prev)
-                        converged = bool(rel_change < self.tol and n_iteration >= self.min_iterations)
-                    converged |= n_iteration >= self.max_iterations
+                of_values, n_iteration = self._fit_loop(given_parameters, verbose, verbosity_freq)
                 self.n_iterations = n_iteration
             finally:
                 self._in_fit = False

@@ -61,6 +61,7 @@ class StandardState:
         self.Wnum = torch.zeros((self.k, self.V), dtype=dt, device=dev)
         self.obj = torch.zeros(1, dtype=torch.float64, device=dev)
         self.weights: dict[str, Any] = {}
+        self.fit_loop: dict[str, Any] = {}  # spare buffers / CUDA graphs of the period-wise fit driver (KLNMF._fit_loop)
 
     def upload(self, host) -> torch.Tensor:
         """Host array -> contiguous device tensor of the model dtype (async DMA when the array is pinned)."""

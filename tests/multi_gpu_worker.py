@@ -1,0 +1,81 @@
+"""
+Worker of tests/test_gpu_multi.py (launched with torchrun, one rank per GPU): sample-sharded KLNMF / MvNMF fits
+must reproduce the single-process trajectories of the live reference (tests/golden/trajectories) -- the only
+exchange per iteration is the all-reduce of the 96 x k numerator (+ scalars), SURVEY.md 8(e).
+"""
+import os
+import sys
+
+import numpy as np
+import pandas as pd
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import salamander_b200 as sal  # noqa: E402
+from salamander_b200 import AnnData  # noqa: E402
+
+rank, local = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+world = dist.get_world_size()
+TRAJ = os.path.join(ROOT, "tests", "golden", "trajectories")
+
+
+def pcawg():
+    counts = pd.read_csv(os.path.join(ROOT, "salamander_b200", "data", "pcawg_breast_sbs.csv"), index_col=0)
+    return AnnData(counts.T)
+
+
+z = np.load(os.path.join(TRAJ, "klnmf_pcawg_k5_seed0.npz"))
+model = sal.models.KLNMF(n_signatures=5, init_method="random", dtype="float64", device=f"cuda:{local}")
+model.fit(pcawg(), init_kwargs={"seed": int(z["seed"])})
+hist = np.array(model.history["objective_function"])
+assert len(hist) == len(z["history"]), (len(hist), len(z["history"]))
+assert np.allclose(hist, z["history"], rtol=1e-9, atol=0), np.max(np.abs(hist - z["history"]) / z["history"])
+assert np.allclose(model.asignatures.X, z["W"], rtol=1e-6, atol=1e-12)
+assert model.adata.obsm["exposures"].shape == (192, 5)
+assert np.allclose(model.adata.obsm["exposures"], z["H"], rtol=1e-6, atol=1e-9)
+
+z = np.load(os.path.join(TRAJ, "mvnmf_pcawg_k3_lam50.npz"))
+m2 = sal.models.MvNMF(n_signatures=3, init_method="random", lam=50.0, delta=0.5, min_iterations=300, max_iterations=300,
+                      dtype="float64", device=f"cuda:{local}")
+m2.fit(pcawg(), init_kwargs={"seed": int(z["seed"])})
+h2 = np.array(m2.history["objective_function"])
+assert np.allclose(h2, z["history"], rtol=1e-9, atol=0), np.max(np.abs(h2 - z["history"]) / z["history"])
+assert np.allclose(m2.asignatures.X, z["W"], rtol=1e-6, atol=1e-12)
+
+# replicas stay bit-identical
+W = torch.as_tensor(model.asignatures.X).cuda()
+ref = W.clone()
+dist.broadcast(ref, src=0)
+assert torch.equal(W, ref)
+
+# fp32 / tensor-core path at a size where it is taken, local shards given directly (shard_input=False)
+import bench  # noqa: E402
+
+D, k = 40_000, 8
+lo, hi = bench.shard_bounds(D, world, rank)
+Xl = bench.synth_rows(lo, hi, k).astype(np.float64)
+W0, H0 = bench.init_rows(Xl, lo, k)
+m3 = sal.models.KLNMF(n_signatures=k, init_method="custom", min_iterations=60, max_iterations=60, dtype="float32", math="tf32",
+                      device=f"cuda:{local}", shard_input=False)
+m3.fit(AnnData(Xl), init_kwargs={"signatures_mat": W0, "exposures_mat": H0})
+kl_multi = m3.history["objective_function"][-1]
+if rank == 0:
+    Xf = bench.synth_rows(0, D, k).astype(np.float64)
+    W0f, H0f = bench.init_rows(Xf, 0, k)
+    from oracle import klnmf as oracle_klnmf
+
+    Wo, Ho = W0f.T.copy(), H0f.T.copy()
+    for _ in range(60):
+        Wo, Ho = oracle_klnmf.update_WH(Xf.T, Wo, Ho)
+    kl_ref = oracle_klnmf.kl_divergence(Xf.T, Wo, Ho)
+    assert abs(kl_multi - kl_ref) / kl_ref < 1e-4, (kl_multi, kl_ref)
+    A, B = m3.asignatures.X, Wo.T
+    cos = np.sum(A * B, axis=1) / (np.linalg.norm(A, axis=1) * np.linalg.norm(B, axis=1))
+    assert cos.min() >= 0.9999, cos
+    print(f"multi-GPU ok: world {world}, fp64 trajectories match, tf32 60-iteration KL {kl_multi:.3f} vs oracle {kl_ref:.3f}")
+dist.barrier()
+dist.destroy_process_group()
