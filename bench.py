@@ -240,6 +240,8 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
     if world != args.gpus:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
     if not torch.cuda.is_available():
@@ -426,8 +428,17 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": cits, "unit": "iterations/s", "cores": threads, "kind": "port", "sample": sample}
         print(json.dumps(line), flush=True)
     if world > 1:
+        # CUDA graphs that captured NCCL collectives keep the communicator busy at teardown: drop them, make sure every
+        # rank is done, and leave without running the (occasionally hanging) communicator destructors
+        del model, e2e_model
+        import gc
+
+        gc.collect()
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

@@ -147,6 +147,8 @@ class SignatureNMF(ABC):
 
     def _release_device(self) -> None:
         if self._dev is not None:
+            if getattr(self._dev, "fit_loop", None):
+                self._dev.fit_loop.clear()  # captured CUDA graphs (and the NCCL work they hold) go first
             self._dev.close()
             self._dev = None
 
