@@ -57,7 +57,9 @@ enum {
     SAL_PASS_OBJECTIVE = 4,  /* write *objective = KL(X||WH) (+ l-half term) of the INPUT W,H */
     SAL_PASS_SAMPLEWISE = 8, /* write per_sample[d] = unweighted KL of sample d              */
     SAL_PASS_HSUM = 16,      /* write hsum[k] = sum_d H_in[d][k]                             */
-    SAL_PASS_POISSON = 32    /* objective = sum x ln(wh) - wh  (Poisson llh w/o ln Gamma)    */
+    SAL_PASS_POISSON = 32,   /* objective = sum x ln(wh) - wh  (Poisson llh w/o ln Gamma)    */
+    SAL_PASS_NOCLIP = 64     /* with UPDATE_H: H_out = H * W^T A without the clip -- this is CorrNMF's
+                                aux^T [D][k] (compute_aux, _utils_corrnmf.py:28-52) when H_in holds the exposures */
 };
 
 const char* sal_last_error(void);
@@ -150,6 +152,37 @@ int sal_mvnmf_w_unconstrained(sal_handle_t h, const void* W, const void* N, cons
  */
 int sal_mvnmf_trial(sal_handle_t h, const void* W, const void* W_unc, double gamma_blend, double delta,
                     void* W_trial, void* h_scale, double* logdet_out, void* stream);
+
+/* ---- correlated NMF (models/_utils_corrnmf.py, models/corrnmf_det.py) -------------------------------------
+ * a [k] signature scalings, b [D] sample scalings, L [k][m] signature embeddings, U [D][m] sample embeddings,
+ * auxT [D][k] (= sal_klnmf_pass UPDATE_H | NOCLIP on the exposures), m = dim_embeddings <= sal_corrnmf_max_dim().
+ * All in the handle's dtype; the arithmetic is float64.  Per-sample quantities are this rank's rows. */
+int sal_corrnmf_max_dim(void);
+/* out[d] = sum_v X[d][v]  (iteration-invariant part of update_sample_scalings, _utils_corrnmf.py:170) */
+int sal_row_sums(sal_handle_t h, const void* X, void* out, void* stream);
+/* H[d][j] = exp(a_j + b_d + l_j . u_d)   (compute_exposures, _utils_corrnmf.py:11-25) */
+int sal_corrnmf_exposures(sal_handle_t h, const void* a, const void* b, const void* L, const void* U, int m, void* H,
+                          void* stream);
+/* b_d = ln xsum_d - ln sum_j exp(a_j + l_j . u_d)   (update_sample_scalings, :141-179) */
+int sal_corrnmf_sample_scalings(sal_handle_t h, const void* xsum, const void* a, const void* L, const void* U, int m,
+                                void* b_out, void* stream);
+/* sums[0..k) = sum_d auxT[d][j], sums[k..2k) = sum_d exp(b_d + l_j . u_d): the two (per-rank) sums of
+ * update_signature_scalings (:103-138); a_j = ln sums[j] - ln sums[k + j] after they were added over the ranks
+ * (sal_corrnmf_signature_scalings_finish). */
+int sal_corrnmf_signature_scalings_sums(sal_handle_t h, const void* auxT, const void* b, const void* L, const void* U,
+                                        int m, double* sums, void* stream);
+int sal_corrnmf_signature_scalings_finish(sal_handle_t h, const double* sums, void* a_out, void* stream);
+/* Newton-CG updates of the embeddings (update_embedding, :354-410; SciPy's algorithm restated on the device):
+ * U[d] for every sample (others = signatures, maxiter Newton iterations; corrnmf_det.py:115-141) and L[j] for every
+ * signature (others = samples; :88-113; single-GPU: the sums over samples are taken over this rank's rows). */
+int sal_corrnmf_sample_embeddings(sal_handle_t h, const void* auxT, const void* a, const void* b, const void* L, void* U,
+                                  int m, double variance, int maxiter, void* stream);
+int sal_corrnmf_signature_embeddings(sal_handle_t h, const void* auxT, const void* a, const void* b, void* L,
+                                     const void* U, int m, double variance, void* stream);
+/* out[0] = sum L^2, out[1] = sum U^2 (update_variance corrnmf_det.py:60-69, ELBO priors _utils_corrnmf.py:93-98),
+ * out[2] = sum lnGamma(1 + X) when X != NULL (constant of poisson_llh, _utils_klnmf.py:159) */
+int sal_corrnmf_norms(sal_handle_t h, const void* L, const void* U, int m, const void* X_or_null, double* out,
+                      void* stream);
 
 #ifdef __cplusplus
 }

@@ -16,6 +16,7 @@ import torch
 from . import _lib
 from ._lib import (  # noqa: F401  (re-exported for callers)
     PASS_HSUM,
+    PASS_NOCLIP,
     PASS_OBJECTIVE,
     PASS_POISSON,
     PASS_SAMPLEWISE,

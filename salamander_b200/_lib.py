@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libsalamander_b200.so")
 
 SAL_F32, SAL_F64 = 0, 1
 MATH_FMA, MATH_TF32, MATH_TF32_ALWAYS = 0, 1, 2
-PASS_UPDATE_H, PASS_WNUM, PASS_OBJECTIVE, PASS_SAMPLEWISE, PASS_HSUM, PASS_POISSON = 1, 2, 4, 8, 16, 32
+PASS_UPDATE_H, PASS_WNUM, PASS_OBJECTIVE, PASS_SAMPLEWISE, PASS_HSUM, PASS_POISSON, PASS_NOCLIP = 1, 2, 4, 8, 16, 32, 64
 
 _vp, _i, _i64, _d = C.c_void_p, C.c_int, C.c_int64, C.c_double
 
@@ -38,6 +38,15 @@ SYMBOLS = {
     "sal_mvnmf_logdet": (_i, [_vp, _vp, _d, _vp, _vp]),
     "sal_mvnmf_w_unconstrained": (_i, [_vp, _vp, _vp, _vp, _d, _d, _i, _vp, _vp]),
     "sal_mvnmf_trial": (_i, [_vp, _vp, _vp, _d, _d, _vp, _vp, _vp, _vp]),
+    "sal_corrnmf_max_dim": (_i, []),
+    "sal_row_sums": (_i, [_vp, _vp, _vp, _vp]),
+    "sal_corrnmf_exposures": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
+    "sal_corrnmf_sample_scalings": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
+    "sal_corrnmf_signature_scalings_sums": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
+    "sal_corrnmf_signature_scalings_finish": (_i, [_vp, _vp, _vp, _vp]),
+    "sal_corrnmf_sample_embeddings": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _d, _i, _vp]),
+    "sal_corrnmf_signature_embeddings": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _d, _vp]),
+    "sal_corrnmf_norms": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp]),
 }
 
 _lib = None

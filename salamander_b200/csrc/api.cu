@@ -225,4 +225,67 @@ int sal_mvnmf_trial(sal_handle_t h, const void* W, const void* W_unc, double gam
                                   (cudaStream_t)stream);
 }
 
+#define SAL_CORR_COMMON(m)                                                        \
+    SAL_CHECK_ARG(h != nullptr, "handle is null");                                \
+    SAL_CHECK_ARG((m) >= 1, "dim_embeddings must be >= 1");                       \
+    if ((m) > sal_corrnmf_max_dim()) {                                            \
+        sal_set_error("dim_embeddings %d exceeds the supported %d", (m), sal_corrnmf_max_dim()); \
+        return SAL_EUNSUPPORTED;                                                  \
+    }                                                                             \
+    SAL_CUDA(cudaSetDevice(h->device));
+
+int sal_row_sums(sal_handle_t h, const void* X, void* out, void* stream) {
+    SAL_CHECK_ARG(h && (h->D == 0 || (X && out)), "null argument");
+    SAL_CUDA(cudaSetDevice(h->device));
+    return sal_launch_row_sums(h, X, out, (cudaStream_t)stream);
+}
+
+int sal_corrnmf_exposures(sal_handle_t h, const void* a, const void* b, const void* L, const void* U, int m, void* H, void* stream) {
+    SAL_CORR_COMMON(m);
+    SAL_CHECK_ARG(a && L && (h->D == 0 || (b && U && H)), "null argument");
+    return sal_launch_corrnmf_exposures(h, a, b, L, U, m, H, (cudaStream_t)stream);
+}
+
+int sal_corrnmf_sample_scalings(sal_handle_t h, const void* xsum, const void* a, const void* L, const void* U, int m, void* b_out,
+                                void* stream) {
+    SAL_CORR_COMMON(m);
+    SAL_CHECK_ARG(a && L && (h->D == 0 || (xsum && U && b_out)), "null argument");
+    return sal_launch_corrnmf_sample_scalings(h, xsum, a, L, U, m, b_out, (cudaStream_t)stream);
+}
+
+int sal_corrnmf_signature_scalings_sums(sal_handle_t h, const void* auxT, const void* b, const void* L, const void* U, int m,
+                                        double* sums, void* stream) {
+    SAL_CORR_COMMON(m);
+    SAL_CHECK_ARG(L && sums && (h->D == 0 || (auxT && b && U)), "null argument");
+    return sal_launch_corrnmf_signature_scalings_sums(h, auxT, b, L, U, m, sums, (cudaStream_t)stream);
+}
+
+int sal_corrnmf_signature_scalings_finish(sal_handle_t h, const double* sums, void* a_out, void* stream) {
+    SAL_CHECK_ARG(h && sums && a_out, "null argument");
+    SAL_CUDA(cudaSetDevice(h->device));
+    return sal_launch_corrnmf_signature_scalings_finish(h, sums, a_out, (cudaStream_t)stream);
+}
+
+int sal_corrnmf_sample_embeddings(sal_handle_t h, const void* auxT, const void* a, const void* b, const void* L, void* U, int m,
+                                  double variance, int maxiter, void* stream) {
+    SAL_CORR_COMMON(m);
+    SAL_CHECK_ARG(a && L && (h->D == 0 || (auxT && b && U)), "null argument");
+    SAL_CHECK_ARG(variance > 0.0 && maxiter >= 0, "variance must be positive, maxiter >= 0");
+    return sal_launch_corrnmf_sample_embeddings(h, auxT, a, b, L, U, m, variance, maxiter, (cudaStream_t)stream);
+}
+
+int sal_corrnmf_signature_embeddings(sal_handle_t h, const void* auxT, const void* a, const void* b, void* L, const void* U, int m,
+                                     double variance, void* stream) {
+    SAL_CORR_COMMON(m);
+    SAL_CHECK_ARG(a && L && (h->D == 0 || (auxT && b && U)), "null argument");
+    SAL_CHECK_ARG(variance > 0.0, "variance must be positive");
+    return sal_launch_corrnmf_signature_embeddings(h, auxT, a, b, L, U, m, variance, (cudaStream_t)stream);
+}
+
+int sal_corrnmf_norms(sal_handle_t h, const void* L, const void* U, int m, const void* X_or_null, double* out, void* stream) {
+    SAL_CORR_COMMON(m);
+    SAL_CHECK_ARG(L && out, "null argument");
+    return sal_launch_corrnmf_norms(h, L, U, m, X_or_null, out, (cudaStream_t)stream);
+}
+
 }  // extern "C"

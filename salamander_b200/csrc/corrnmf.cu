@@ -1,0 +1,548 @@
+// Correlated NMF kernels (reference models/_utils_corrnmf.py, models/corrnmf_det.py).
+//
+//   exposures            H_dk = exp(a_k + b_d + l_k.u_d)                          _utils_corrnmf.py:11-25
+//   sample scalings      b_d  = ln sum_v x_dv - ln sum_k exp(a_k + l_k.u_d)       :141-179
+//   signature scalings   a_k  = ln sum_d aux_kd - ln sum_d exp(b_d + l_k.u_d)     :103-138
+//   embedding updates    argmin_e -[sum_i (o_i.e) aux_i - sum_i exp(s + s_i + o_i.e) - |e|^2/(2 var)]   :182-410
+//                        sample embeddings: one THREAD per sample (others = the k signatures, 3 Newton iterations,
+//                        corrnmf_det.py:115-141); signature embeddings: one CTA per signature, every objective /
+//                        gradient / Hessian evaluation is a fixed-order block reduction over the samples (:88-113)
+//   variance             clip(mean([L;U]^2))                                      corrnmf_det.py:60-69
+//   aux and the W numerator come from the fused pass (klnmf_pass.cu, SAL_PASS_NOCLIP): aux_kd = H_dk (W^T A)_kd.
+//
+// The minimiser is a device restatement of SciPy's Newton-CG -- truncated Newton, CG inner loop, More'-Thuente DCSRCH
+// line search with SciPy's defaults -- the third-party algorithm the reference calls at _utils_corrnmf.py:400-407;
+// oracle/corrnmf.py::newton_cg is the same restatement in numpy and is pinned against scipy itself.
+// All arithmetic is float64 whatever the handle's storage dtype.
+#include "sal_common.cuh"
+
+namespace {
+
+constexpr int MAXM = 16;  // embedding dimensions handled (SAL_EUNSUPPORTED above)
+
+// ---------------------------------------------------------------------------------------------------------
+// DCSRCH / dcstep (MINPACK-2, as shipped in scipy/optimize/_dcsrch.py): scalar state machine
+// ---------------------------------------------------------------------------------------------------------
+struct StepState {
+    double stx, fx, dx, sty, fy, dy, stp;
+    bool brackt;
+};
+
+__device__ inline double sgn(double v) { return (v > 0.0) - (v < 0.0); }
+
+__device__ void dcstep(StepState& s, double fp, double dp, double stpmin, double stpmax) {
+    const double sgnd = sgn(dp) * sgn(s.dx);
+    double stpf, stpc, stpq;
+    if (fp > s.fx) {
+        const double theta = 3.0 * (s.fx - fp) / (s.stp - s.stx) + s.dx + dp;
+        const double sc = fmax(fabs(theta), fmax(fabs(s.dx), fabs(dp)));
+        double gamma = sc * sqrt((theta / sc) * (theta / sc) - (s.dx / sc) * (dp / sc));
+        if (s.stp < s.stx) gamma = -gamma;
+        const double p = (gamma - s.dx) + theta, q = ((gamma - s.dx) + gamma) + dp, r = p / q;
+        stpc = s.stx + r * (s.stp - s.stx);
+        stpq = s.stx + ((s.dx / ((s.fx - fp) / (s.stp - s.stx) + s.dx)) / 2.0) * (s.stp - s.stx);
+        stpf = fabs(stpc - s.stx) <= fabs(stpq - s.stx) ? stpc : stpc + (stpq - stpc) / 2.0;
+        s.brackt = true;
+    } else if (sgnd < 0.0) {
+        const double theta = 3.0 * (s.fx - fp) / (s.stp - s.stx) + s.dx + dp;
+        const double sc = fmax(fabs(theta), fmax(fabs(s.dx), fabs(dp)));
+        double gamma = sc * sqrt((theta / sc) * (theta / sc) - (s.dx / sc) * (dp / sc));
+        if (s.stp > s.stx) gamma = -gamma;
+        const double p = (gamma - dp) + theta, q = ((gamma - dp) + gamma) + s.dx, r = p / q;
+        stpc = s.stp + r * (s.stx - s.stp);
+        stpq = s.stp + (dp / (dp - s.dx)) * (s.stx - s.stp);
+        stpf = fabs(stpc - s.stp) > fabs(stpq - s.stp) ? stpc : stpq;
+        s.brackt = true;
+    } else if (fabs(dp) < fabs(s.dx)) {
+        const double theta = 3.0 * (s.fx - fp) / (s.stp - s.stx) + s.dx + dp;
+        const double sc = fmax(fabs(theta), fmax(fabs(s.dx), fabs(dp)));
+        double gamma = sc * sqrt(fmax(0.0, (theta / sc) * (theta / sc) - (s.dx / sc) * (dp / sc)));
+        if (s.stp > s.stx) gamma = -gamma;
+        const double p = (gamma - dp) + theta, q = (gamma + (s.dx - dp)) + gamma, r = p / q;
+        if (r < 0.0 && gamma != 0.0)
+            stpc = s.stp + r * (s.stx - s.stp);
+        else
+            stpc = s.stp > s.stx ? stpmax : stpmin;
+        stpq = s.stp + (dp / (dp - s.dx)) * (s.stx - s.stp);
+        if (s.brackt) {
+            stpf = fabs(stpc - s.stp) < fabs(stpq - s.stp) ? stpc : stpq;
+            stpf = s.stp > s.stx ? fmin(s.stp + 0.66 * (s.sty - s.stp), stpf) : fmax(s.stp + 0.66 * (s.sty - s.stp), stpf);
+        } else {
+            stpf = fabs(stpc - s.stp) > fabs(stpq - s.stp) ? stpc : stpq;
+            stpf = fmin(fmax(stpf, stpmin), stpmax);
+        }
+    } else {
+        if (s.brackt) {
+            const double theta = 3.0 * (fp - s.fy) / (s.sty - s.stp) + s.dy + dp;
+            const double sc = fmax(fabs(theta), fmax(fabs(s.dy), fabs(dp)));
+            double gamma = sc * sqrt((theta / sc) * (theta / sc) - (s.dy / sc) * (dp / sc));
+            if (s.stp > s.sty) gamma = -gamma;
+            const double p = (gamma - dp) + theta, q = ((gamma - dp) + gamma) + s.dy, r = p / q;
+            stpf = s.stp + r * (s.sty - s.stp);
+        } else {
+            stpf = s.stp > s.stx ? stpmax : stpmin;
+        }
+    }
+    if (fp > s.fx) {
+        s.sty = s.stp, s.fy = fp, s.dy = dp;
+    } else {
+        if (sgnd < 0.0) s.sty = s.stx, s.fy = s.fx, s.dy = s.dx;
+        s.stx = s.stp, s.fx = fp, s.dx = dp;
+    }
+    s.stp = stpf;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Newton-CG.  Problem P provides (collectively for the calling threads; every thread gets the same values):
+//   double f(const double* x);  void grad(const double* x, double* g);  void hess(const double* x, double* A /*m*m*/)
+// ---------------------------------------------------------------------------------------------------------
+template <class P>
+__device__ void newton_cg(P& prob, double* x, int m, int maxiter) {
+    const double ftol = 1e-4, gtol = 0.9, ls_xtol = 1e-14, stpmin = 1e-8, stpmax = 50.0, eps64 = 2.220446049250313e-16;
+    const double xtol = m * 1e-5;
+    const int cg_maxiter = 20 * m;
+    double b[MAXM], xs[MAXM], ri[MAXM], ps[MAXM], Ap[MAXM], xt[MAXM], gt[MAXM], A[MAXM * MAXM];
+    double old_fval = prob.f(x), old_old_fval = 0.0;
+    bool have_old_old = false;
+    double update_l1 = 1.7976931348623157e308;
+    int k = 0;
+    while (update_l1 > xtol) {
+        if (k >= maxiter) break;
+        prob.grad(x, gt);
+        double maggrad = 0.0;
+        for (int i = 0; i < m; ++i) b[i] = -gt[i], maggrad += fabs(b[i]);
+        const double termcond = fmin(0.5, sqrt(maggrad)) * maggrad;
+        double dri0 = 0.0;
+        for (int i = 0; i < m; ++i) xs[i] = 0.0, ri[i] = -b[i], ps[i] = b[i], dri0 += ri[i] * ri[i];
+        prob.hess(x, A);
+        int it = 0;
+        bool failed = true;
+        for (int k2 = 0; k2 < cg_maxiter; ++k2) {
+            double rn = 0.0;
+            for (int i = 0; i < m; ++i) rn += fabs(ri[i]);
+            if (rn <= termcond) {
+                failed = false;
+                break;
+            }
+            double curv = 0.0;
+            for (int i = 0; i < m; ++i) {
+                double t = 0.0;
+                for (int j = 0; j < m; ++j) t += A[i * m + j] * ps[j];
+                Ap[i] = t;
+            }
+            for (int i = 0; i < m; ++i) curv += ps[i] * Ap[i];
+            if (curv >= 0.0 && curv <= 3.0 * eps64) {
+                failed = false;
+                break;
+            } else if (curv < 0.0) {
+                if (it == 0)
+                    for (int i = 0; i < m; ++i) xs[i] = dri0 / (-curv) * b[i];
+                failed = false;
+                break;
+            }
+            const double alphai = dri0 / curv;
+            double dri1 = 0.0;
+            for (int i = 0; i < m; ++i) xs[i] += alphai * ps[i], ri[i] += alphai * Ap[i], dri1 += ri[i] * ri[i];
+            const double betai = dri1 / dri0;
+            for (int i = 0; i < m; ++i) ps[i] = -ri[i] + betai * ps[i];
+            ++it;
+            dri0 = dri1;
+        }
+        if (failed) break;  // "CG iterations didn't converge"
+        // ---- line search along pk = xs (DCSRCH)
+        double derphi0 = 0.0;
+        for (int i = 0; i < m; ++i) derphi0 += gt[i] * xs[i];
+        double alpha1 = 1.0;
+        if (have_old_old && derphi0 != 0.0) {
+            alpha1 = fmin(1.0, 1.01 * 2.0 * (old_fval - old_old_fval) / derphi0);
+            if (alpha1 < 0.0) alpha1 = 1.0;
+        }
+        bool ok = false;
+        double fnew = old_fval, stp_ok = 0.0;
+        if (!(alpha1 < stpmin || alpha1 > stpmax || derphi0 >= 0.0)) {
+            StepState s;
+            s.brackt = false;
+            int stage = 1;
+            const double finit = old_fval, ginit = derphi0, gtest = ftol * ginit;
+            double width = stpmax - stpmin, width1 = width / 0.5;
+            s.stx = s.sty = 0.0, s.fx = s.fy = finit, s.dx = s.dy = ginit, s.stp = alpha1;
+            double stmin = 0.0, stmax = alpha1 + 4.0 * alpha1;
+            for (int ls = 0; ls < 99; ++ls) {
+                for (int i = 0; i < m; ++i) xt[i] = x[i] + s.stp * xs[i];
+                const double f = prob.f(xt);
+                double gl[MAXM];
+                prob.grad(xt, gl);
+                double g = 0.0;
+                for (int i = 0; i < m; ++i) g += gl[i] * xs[i];
+                const double ftest = finit + s.stp * gtest;
+                if (stage == 1 && f <= ftest && g >= 0.0) stage = 2;
+                bool warn = false;
+                if (s.brackt && (s.stp <= stmin || s.stp >= stmax)) warn = true;
+                if (s.brackt && stmax - stmin <= ls_xtol * stmax) warn = true;
+                if (s.stp == stpmax && f <= ftest && g <= gtest) warn = true;
+                if (s.stp == stpmin && (f > ftest || g >= gtest)) warn = true;
+                if (f <= ftest && fabs(g) <= gtol * -ginit) {
+                    ok = true, fnew = f, stp_ok = s.stp;
+                    break;
+                }
+                if (warn) break;
+                if (stage == 1 && f <= s.fx && f > ftest) {
+                    StepState t = s;
+                    t.fx = s.fx - s.stx * gtest, t.fy = s.fy - s.sty * gtest, t.dx = s.dx - gtest, t.dy = s.dy - gtest;
+                    dcstep(t, f - s.stp * gtest, g - gtest, stmin, stmax);
+                    s = t;
+                    s.fx = t.fx + t.stx * gtest, s.fy = t.fy + t.sty * gtest, s.dx = t.dx + gtest, s.dy = t.dy + gtest;
+                } else {
+                    dcstep(s, f, g, stmin, stmax);
+                }
+                if (s.brackt) {
+                    if (fabs(s.sty - s.stx) >= 0.66 * width1) s.stp = s.stx + 0.5 * (s.sty - s.stx);
+                    width1 = width;
+                    width = fabs(s.sty - s.stx);
+                    stmin = fmin(s.stx, s.sty), stmax = fmax(s.stx, s.sty);
+                } else {
+                    stmin = s.stp + 1.1 * (s.stp - s.stx), stmax = s.stp + 4.0 * (s.stp - s.stx);
+                }
+                s.stp = fmin(fmax(s.stp, stpmin), stpmax);
+                if ((s.brackt && (s.stp <= stmin || s.stp >= stmax)) || (s.brackt && stmax - stmin <= ls_xtol * stmax)) s.stp = s.stx;
+                if (!isfinite(s.stp)) break;
+            }
+        }
+        if (!ok) break;  // line search failed: keep the current point
+        old_old_fval = old_fval, have_old_old = true, old_fval = fnew;
+        update_l1 = 0.0;
+        for (int i = 0; i < m; ++i) {
+            const double u = stp_ok * xs[i];
+            x[i] += u;
+            update_l1 += fabs(u);
+        }
+        ++k;
+    }
+}
+
+__device__ inline double snap_eps(double e) {
+    const double eps = SAL_EPS_F32;
+    if (e > 0.0 && e < eps) return eps;
+    if (e < 0.0 && e > -eps) return -eps;
+    return e;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// sample embeddings: one thread per sample, the k signature embeddings / scalings in shared memory
+// ---------------------------------------------------------------------------------------------------------
+struct SampleProblem {
+    const double* others;    // [k][m] shared
+    const double* s_others;  // [k]    shared
+    const double* aux;       // [k]    local
+    double s, inv_var;
+    int k, m;
+    __device__ double f(const double* x) const {
+        double acc = 0.0, nrm = 0.0;
+        for (int i = 0; i < k; ++i) {
+            double sp = 0.0;
+            for (int j = 0; j < m; ++j) sp += others[i * m + j] * x[j];
+            acc += sp * aux[i] - exp(s + s_others[i] + sp);
+        }
+        for (int j = 0; j < m; ++j) nrm += x[j] * x[j];
+        return -(acc - 0.5 * nrm * inv_var);
+    }
+    __device__ void grad(const double* x, double* g) const {
+        for (int j = 0; j < m; ++j) g[j] = x[j] * inv_var;
+        for (int i = 0; i < k; ++i) {
+            double sp = 0.0;
+            for (int j = 0; j < m; ++j) sp += others[i * m + j] * x[j];
+            const double w = exp(s + s_others[i] + sp) - aux[i];
+            for (int j = 0; j < m; ++j) g[j] += w * others[i * m + j];
+        }
+    }
+    __device__ void hess(const double* x, double* A) const {
+        for (int j = 0; j < m * m; ++j) A[j] = 0.0;
+        for (int j = 0; j < m; ++j) A[j * m + j] = inv_var;
+        for (int i = 0; i < k; ++i) {
+            double sp = 0.0;
+            for (int j = 0; j < m; ++j) sp += others[i * m + j] * x[j];
+            const double w = exp(s + s_others[i] + sp);
+            for (int p = 0; p < m; ++p)
+                for (int q = 0; q < m; ++q) A[p * m + q] += w * others[i * m + p] * others[i * m + q];
+        }
+    }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(128) sample_embeddings_kernel(const T* auxT, const T* a, const T* b, const T* L, T* U, int64_t D,
+                                                               int k, int m, double variance, int maxiter) {
+    __shared__ double sL[SAL_KMAX * MAXM];
+    __shared__ double sa[SAL_KMAX];
+    for (int i = threadIdx.x; i < k * m; i += blockDim.x) sL[i] = (double)L[i];
+    for (int i = threadIdx.x; i < k; i += blockDim.x) sa[i] = (double)a[i];
+    __syncthreads();
+    const int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= D) return;
+    double aux[SAL_KMAX], x[MAXM];
+    for (int i = 0; i < k; ++i) aux[i] = (double)auxT[d * k + i];
+    for (int j = 0; j < m; ++j) x[j] = (double)U[d * m + j];
+    SampleProblem p{sL, sa, aux, (double)b[d], 1.0 / variance, k, m};
+    newton_cg(p, x, m, maxiter);
+    for (int j = 0; j < m; ++j) U[d * m + j] = (T)snap_eps(x[j]);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// signature embeddings: one CTA per signature; evaluations are block reductions over the samples
+// ---------------------------------------------------------------------------------------------------------
+constexpr int SIG_THREADS = 256;
+
+template <typename T>
+struct SignatureProblem {
+    const T *U, *b, *auxT;  // U [D][m], b [D], auxT [D][k]
+    double* red;            // shared [SIG_THREADS / 32][1 + MAXM + MAXM * MAXM] + result slot
+    double s, inv_var;
+    int64_t D;
+    int k, m, j;
+
+    // fixed-order block reduction of n values per thread; result broadcast to all threads through shared memory
+    __device__ void reduce(double* v, int n) const {
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, stride = 1 + MAXM + MAXM * MAXM;
+        for (int i = 0; i < n; ++i) {
+            double t = v[i];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+            if (lane == 0) red[w * stride + i] = t;
+        }
+        __syncthreads();
+        for (int i = 0; i < n; ++i) {
+            double t = 0.0;
+            for (int ww = 0; ww < SIG_THREADS / 32; ++ww) t += red[ww * stride + i];
+            v[i] = t;
+        }
+        __syncthreads();
+    }
+    __device__ double f(const double* x) const {
+        double acc = 0.0;
+        for (int64_t d = threadIdx.x; d < D; d += SIG_THREADS) {
+            double sp = 0.0;
+            for (int q = 0; q < m; ++q) sp += (double)U[d * m + q] * x[q];
+            acc += sp * (double)auxT[d * k + j] - exp(s + (double)b[d] + sp);
+        }
+        reduce(&acc, 1);
+        double nrm = 0.0;
+        for (int q = 0; q < m; ++q) nrm += x[q] * x[q];
+        return -(acc - 0.5 * nrm * inv_var);
+    }
+    __device__ void grad(const double* x, double* g) const {
+        for (int q = 0; q < m; ++q) g[q] = 0.0;
+        for (int64_t d = threadIdx.x; d < D; d += SIG_THREADS) {
+            double sp = 0.0;
+            for (int q = 0; q < m; ++q) sp += (double)U[d * m + q] * x[q];
+            const double w = exp(s + (double)b[d] + sp) - (double)auxT[d * k + j];
+            for (int q = 0; q < m; ++q) g[q] += w * (double)U[d * m + q];
+        }
+        reduce(g, m);
+        for (int q = 0; q < m; ++q) g[q] += x[q] * inv_var;
+    }
+    __device__ void hess(const double* x, double* A) const {
+        for (int q = 0; q < m * m; ++q) A[q] = 0.0;
+        for (int64_t d = threadIdx.x; d < D; d += SIG_THREADS) {
+            double sp = 0.0;
+            for (int q = 0; q < m; ++q) sp += (double)U[d * m + q] * x[q];
+            const double w = exp(s + (double)b[d] + sp);
+            for (int p = 0; p < m; ++p)
+                for (int q = 0; q < m; ++q) A[p * m + q] += w * (double)U[d * m + p] * (double)U[d * m + q];
+        }
+        reduce(A, m * m);
+        for (int q = 0; q < m; ++q) A[q * m + q] += inv_var;
+    }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(SIG_THREADS) signature_embeddings_kernel(const T* auxT, const T* a, const T* b, T* L, const T* U,
+                                                                          int64_t D, int k, int m, double variance) {
+    __shared__ double red[(SIG_THREADS / 32) * (1 + MAXM + MAXM * MAXM)];
+    const int j = blockIdx.x;
+    double x[MAXM];
+    for (int q = 0; q < m; ++q) x[q] = (double)L[j * m + q];
+    SignatureProblem<T> p{U, b, auxT, red, (double)a[j], 1.0 / variance, D, k, m, j};
+    newton_cg(p, x, m, 200 * m);
+    if (threadIdx.x == 0)
+        for (int q = 0; q < m; ++q) L[j * m + q] = (T)snap_eps(x[q]);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// element-wise / reduction kernels
+// ---------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) exposures_kernel(const T* a, const T* b, const T* L, const T* U, int64_t D, int k, int m, T* H) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= D * k) return;
+    const int64_t d = i / k;
+    const int j = (int)(i - d * k);
+    double sp = 0.0;
+    for (int q = 0; q < m; ++q) sp += (double)L[j * m + q] * (double)U[d * m + q];
+    H[i] = (T)exp((double)a[j] + (double)b[d] + sp);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) row_sums_kernel(const T* X, int64_t D, int V, T* out) {
+    const int64_t d = (int64_t)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+    if (d >= D) return;
+    double s = 0.0;
+    for (int v = threadIdx.x & 31; v < V; v += 32) s += (double)X[d * V + v];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) out[d] = (T)s;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) sample_scalings_kernel(const T* xsum, const T* a, const T* L, const T* U, int64_t D, int k, int m,
+                                                             T* b) {
+    const int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= D) return;
+    double s = 0.0;
+    for (int j = 0; j < k; ++j) {
+        double sp = 0.0;
+        for (int q = 0; q < m; ++q) sp += (double)L[j * m + q] * (double)U[d * m + q];
+        s += exp((double)a[j] + sp);
+    }
+    b[d] = (T)(log((double)xsum[d]) - log(s));
+}
+
+__device__ double block_sum_256(double v, double* s_red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += s_red[w];
+    return t;
+}
+
+// one CTA per signature: sums[j] = sum_d aux_dj, sums[k + j] = sum_d exp(b_d + l_j.u_d)  (this rank's samples)
+template <typename T>
+__global__ void __launch_bounds__(256) signature_scalings_kernel(const T* auxT, const T* b, const T* L, const T* U, int64_t D, int k, int m,
+                                                                double* sums) {
+    __shared__ double s_red[8];
+    const int j = blockIdx.x;
+    double s1 = 0.0, s2 = 0.0;
+    for (int64_t d = threadIdx.x; d < D; d += 256) {
+        double sp = 0.0;
+        for (int q = 0; q < m; ++q) sp += (double)L[j * m + q] * (double)U[d * m + q];
+        s1 += (double)auxT[d * k + j];
+        s2 += exp((double)b[d] + sp);
+    }
+    s1 = block_sum_256(s1, s_red);
+    s2 = block_sum_256(s2, s_red);
+    if (threadIdx.x == 0) sums[j] = s1, sums[k + j] = s2;
+}
+
+template <typename T>
+__global__ void signature_scalings_finish_kernel(const double* sums, int k, T* a) {
+    const int j = threadIdx.x;
+    if (j < k) a[j] = (T)(log(sums[j]) - log(sums[k + j]));
+}
+
+// out[0] = sum L^2, out[1] = sum U^2 (this rank's samples), out[2] = sum_x lnGamma(1 + x) when X != null
+template <typename T>
+__global__ void __launch_bounds__(256) norms_kernel(const T* L, int64_t nL, const T* U, int64_t nU, const T* X, int64_t nX, double* out) {
+    __shared__ double s_red[8];
+    double s = 0.0;
+    const T* src = blockIdx.x == 0 ? L : blockIdx.x == 1 ? U : X;
+    const int64_t n = blockIdx.x == 0 ? nL : blockIdx.x == 1 ? nU : nX;
+    if (blockIdx.x < 2) {
+        for (int64_t i = threadIdx.x; i < n; i += 256) s += (double)src[i] * (double)src[i];
+    } else {
+        for (int64_t i = threadIdx.x; i < n; i += 256) s += lgamma(1.0 + (double)src[i]);
+    }
+    s = block_sum_256(s, s_red);
+    if (threadIdx.x == 0) out[blockIdx.x] = s;
+}
+
+}  // namespace
+
+#define SAL_DISPATCH_T(c, call_f, call_d) \
+    do {                                  \
+        if ((c)->dtype == SAL_F32) {      \
+            call_f;                       \
+        } else {                          \
+            call_d;                       \
+        }                                 \
+    } while (0)
+
+int sal_launch_corrnmf_exposures(sal_ctx* c, const void* a, const void* b, const void* L, const void* U, int m, void* H, cudaStream_t st) {
+    const int64_t n = c->D * c->k;
+    if (n == 0) return 0;
+    const int grid = (int)((n + 255) / 256);
+    SAL_DISPATCH_T(c, (exposures_kernel<float><<<grid, 256, 0, st>>>((const float*)a, (const float*)b, (const float*)L, (const float*)U, c->D, c->k, m, (float*)H)),
+                   (exposures_kernel<double><<<grid, 256, 0, st>>>((const double*)a, (const double*)b, (const double*)L, (const double*)U, c->D, c->k, m, (double*)H)));
+    SAL_CUDA(cudaGetLastError());
+    c->launches++;
+    return 0;
+}
+
+int sal_launch_row_sums(sal_ctx* c, const void* X, void* out, cudaStream_t st) {
+    if (c->D == 0) return 0;
+    const int grid = (int)((c->D + 7) / 8);
+    SAL_DISPATCH_T(c, (row_sums_kernel<float><<<grid, 256, 0, st>>>((const float*)X, c->D, c->V, (float*)out)),
+                   (row_sums_kernel<double><<<grid, 256, 0, st>>>((const double*)X, c->D, c->V, (double*)out)));
+    SAL_CUDA(cudaGetLastError());
+    c->launches++;
+    return 0;
+}
+
+int sal_launch_corrnmf_sample_scalings(sal_ctx* c, const void* xsum, const void* a, const void* L, const void* U, int m, void* b,
+                                       cudaStream_t st) {
+    if (c->D == 0) return 0;
+    const int grid = (int)((c->D + 255) / 256);
+    SAL_DISPATCH_T(c, (sample_scalings_kernel<float><<<grid, 256, 0, st>>>((const float*)xsum, (const float*)a, (const float*)L, (const float*)U, c->D, c->k, m, (float*)b)),
+                   (sample_scalings_kernel<double><<<grid, 256, 0, st>>>((const double*)xsum, (const double*)a, (const double*)L, (const double*)U, c->D, c->k, m, (double*)b)));
+    SAL_CUDA(cudaGetLastError());
+    c->launches++;
+    return 0;
+}
+
+int sal_launch_corrnmf_signature_scalings_sums(sal_ctx* c, const void* auxT, const void* b, const void* L, const void* U, int m,
+                                               double* sums, cudaStream_t st) {
+    SAL_DISPATCH_T(c, (signature_scalings_kernel<float><<<c->k, 256, 0, st>>>((const float*)auxT, (const float*)b, (const float*)L, (const float*)U, c->D, c->k, m, sums)),
+                   (signature_scalings_kernel<double><<<c->k, 256, 0, st>>>((const double*)auxT, (const double*)b, (const double*)L, (const double*)U, c->D, c->k, m, sums)));
+    SAL_CUDA(cudaGetLastError());
+    c->launches++;
+    return 0;
+}
+
+int sal_launch_corrnmf_signature_scalings_finish(sal_ctx* c, const double* sums, void* a, cudaStream_t st) {
+    SAL_DISPATCH_T(c, (signature_scalings_finish_kernel<float><<<1, 32, 0, st>>>(sums, c->k, (float*)a)),
+                   (signature_scalings_finish_kernel<double><<<1, 32, 0, st>>>(sums, c->k, (double*)a)));
+    SAL_CUDA(cudaGetLastError());
+    c->launches++;
+    return 0;
+}
+
+int sal_launch_corrnmf_sample_embeddings(sal_ctx* c, const void* auxT, const void* a, const void* b, const void* L, void* U, int m,
+                                         double variance, int maxiter, cudaStream_t st) {
+    if (c->D == 0) return 0;
+    const int grid = (int)((c->D + 127) / 128);
+    SAL_DISPATCH_T(c, (sample_embeddings_kernel<float><<<grid, 128, 0, st>>>((const float*)auxT, (const float*)a, (const float*)b, (const float*)L, (float*)U, c->D, c->k, m, variance, maxiter)),
+                   (sample_embeddings_kernel<double><<<grid, 128, 0, st>>>((const double*)auxT, (const double*)a, (const double*)b, (const double*)L, (double*)U, c->D, c->k, m, variance, maxiter)));
+    SAL_CUDA(cudaGetLastError());
+    c->launches++;
+    return 0;
+}
+
+int sal_launch_corrnmf_signature_embeddings(sal_ctx* c, const void* auxT, const void* a, const void* b, void* L, const void* U, int m,
+                                            double variance, cudaStream_t st) {
+    SAL_DISPATCH_T(c, (signature_embeddings_kernel<float><<<c->k, SIG_THREADS, 0, st>>>((const float*)auxT, (const float*)a, (const float*)b, (float*)L, (const float*)U, c->D, c->k, m, variance)),
+                   (signature_embeddings_kernel<double><<<c->k, SIG_THREADS, 0, st>>>((const double*)auxT, (const double*)a, (const double*)b, (double*)L, (const double*)U, c->D, c->k, m, variance)));
+    SAL_CUDA(cudaGetLastError());
+    c->launches++;
+    return 0;
+}
+
+int sal_launch_corrnmf_norms(sal_ctx* c, const void* L, const void* U, int m, const void* X_or_null, double* out, cudaStream_t st) {
+    const int blocks = X_or_null ? 3 : 2;
+    SAL_DISPATCH_T(c, (norms_kernel<float><<<blocks, 256, 0, st>>>((const float*)L, (int64_t)c->k * m, (const float*)U, c->D * m, (const float*)X_or_null, c->D * c->V, out)),
+                   (norms_kernel<double><<<blocks, 256, 0, st>>>((const double*)L, (int64_t)c->k * m, (const double*)U, c->D * m, (const double*)X_or_null, c->D * c->V, out)));
+    SAL_CUDA(cudaGetLastError());
+    c->launches++;
+    return 0;
+}
+
+int sal_corrnmf_max_dim(void) { return MAXM; }

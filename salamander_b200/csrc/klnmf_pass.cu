@@ -209,6 +209,9 @@ __global__ void __launch_bounds__(NT, Cfg<T>::OCC) klnmf_pass_kernel(PassParams<
                     if (p.h_scale) {
 #pragma unroll
                         for (int j = 0; j < KP; ++j) hn[j] = h[j];
+                    } else if (p.flags & SAL_PASS_NOCLIP) {
+#pragma unroll
+                        for (int j = 0; j < KP; ++j) hn[j] = h[j] * hn[j];
                     } else if (!p.w_lhalf) {
 #pragma unroll
                         for (int j = 0; j < KP; ++j) hn[j] = max(h[j] * hn[j], eps);

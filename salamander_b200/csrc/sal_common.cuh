@@ -76,3 +76,17 @@ int sal_launch_mvnmf_w_unc(sal_ctx* c, const void* W, const void* N, const void*
                            double delta, int n_given, void* W_unc, cudaStream_t st);
 int sal_launch_mvnmf_trial(sal_ctx* c, const void* W, const void* W_unc, double gamma, double delta,
                            void* W_trial, void* h_scale, double* logdet_out, cudaStream_t st);
+
+// ---- correlated NMF launchers (corrnmf.cu) --------------------------------------------------------------
+int sal_launch_corrnmf_exposures(sal_ctx* c, const void* a, const void* b, const void* L, const void* U, int m, void* H, cudaStream_t st);
+int sal_launch_row_sums(sal_ctx* c, const void* X, void* out, cudaStream_t st);
+int sal_launch_corrnmf_sample_scalings(sal_ctx* c, const void* xsum, const void* a, const void* L, const void* U, int m, void* b,
+                                       cudaStream_t st);
+int sal_launch_corrnmf_signature_scalings_sums(sal_ctx* c, const void* auxT, const void* b, const void* L, const void* U, int m,
+                                               double* sums, cudaStream_t st);
+int sal_launch_corrnmf_signature_scalings_finish(sal_ctx* c, const double* sums, void* a, cudaStream_t st);
+int sal_launch_corrnmf_sample_embeddings(sal_ctx* c, const void* auxT, const void* a, const void* b, const void* L, void* U, int m,
+                                         double variance, int maxiter, cudaStream_t st);
+int sal_launch_corrnmf_signature_embeddings(sal_ctx* c, const void* auxT, const void* a, const void* b, void* L, const void* U, int m,
+                                            double variance, cudaStream_t st);
+int sal_launch_corrnmf_norms(sal_ctx* c, const void* L, const void* U, int m, const void* X_or_null, double* out, cudaStream_t st);

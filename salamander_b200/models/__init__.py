@@ -1,6 +1,7 @@
 """Model namespace, mirroring reference models/__init__.py:4-15."""
 
+from .corrnmf import CorrNMFDet
 from .klnmf import KLNMF
 from .mvnmf import MvNMF
 
-__all__ = ["KLNMF", "MvNMF"]
+__all__ = ["CorrNMFDet", "KLNMF", "MvNMF"]

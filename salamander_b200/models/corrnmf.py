@@ -1,0 +1,258 @@
+"""
+``CorrNMFDet``: correlated NMF with deterministic batch updates -- exposures are parameterised as
+``exp(signature scaling + sample scaling + <signature embedding, sample embedding>)`` with Gaussian priors on the
+embeddings.  Same interface as reference models/corrnmf.py:25-235 (abstract ``CorrNMF``) and
+models/corrnmf_det.py:18-169 (``CorrNMFDet``): constructor, ``fit``, the single-parameter update methods the
+reference's tests call, ``given_parameters`` keys that freeze individual parameters, results in
+``asignatures.X / .obs['scalings'] / .obsm['embeddings']``, ``adata.obs['scalings'] / .obsm['embeddings'] /
+.obsm['exposures']`` and ``model.variance``.
+
+All numerics run on the device through the C ABI (csrc/corrnmf.cu + the fused pass): per iteration ONE pass over X
+produces aux and the W numerator (both use the exposures computed before the scaling / embedding updates, like the
+reference), the sample embeddings are updated one thread per sample and the signature embeddings
+one CTA per signature by a device restatement of SciPy's Newton-CG (the third-party algorithm behind
+_utils_corrnmf.py:400-407).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from typing import Any, Literal
+
+import numpy as np
+import torch
+
+from .. import _dist, _lib
+from .._device import PASS_NOCLIP, PASS_POISSON, PASS_SAMPLEWISE, PASS_UPDATE_H, PASS_WNUM, Workspace
+from ..initialization.initialize import initialize_corrnmf
+from .signature_nmf import SignatureNMF
+
+
+class CorrState:
+    """Device-resident state: X [D][V], W [k][V], a [k], b [D], L [k][m], U [D][m], H / auxT [D][k]."""
+
+    def __init__(self, model: "CorrNMF"):
+        dev = model._resolved_device()
+        dt = model.dtype
+        if _dist.world()[1] > 1:
+            raise NotImplementedError(
+                "CorrNMF on several GPUs is not built yet: the signature-embedding Newton-CG needs an all-reduce per "
+                "objective / gradient / Hessian evaluation (SURVEY.md 8(e))."
+            )
+        model.transfer_bytes = {"h2d": 0, "d2h": 0}
+        self.model, self.device, self.dtype = model, dev, dt
+        X = np.asarray(model.adata.X)
+        self.D, self.V = X.shape
+        self.k, self.m = int(model.n_signatures), int(model.dim_embeddings)
+        self.ws = Workspace(self.V, self.D, self.k, dt, dev, math="fma")
+        self.lib = self.ws.lib
+        if self.m > self.lib.sal_corrnmf_max_dim():
+            raise NotImplementedError(f"dim_embeddings > {self.lib.sal_corrnmf_max_dim()} is not supported by the device kernels.")
+        up = self.upload
+        self.X = up(X)
+        if model._clip_on_device:
+            changed = torch.zeros(1, dtype=torch.int64, device=dev)
+            self.ws.clip_counts(self.X, changed)
+            if int(changed.item()) > 0:
+                model.adata.X = self.download(self.X)
+            model._clip_on_device = False
+        asig, adata = model.asignatures, model.adata
+        self.W = up(np.asarray(asig.X, dtype=np.float64))
+        self.a = up(np.asarray(asig.obs["scalings"].values, dtype=np.float64))
+        self.L = up(np.asarray(asig.obsm["embeddings"], dtype=np.float64))
+        self.b = up(np.asarray(adata.obs["scalings"].values, dtype=np.float64))
+        self.U = up(np.asarray(adata.obsm["embeddings"], dtype=np.float64))
+        self.H = up(np.asarray(adata.obsm["exposures"], dtype=np.float64)) if "exposures" in adata.obsm else torch.empty((self.D, self.k), dtype=dt, device=dev)
+        self.auxT = torch.empty((self.D, self.k), dtype=dt, device=dev)
+        self.Wnum = torch.empty((self.k, self.V), dtype=dt, device=dev)
+        self.xsum = torch.empty(self.D, dtype=dt, device=dev)
+        self.sums = torch.zeros(2 * self.k, dtype=torch.float64, device=dev)
+        self.norms = torch.zeros(3, dtype=torch.float64, device=dev)
+        self.obj = torch.zeros(1, dtype=torch.float64, device=dev)
+        self.call("sal_row_sums", self.X, self.xsum)
+        self.lgamma_sum = None  # sum lnGamma(1 + x), constant of the ELBO, computed at the first objective
+
+    # -- plumbing ------------------------------------------------------------------------------
+    def upload(self, host) -> torch.Tensor:
+        t = torch.from_numpy(np.ascontiguousarray(host))
+        self.model.transfer_bytes["h2d"] += t.numel() * t.element_size()
+        return t.to(self.device, non_blocking=True).to(self.dtype).contiguous()
+
+    def download(self, t: torch.Tensor) -> np.ndarray:
+        out = t.to(torch.float64).cpu().numpy()
+        self.model.transfer_bytes["d2h"] += out.nbytes
+        return out
+
+    def call(self, name: str, *args) -> None:
+        """Call ``name(handle, *args, stream)``: tensors become device pointers, ints / floats pass through."""
+        conv = []
+        for x in args:
+            if isinstance(x, torch.Tensor):
+                conv.append(C.c_void_p(x.data_ptr()))
+            elif x is None:
+                conv.append(None)
+            else:
+                conv.append(x)
+        stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        _lib.check(getattr(self.lib, name)(self.ws._h, *conv, stream), name)
+
+    def close(self) -> None:
+        self.ws.close()
+
+
+class CorrNMF(SignatureNMF):
+    def __init__(
+        self,
+        n_signatures: int = 1,
+        init_method: str = "nndsvd",
+        dim_embeddings: int | None = None,
+        min_iterations: int = 500,
+        max_iterations: int = 10000,
+        conv_test_freq: int = 10,
+        tol: float = 1e-7,
+        **device_kwargs,
+    ):
+        device_kwargs.pop("math", None)  # the correlated models always use the exact kernels
+        super().__init__(n_signatures, init_method, min_iterations, max_iterations, conv_test_freq, tol, **device_kwargs)
+        if dim_embeddings is None:
+            dim_embeddings = n_signatures
+        self.dim_embeddings = dim_embeddings
+        self.variance = 1.0
+
+    @property
+    def objective(self) -> Literal["minimize", "maximize"]:
+        return "maximize"
+
+    # ---- device residency ------------------------------------------------------------------------
+    def _to_device(self) -> None:
+        self._dev = CorrState(self)
+
+    def _to_host(self) -> None:
+        st = self._dev
+        self.asignatures.X = st.download(st.W)
+        self.asignatures.obs["scalings"] = st.download(st.a)
+        self.asignatures.obsm["embeddings"] = st.download(st.L)
+        self.adata.obs["scalings"] = st.download(st.b)
+        self.adata.obsm["embeddings"] = st.download(st.U)
+        self.adata.obsm["exposures"] = st.download(st.H)
+
+    # ---- reference corrnmf.py:66-98 --------------------------------------------------------------
+    def compute_exposures(self) -> None:
+        with self._resident() as st:
+            st.call("sal_corrnmf_exposures", st.a, st.b, st.L, st.U, st.m, st.H)
+
+    def compute_reconstruction_errors(self) -> None:
+        with self._resident() as st:
+            st.call("sal_corrnmf_exposures", st.a, st.b, st.L, st.U, st.m, st.H)
+            out = torch.empty(st.D, dtype=st.dtype, device=st.device)
+            st.ws.klnmf_pass(st.X, st.W, st.H, PASS_SAMPLEWISE, per_sample=out)
+            self.adata.obs["reconstruction_error"] = st.download(out)
+
+    def objective_function(self, penalize_sample_embeddings: bool = True) -> float:
+        """The evidence lower bound with the exposures as they are stored (reference corrnmf.py:86-98 ->
+        _utils_corrnmf.py:55-100): Poisson log-likelihood minus the Gaussian priors of the embeddings."""
+        with self._resident() as st:
+            st.ws.klnmf_pass(st.X, st.W, st.H, PASS_POISSON, objective=st.obj)
+            need_lgamma = st.lgamma_sum is None
+            st.call("sal_corrnmf_norms", st.L, st.U, st.m, st.X if need_lgamma else None, st.norms)
+            vals = torch.cat([st.obj, st.norms]).tolist()
+            if need_lgamma:
+                st.lgamma_sum = vals[3]
+            llh, sumL2, sumU2 = vals[0] - st.lgamma_sum, vals[1], vals[2]
+            var, m = float(self.variance), st.m
+            elbo = llh - 0.5 * m * st.k * np.log(2 * np.pi * var) - sumL2 / (2 * var)
+            if penalize_sample_embeddings:
+                elbo -= 0.5 * m * st.D * np.log(2 * np.pi * var) + sumU2 / (2 * var)
+            return float(elbo)
+
+    # ---- initialisation (reference corrnmf.py:104-136) -------------------------------------------
+    def _initialize(self, given_parameters=None, init_kwargs=None) -> None:
+        init_kwargs = {} if init_kwargs is None else init_kwargs.copy()
+        self.asignatures, self.variance = initialize_corrnmf(
+            self.adata, self.n_signatures, self.dim_embeddings, self.init_method, given_parameters, **init_kwargs
+        )
+        self.adata.obsm.pop("exposures", None)
+        self.compute_exposures()
+
+    def _setup_fitting_parameters(self, fitting_kwargs: dict[str, Any] | None = None) -> None:
+        return
+
+
+class CorrNMFDet(CorrNMF):
+    # ---- single-parameter updates (reference corrnmf_det.py:27-155) ------------------------------
+    def _compute_aux(self):
+        """aux (and the raw W numerator) in one pass over X; returned as the (k, D) host array the reference uses."""
+        with self._resident() as st:
+            st.ws.klnmf_pass(st.X, st.W, st.H, PASS_UPDATE_H | PASS_WNUM | PASS_NOCLIP, H_out=st.auxT, Wnum=st.Wnum)
+            return None if self._in_fit else st.download(st.auxT).T
+
+    def _aux_to_device(self, st, aux) -> None:
+        if aux is not None:
+            st.auxT = st.upload(np.asarray(aux, dtype=np.float64).T)
+
+    def update_sample_scalings(self, given_parameters: dict[str, Any] | None = None) -> None:
+        if given_parameters and "sample_scalings" in given_parameters:
+            return
+        with self._resident() as st:
+            st.call("sal_corrnmf_sample_scalings", st.xsum, st.a, st.L, st.U, st.m, st.b)
+
+    def update_signature_scalings(self, aux=None, given_parameters: dict[str, Any] | None = None) -> None:
+        if given_parameters and "signature_scalings" in given_parameters:
+            return
+        with self._resident() as st:
+            self._aux_to_device(st, aux)
+            st.call("sal_corrnmf_signature_scalings_sums", st.auxT, st.b, st.L, st.U, st.m, st.sums)
+            st.call("sal_corrnmf_signature_scalings_finish", st.sums, st.a)
+
+    def update_variance(self, given_parameters: dict[str, Any] | None = None) -> None:
+        if given_parameters and "variance" in given_parameters:
+            return
+        with self._resident() as st:
+            st.call("sal_corrnmf_norms", st.L, st.U, st.m, None, st.norms)
+            sumL2, sumU2 = st.norms[:2].tolist()
+            self.variance = float(np.clip((sumL2 + sumU2) / ((st.k + st.D) * st.m), _lib_eps(), None))
+
+    def update_signatures(self, given_parameters: dict[str, Any] | None = None) -> None:
+        """update_W with the exposures as stored; only the non-given signatures are clipped (reference :71-86)."""
+        n_given = given_parameters["asignatures"].n_obs if given_parameters and "asignatures" in given_parameters else 0
+        with self._resident() as st:
+            if not self._in_fit:  # standalone call: the numerator has to be computed first
+                st.ws.klnmf_pass(st.X, st.W, st.H, PASS_WNUM, Wnum=st.Wnum)
+            st.ws.w_epilogue(st.W, st.Wnum, n_given, False, st.W)
+
+    def update_signature_embeddings(self, aux=None) -> None:
+        with self._resident() as st:
+            self._aux_to_device(st, aux)
+            st.call("sal_corrnmf_signature_embeddings", st.auxT, st.a, st.b, st.L, st.U, st.m, float(self.variance))
+
+    def update_sample_embeddings(self, aux=None) -> None:
+        with self._resident() as st:
+            self._aux_to_device(st, aux)
+            st.call("sal_corrnmf_sample_embeddings", st.auxT, st.a, st.b, st.L, st.U, st.m, float(self.variance), 3)
+
+    def update_embeddings(self, aux=None, given_parameters: dict[str, Any] | None = None) -> None:
+        given_parameters = given_parameters or {}
+        if "signature_embeddings" not in given_parameters:
+            self.update_signature_embeddings(aux)
+        if "sample_embeddings" not in given_parameters:
+            self.update_sample_embeddings(aux)
+
+    def _update_parameters(self, given_parameters: dict[str, Any] | None = None) -> None:
+        """One iteration in the reference's order (corrnmf_det.py:157-169)."""
+        given_parameters = given_parameters or {}
+        with self._resident():
+            in_fit, self._in_fit = self._in_fit, True  # aux / numerator stay on the device between the steps
+            try:
+                self.update_sample_scalings(given_parameters)
+                self.compute_exposures()
+                self._compute_aux()
+                self.update_signature_scalings(None, given_parameters)
+                self.update_embeddings(None, given_parameters)
+                self.update_variance(given_parameters)
+                self.update_signatures(given_parameters)
+            finally:
+                self._in_fit = in_fit
+
+
+def _lib_eps() -> float:
+    return float(np.finfo(np.float32).eps)

@@ -1,0 +1,167 @@
+"""
+GPU parity of CorrNMFDet through the public API, mirroring reference tests/test_corrnmf.py:108-245 on the
+reference's golden fixtures (tests/golden/models/corrnmf), plus several whole iterations against the oracle
+(whose embedding solver is scipy's Newton-CG, as in the reference) on the PCAWG counts.
+"""
+
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+from conftest import ROOT, golden_path
+
+import salamander_b200 as sal
+from salamander_b200 import AnnData
+
+from oracle import corrnmf as oracle
+
+pytestmark = pytest.mark.gpu
+P = "models/corrnmf"
+
+
+def counts():
+    return pd.read_csv(golden_path(P, "counts.csv"), index_col=0).T
+
+
+@pytest.fixture(params=[1, 2])
+def n(request):
+    return request.param
+
+
+@pytest.fixture(params=["float64"])
+def dtype(request):
+    return request.param
+
+
+def ld(name, n):
+    return np.load(golden_path(P, f"{name}_nsigs{n}_dim{n}.npy"))
+
+
+@pytest.fixture
+def model_init(n, dtype):
+    adata = AnnData(counts())
+    adata.obs["scalings"] = ld("sample_scalings_init", n)
+    adata.obsm["embeddings"] = ld("sample_embeddings_init", n).T
+    asig = AnnData(ld("signatures_mat_init", n).T)
+    asig.var_names = adata.var_names
+    asig.obs["scalings"] = ld("signature_scalings_init", n)
+    asig.obsm["embeddings"] = ld("signature_embeddings_init", n).T
+    model = sal.models.CorrNMFDet(n_signatures=n, dim_embeddings=n, dtype=dtype)
+    model.adata = adata
+    model.asignatures = asig
+    model.compute_exposures()
+    model.variance = float(ld("variance_init", n))
+    return model
+
+
+def test_objective_function(model_init, n):
+    assert np.allclose(model_init.objective_function(), ld("objective_init", n))
+
+
+def test_compute_aux(model_init, n):
+    assert np.allclose(model_init._compute_aux(), ld("aux", n))
+
+
+def test_update_signatures(model_init, n):
+    model_init.update_signatures()
+    assert np.allclose(model_init.asignatures.X, ld("signatures_mat_updated", n).T)
+
+
+def test_update_signature_scalings(model_init, n):
+    model_init.update_signature_scalings(ld("aux", n))
+    assert np.allclose(model_init.asignatures.obs["scalings"].values, ld("signature_scalings_updated", n))
+
+
+def test_update_sample_scalings(model_init, n):
+    model_init.update_sample_scalings()
+    assert np.allclose(model_init.adata.obs["scalings"].values, ld("sample_scalings_updated", n))
+
+
+def test_update_signature_embeddings(model_init, n):
+    model_init.update_signature_embeddings(ld("aux", n))
+    assert np.allclose(model_init.asignatures.obsm["embeddings"], ld("signature_embeddings_updated", n).T)
+
+
+def test_update_sample_embeddings(model_init, n):
+    model_init.update_sample_embeddings(ld("aux", n))
+    assert np.allclose(model_init.adata.obsm["embeddings"], ld("sample_embeddings_updated", n).T)
+
+
+def test_update_variance(model_init, n):
+    model_init.update_variance()
+    assert np.allclose(model_init.variance, ld("variance_updated", n))
+
+
+@pytest.mark.parametrize("k,m", [(1, 1), (2, 1), (2, 2)])
+def test_given_parameters_stay_fixed(k, m):
+    adata = AnnData(counts())
+    rng = np.random.default_rng(0)
+
+    def model():
+        return sal.models.CorrNMFDet(n_signatures=k, dim_embeddings=m, min_iterations=3, max_iterations=3, init_method="random")
+
+    for n_given in range(1, k + 1):
+        given = adata[:n_given, :].copy()
+        given.X = given.X / np.sum(given.X, axis=1, keepdims=True)
+        mod = model()
+        mod.fit(adata.copy(), given_parameters={"asignatures": given}, init_kwargs={"seed": 1})
+        assert np.allclose(given.X, mod.asignatures.X[:n_given, :])
+    cases = {
+        "signature_scalings": rng.uniform(size=k),
+        "sample_scalings": rng.uniform(size=adata.n_obs),
+        "signature_embeddings": rng.uniform(size=(k, m)),
+        "sample_embeddings": rng.uniform(size=(adata.n_obs, m)),
+        "variance": 3,
+    }
+    for key, val in cases.items():
+        mod = model()
+        mod.fit(adata.copy(), given_parameters={key: val}, init_kwargs={"seed": 1})
+        got = {
+            "signature_scalings": lambda: mod.asignatures.obs["scalings"].values,
+            "sample_scalings": lambda: mod.adata.obs["scalings"].values,
+            "signature_embeddings": lambda: mod.asignatures.obsm["embeddings"],
+            "sample_embeddings": lambda: mod.adata.obsm["embeddings"],
+            "variance": lambda: mod.variance,
+        }[key]()
+        assert np.allclose(val, got), key
+    with pytest.raises(ValueError):
+        model().fit(adata.copy(), given_parameters={"variance": -1.0})
+    with pytest.raises(ValueError):
+        sal.models.CorrNMFDet(n_signatures=2, init_method="custom").fit(adata.copy())
+
+
+def test_iterations_match_the_oracle_on_pcawg():
+    """5 whole iterations (k = 4, dim 3) from the same start: every parameter and the ELBO history."""
+    cnt = pd.read_csv(os.path.join(ROOT, "salamander_b200", "data", "pcawg_breast_sbs.csv"), index_col=0).T
+    k, m, n_iter = 4, 3, 5
+    model = sal.models.CorrNMFDet(n_signatures=k, dim_embeddings=m, init_method="random", min_iterations=n_iter, max_iterations=n_iter,
+                                  conv_test_freq=1)
+    adata = AnnData(cnt)
+    model._setup_adata(adata)
+    np.random.seed(3)
+    model._initialize(None, {"seed": 3})
+    X = np.asarray(adata.X, dtype=float)
+    W = np.array(model.asignatures.X)
+    a, b = np.array(model.asignatures.obs["scalings"].values, dtype=float), np.array(adata.obs["scalings"].values, dtype=float)
+    L, U = np.array(model.asignatures.obsm["embeddings"]), np.array(adata.obsm["embeddings"])
+    var = float(model.variance)
+    hist_ref = []
+    for _ in range(n_iter):
+        W, a, b, L, U, var, H = oracle.update_parameters(X, W, a, b, L, U, var)
+        hist_ref.append(oracle.elbo(X, W, H, L, U, var))
+    # run the device model from the very same start
+    with model._resident():
+        model._in_fit = True
+        hist = []
+        for _ in range(n_iter):
+            model._update_parameters(None)
+            hist.append(model.objective_function())
+        model._in_fit = False
+    assert np.allclose(hist, hist_ref, rtol=1e-8), (hist, hist_ref)
+    assert np.allclose(model.asignatures.X, W, rtol=1e-6, atol=1e-12)
+    assert np.allclose(model.asignatures.obs["scalings"].values, a, rtol=1e-6)
+    assert np.allclose(model.adata.obs["scalings"].values, b, rtol=1e-6)
+    assert np.allclose(model.asignatures.obsm["embeddings"], L, rtol=1e-5, atol=1e-8)
+    assert np.allclose(model.adata.obsm["embeddings"], U, rtol=1e-5, atol=1e-7)
+    assert np.isclose(model.variance, var, rtol=1e-7)

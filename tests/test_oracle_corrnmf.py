@@ -1,0 +1,77 @@
+"""
+Pins the CorrNMF oracle (oracle/corrnmf.py) against the reference's own golden fixtures
+(tests/golden/models/corrnmf = reference tests/test_data/models/corrnmf, used by reference
+tests/test_corrnmf.py:108-175) and pins the restated Newton-CG against scipy's.  CPU only.
+"""
+
+import numpy as np
+import pytest
+from conftest import golden_path, load_counts
+
+from oracle import corrnmf, klnmf
+
+P = "models/corrnmf"
+
+
+@pytest.fixture(params=[1, 2])
+def fx(request):
+    n = request.param
+    suf = f"nsigs{n}_dim{n}.npy"
+    ld = lambda name: np.load(golden_path(P, f"{name}_{suf}"))  # noqa: E731
+    X = load_counts(P, "counts.csv").T.astype(float)  # (D, V)
+    d = dict(
+        X=X,
+        W=ld("signatures_mat_init").T,
+        a=ld("signature_scalings_init"),
+        b=ld("sample_scalings_init"),
+        L=ld("signature_embeddings_init").T,
+        U=ld("sample_embeddings_init").T,
+        var=float(ld("variance_init")),
+        aux=ld("aux"),
+        ld=ld,
+    )
+    d["H"] = corrnmf.compute_exposures(d["a"], d["b"], d["L"], d["U"])
+    return d
+
+
+def test_elbo(fx):
+    assert np.allclose(corrnmf.elbo(fx["X"], fx["W"], fx["H"], fx["L"], fx["U"], fx["var"]), fx["ld"]("objective_init"))
+
+
+def test_aux_and_signatures(fx):
+    assert np.allclose(corrnmf.compute_aux(fx["X"], fx["W"], fx["H"]), fx["aux"])
+    W = klnmf.update_W(fx["X"].T, fx["W"].T, fx["H"].T).T
+    assert np.allclose(W, fx["ld"]("signatures_mat_updated").T)
+
+
+def test_scalings_and_variance(fx):
+    assert np.allclose(corrnmf.update_signature_scalings(fx["aux"], fx["b"], fx["L"], fx["U"]), fx["ld"]("signature_scalings_updated"))
+    assert np.allclose(corrnmf.update_sample_scalings(fx["X"], fx["a"], fx["L"], fx["U"]), fx["ld"]("sample_scalings_updated"))
+    assert np.allclose(corrnmf.update_variance(fx["L"], fx["U"]), fx["ld"]("variance_updated"))
+
+
+@pytest.mark.parametrize("solver", ["scipy", "own"])
+def test_embedding_updates(fx, solver):
+    Ln = corrnmf.update_signature_embeddings(fx["aux"], fx["a"], fx["b"], fx["L"], fx["U"], fx["var"], solver)
+    assert np.allclose(Ln, fx["ld"]("signature_embeddings_updated").T)
+    Un = corrnmf.update_sample_embeddings(fx["aux"], fx["a"], fx["b"], fx["L"], fx["U"], fx["var"], solver)
+    assert np.allclose(Un, fx["ld"]("sample_embeddings_updated").T)
+
+
+def test_own_newton_cg_equals_scipy_on_random_problems():
+    """600 embedding problems of the CorrNMF kind (aux consistent with the exponential model, like inside a fit)."""
+    rng = np.random.default_rng(0)
+    worst = 0.0
+    for trial in range(300):
+        m, n_other = int(rng.integers(1, 7)), int(rng.integers(2, 40))
+        others = rng.normal(size=(n_other, m))
+        s, s_others = float(rng.normal()), rng.normal(size=n_other)
+        var = float(rng.uniform(0.3, 3.0))
+        e_true = rng.normal(size=m) * 0.7
+        aux_vec = rng.poisson(np.exp(s + s_others + others @ e_true) * 20 + 1.0).astype(float) / 20
+        e0 = rng.normal(size=m)
+        for maxiter in (3, None):
+            a = corrnmf.update_embedding(e0, others, s, s_others, var, aux_vec, maxiter, "scipy")
+            b = corrnmf.update_embedding(e0, others, s, s_others, var, aux_vec, maxiter, "own")
+            worst = max(worst, float(np.max(np.abs(a - b) / (np.abs(a) + 1e-6))))
+    assert worst < 1e-6, worst
