@@ -132,6 +132,10 @@ int sal_w_epilogue(sal_handle_t h, const void* W_in, const void* Wnum, int n_giv
  */
 int sal_clip_counts(sal_handle_t h, void* X, int64_t n, long long* n_changed, void* stream);
 
+/* H[d][j] <- max(H[d][j] * scale[j], EPSILON) in place: the exposure half of the normalise-and-clip that ends every
+ * initialisation (initialize_mat, initialization/initialize.py:116-118; normalize_WH, utils.py:155-158). */
+int sal_scale_clip_rows(sal_handle_t h, void* H, const void* scale, void* stream);
+
 /* ---- MvNMF single-CTA k x k steps (models/mvnmf.py) -------------------------------- */
 
 /* out[0] = ln det(W^T W + delta I)   (volume_logdet, mvnmf.py:19-24; LU with pivoting) */

@@ -205,6 +205,13 @@ class Workspace:
             "sal_clip_counts",
         )
 
+    def scale_clip_rows(self, H, scale) -> None:
+        """H[d][j] <- max(H[d][j] * scale[j], EPSILON) in place (sal_scale_clip_rows)."""
+        _lib.check(
+            self.lib.sal_scale_clip_rows(self._h, self._ptr(H, self.D * self.k, "H"), self._ptr(scale, self.k, "scale"), self._stream()),
+            "sal_scale_clip_rows",
+        )
+
     def mvnmf_logdet(self, W, delta: float, out) -> None:
         _lib.check(
             self.lib.sal_mvnmf_logdet(

@@ -35,6 +35,7 @@ SYMBOLS = {
     "sal_klnmf_update": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "sal_w_epilogue": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),
     "sal_clip_counts": (_i, [_vp, _vp, _i64, _vp, _vp]),
+    "sal_scale_clip_rows": (_i, [_vp, _vp, _vp, _vp]),
     "sal_mvnmf_logdet": (_i, [_vp, _vp, _d, _vp, _vp]),
     "sal_mvnmf_w_unconstrained": (_i, [_vp, _vp, _vp, _vp, _d, _d, _i, _vp, _vp]),
     "sal_mvnmf_trial": (_i, [_vp, _vp, _vp, _d, _d, _vp, _vp, _vp, _vp]),

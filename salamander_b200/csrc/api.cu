@@ -203,6 +203,13 @@ int sal_clip_counts(sal_handle_t h, void* X, int64_t n, long long* n_changed, vo
     return sal_launch_clip_counts(h, X, n, n_changed, (cudaStream_t)stream);
 }
 
+int sal_scale_clip_rows(sal_handle_t h, void* H, const void* scale, void* stream) {
+    SAL_CHECK_ARG(h && scale && (h->D == 0 || H), "null argument");
+    if (h->D == 0) return 0;
+    SAL_CUDA(cudaSetDevice(h->device));
+    return sal_launch_scale_clip_rows(h, H, scale, (cudaStream_t)stream);
+}
+
 int sal_mvnmf_logdet(sal_handle_t h, const void* W, double delta, double* out, void* stream) {
     SAL_CHECK_ARG(h && W && out, "null argument");
     SAL_CUDA(cudaSetDevice(h->device));

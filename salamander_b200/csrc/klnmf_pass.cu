@@ -394,6 +394,13 @@ __global__ void __launch_bounds__(256) clip_counts_kernel(T* X, int64_t n, unsig
     if (threadIdx.x == 0 && s_cnt) atomicAdd(n_changed, (unsigned long long)s_cnt);
 }
 
+template <typename T>
+__global__ void __launch_bounds__(256) scale_clip_rows_kernel(T* H, const T* scale, int64_t n, int k) {
+    const T eps = (T)SAL_EPS_F32;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        H[i] = max(H[i] * scale[i % k], eps);
+}
+
 template <typename T, int KP>
 size_t pass_smem_bytes() {
     using C = Cfg<T>;
@@ -493,6 +500,18 @@ int sal_launch_clip_counts(sal_ctx* c, void* X, int64_t n, long long* n_changed,
         clip_counts_kernel<float><<<grid, 256, 0, st>>>((float*)X, n, (unsigned long long*)n_changed);
     else
         clip_counts_kernel<double><<<grid, 256, 0, st>>>((double*)X, n, (unsigned long long*)n_changed);
+    SAL_CUDA(cudaGetLastError());
+    c->launches++;
+    return 0;
+}
+
+int sal_launch_scale_clip_rows(sal_ctx* c, void* H, const void* scale, cudaStream_t st) {
+    const int64_t n = c->D * c->k, want = (n + 255) / 256;
+    const int grid = (int)(want < (int64_t)c->n_sm * 8 ? want : (int64_t)c->n_sm * 8);
+    if (c->dtype == SAL_F32)
+        scale_clip_rows_kernel<float><<<grid, 256, 0, st>>>((float*)H, (const float*)scale, n, c->k);
+    else
+        scale_clip_rows_kernel<double><<<grid, 256, 0, st>>>((double*)H, (const double*)scale, n, c->k);
     SAL_CUDA(cudaGetLastError());
     c->launches++;
     return 0;

@@ -71,6 +71,7 @@ int sal_pass_smem_bytes(int dtype, int KP);
 int sal_launch_w_epilogue(sal_ctx* c, const void* W_in, const void* Wnum, int n_given, int clip_given,
                           void* W_out, cudaStream_t st);
 int sal_launch_clip_counts(sal_ctx* c, void* X, int64_t n, long long* n_changed, cudaStream_t st);
+int sal_launch_scale_clip_rows(sal_ctx* c, void* H, const void* scale, cudaStream_t st);
 int sal_launch_mvnmf_logdet(sal_ctx* c, const void* W, double delta, double* out, cudaStream_t st);
 int sal_launch_mvnmf_w_unc(sal_ctx* c, const void* W, const void* N, const void* hsum, double lam,
                            double delta, int n_given, void* W_unc, cudaStream_t st);

@@ -34,9 +34,16 @@ GIVEN_PARAMETERS_CORRNMF = [
 ]
 
 
-def initialize_mat(data_mat, n_signatures, method="nndsvd", given_signatures_mat=None, **kwargs):
+DEFER_MIN_SIZE = 1 << 22  # exposure matrices at least this large are rescaled / clipped on the device
+
+
+def initialize_mat(data_mat, n_signatures, method="nndsvd", given_signatures_mat=None, _defer=None, **kwargs):
     """(signatures_mat (k,V), exposures_mat (D,k)): method dispatch, given signatures written over the
-    first rows, then normalise columns of W and clip both to EPSILON (reference initialize.py:44-119)."""
+    first rows, then normalise columns of W and clip both to EPSILON (reference initialize.py:44-119).
+
+    ``_defer`` (a dict, internal): for large custom exposure matrices the second half of that last step,
+    ``H <- clip(H * colsum(W))``, is left to the device right after the upload (sal_scale_clip_rows); the
+    column sums are returned in ``_defer['exposure_scale']`` and the exposures are handed back untouched."""
     value_checker("method", method, _INIT_METHODS)
     if method == "custom":
         sigs, expo = init_custom(data_mat, n_signatures, **kwargs)
@@ -58,6 +65,10 @@ def initialize_mat(data_mat, n_signatures, method="nndsvd", given_signatures_mat
             raise ValueError("The given signature matrix contains too many signatures.")
         sigs[:n_given, :] = given_signatures_mat.copy()
 
+    if _defer is not None and method == "custom" and expo.size >= DEFER_MIN_SIZE:
+        scale = np.sum(sigs, axis=1)
+        _defer["exposure_scale"] = scale
+        return (sigs / scale[:, None]).clip(EPSILON), expo
     W, H = normalize_WH(sigs.T, expo.T)
     W, H = W.clip(EPSILON), H.clip(EPSILON)
     return W.T, H.T
@@ -74,14 +85,14 @@ def check_given_asignatures(given_asignatures, adata, n_signatures) -> None:
         raise ValueError("The number of given signatures exceeds the number of signatures to initialize.")
 
 
-def initialize_base(adata, n_signatures, method="nndsvd", given_asignatures=None, **kwargs):
+def initialize_base(adata, n_signatures, method="nndsvd", given_asignatures=None, _defer=None, **kwargs):
     """Signature AnnData (names 'Sig1..', given signatures first, keeping their names) plus the
     exposure matrix (reference initialize.py:158-218)."""
     given_mat = None
     if given_asignatures is not None:
         check_given_asignatures(given_asignatures, adata, n_signatures)
         given_mat = np.asarray(given_asignatures.X)
-    sigs, expo = initialize_mat(np.asarray(adata.X), n_signatures, method, given_mat, **kwargs)
+    sigs, expo = initialize_mat(np.asarray(adata.X), n_signatures, method, given_mat, _defer=_defer, **kwargs)
     asignatures = AnnData(np.ascontiguousarray(sigs))
     asignatures.var_names = adata.var_names
     asignatures.obs_names = [f"Sig{j + 1}" for j in range(n_signatures)]
@@ -98,11 +109,11 @@ def check_given_parameters_standard_nmf(adata, n_signatures, given_parameters) -
         check_given_asignatures(given_parameters["asignatures"], adata, n_signatures)
 
 
-def initialize_standard_nmf(adata, n_signatures, method="nndsvd", given_parameters=None, **kwargs):
+def initialize_standard_nmf(adata, n_signatures, method="nndsvd", given_parameters=None, _defer=None, **kwargs):
     """Sets ``adata.obsm['exposures']`` and returns the signature AnnData (reference initialize.py:232-255)."""
     given_parameters = {} if given_parameters is None else given_parameters.copy()
     check_given_parameters_standard_nmf(adata, n_signatures, given_parameters)
-    asignatures, expo = initialize_base(adata, n_signatures, method, given_parameters.get("asignatures"), **kwargs)
+    asignatures, expo = initialize_base(adata, n_signatures, method, given_parameters.get("asignatures"), _defer=_defer, **kwargs)
     adata.obsm["exposures"] = np.ascontiguousarray(expo)
     return asignatures
 

@@ -64,6 +64,7 @@ class SignatureNMF(ABC):
 
         self._dev = None  # device-resident state while fitting
         self._clip_on_device = False
+        self._exposure_scale = None
         self._in_fit = False
         self.n_iterations = 0
 

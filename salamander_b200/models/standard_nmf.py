@@ -57,6 +57,10 @@ class StandardState:
             model._clip_on_device = False
         self.W = self.upload(W_host)
         self.H = self.upload(H_host[self.lo : self.hi])
+        scale = getattr(model, "_exposure_scale", None)
+        if scale is not None:
+            self.ws.scale_clip_rows(self.H, self.upload(np.asarray(scale, dtype=np.float64)))
+            model._exposure_scale = None
         self.W_next = torch.empty_like(self.W)  # the joint update writes W here (H needs the old W), then they swap
         self.Wnum = torch.zeros((self.k, self.V), dtype=dt, device=dev)
         self.obj = torch.zeros(1, dtype=torch.float64, device=dev)
@@ -100,9 +104,12 @@ class StandardNMF(SignatureNMF):
     def _initialize(self, given_parameters=None, init_kwargs=None) -> None:
         """Initialise signatures and exposures; given signatures are kept fixed (reference :32-58)."""
         init_kwargs = {} if init_kwargs is None else init_kwargs.copy()
+        defer: dict[str, Any] = {}
         self.asignatures = initialize_standard_nmf(
-            self.adata, self.n_signatures, self.init_method, given_parameters, **init_kwargs
+            self.adata, self.n_signatures, self.init_method, given_parameters, _defer=defer, **init_kwargs
         )
+        # large custom exposures: H <- clip(H * colsum(W)) (reference initialize.py:116-118) runs on the device
+        self._exposure_scale = defer.get("exposure_scale")
 
     def _to_device(self) -> None:
         self._dev = StandardState(self)

@@ -208,3 +208,23 @@ def test_reconstruction_error(dtype):
     model.compute_reconstruction_errors()
     assert np.allclose(adata.obs["reconstruction_error"].values, ref, rtol=1e-9 if dtype == "float64" else 2e-3, atol=1e-2 if dtype == "float32" else 0)
     assert np.isclose(model.reconstruction_error, ref.sum(), rtol=1e-5)
+
+
+def test_custom_init_rescaled_on_device_equals_host_path(monkeypatch):
+    """Large custom exposure matrices are normalised / clipped on the device (sal_scale_clip_rows) instead of on the
+    host (reference initialize.py:116-118); both routes must give the same fit."""
+    from salamander_b200.initialization import initialize
+
+    rng = np.random.default_rng(11)
+    adata = pcawg_adata()
+    W0 = rng.dirichlet(np.ones(96), size=4) * rng.uniform(0.5, 2.0, size=(4, 1))  # rows deliberately not normalised
+    H0 = rng.gamma(1.0, 50.0, size=(192, 4))
+    H0[3, 2] = 0.0  # clipped to EPSILON by either route
+    res = []
+    for min_size in (1 << 22, 1):
+        monkeypatch.setattr(initialize, "DEFER_MIN_SIZE", min_size)
+        model = sal.models.KLNMF(n_signatures=4, init_method="custom", min_iterations=30, max_iterations=30, dtype="float64")
+        model.fit(adata.copy(), init_kwargs={"signatures_mat": W0.copy(), "exposures_mat": H0.copy()})
+        res.append((model.asignatures.X, model.adata.obsm["exposures"], model.history["objective_function"]))
+    assert np.allclose(res[0][0], res[1][0], rtol=1e-13) and np.allclose(res[0][1], res[1][1], rtol=1e-13)
+    assert np.allclose(res[0][2], res[1][2], rtol=1e-13)
