@@ -181,6 +181,11 @@ int sal_corrnmf_signature_scalings_finish(sal_handle_t h, const double* sums, vo
  * signature (others = samples; :88-113; single-GPU: the sums over samples are taken over this rank's rows). */
 int sal_corrnmf_sample_embeddings(sal_handle_t h, const void* auxT, const void* a, const void* b, const void* L, void* U,
                                   int m, double variance, int maxiter, void* stream);
+/* Multimodal variant (MultimodalCorrNMF.update_sample_embeddings, models/mmcorrnmf.py:398-428): the handle's k is the
+ * TOTAL number of signatures over all modalities; auxT [D][k], a [k], L [k][m] are the modalities' values concatenated
+ * and b_mat [D][k] holds, for every sample, its scaling in the modality each signature belongs to. */
+int sal_corrnmf_sample_embeddings_mm(sal_handle_t h, const void* auxT, const void* a, const void* b_mat, const void* L,
+                                     void* U, int m, double variance, int maxiter, void* stream);
 int sal_corrnmf_signature_embeddings(sal_handle_t h, const void* auxT, const void* a, const void* b, void* L,
                                      const void* U, int m, double variance, void* stream);
 /* out[0] = sum L^2, out[1] = sum U^2 (update_variance corrnmf_det.py:60-69, ELBO priors _utils_corrnmf.py:93-98),

@@ -8,7 +8,7 @@ step is hand-written CUDA behind the C ABI in include/salamander_b200.h.
 """
 
 from . import models
-from ._anndata import AnnData
+from ._anndata import AnnData, MuData
 
 __version__ = "0.1.0"
-__all__ = ["models", "AnnData"]
+__all__ = ["models", "AnnData", "MuData"]

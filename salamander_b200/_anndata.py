@@ -106,3 +106,42 @@ except Exception:  # pragma: no cover
             if all(key in a.obsm for a in adatas):
                 out.obsm[key] = np.concatenate([np.asarray(a.obsm[key]) for a in adatas], axis=0)
         return out
+
+
+try:  # pragma: no cover - not installed in the build image
+    from mudata import MuData  # type: ignore
+
+    HAVE_MUDATA = True
+except Exception:  # pragma: no cover
+    HAVE_MUDATA = False
+
+    class MuData:  # type: ignore[no-redef]
+        """Minimal stand-in for ``mudata.MuData``: named AnnData modalities over the same samples plus the shared
+        ``obsm`` (multimodal correlated NMF keeps the joint sample embeddings there)."""
+
+        def __init__(self, mods: dict):
+            self.mod = dict(mods)
+            self.obsm: dict = {}
+            first = next(iter(self.mod.values()), None)
+            self.obs = pd.DataFrame(index=first.obs_names if first is not None and first.X is not None else pd.Index([]))
+
+        @property
+        def n_mod(self) -> int:
+            return len(self.mod)
+
+        @property
+        def obs_names(self):
+            return self.obs.index
+
+        @property
+        def n_obs(self) -> int:
+            return len(self.obs.index)
+
+        def __getitem__(self, name: str):
+            return self.mod[name]
+
+        def update(self) -> None:
+            return
+
+        def __repr__(self) -> str:
+            return f"MuData object with n_obs = {self.n_obs}, modalities {list(self.mod)}"

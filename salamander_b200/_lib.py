@@ -46,6 +46,7 @@ SYMBOLS = {
     "sal_corrnmf_signature_scalings_sums": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
     "sal_corrnmf_signature_scalings_finish": (_i, [_vp, _vp, _vp, _vp]),
     "sal_corrnmf_sample_embeddings": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _d, _i, _vp]),
+    "sal_corrnmf_sample_embeddings_mm": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _d, _i, _vp]),
     "sal_corrnmf_signature_embeddings": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _d, _vp]),
     "sal_corrnmf_norms": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp]),
 }

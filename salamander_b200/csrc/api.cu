@@ -278,7 +278,15 @@ int sal_corrnmf_sample_embeddings(sal_handle_t h, const void* auxT, const void* 
     SAL_CORR_COMMON(m);
     SAL_CHECK_ARG(a && L && (h->D == 0 || (auxT && b && U)), "null argument");
     SAL_CHECK_ARG(variance > 0.0 && maxiter >= 0, "variance must be positive, maxiter >= 0");
-    return sal_launch_corrnmf_sample_embeddings(h, auxT, a, b, L, U, m, variance, maxiter, (cudaStream_t)stream);
+    return sal_launch_corrnmf_sample_embeddings(h, auxT, a, b, 0, L, U, m, variance, maxiter, (cudaStream_t)stream);
+}
+
+int sal_corrnmf_sample_embeddings_mm(sal_handle_t h, const void* auxT, const void* a, const void* b_mat, const void* L, void* U, int m,
+                                     double variance, int maxiter, void* stream) {
+    SAL_CORR_COMMON(m);
+    SAL_CHECK_ARG(a && L && (h->D == 0 || (auxT && b_mat && U)), "null argument");
+    SAL_CHECK_ARG(variance > 0.0 && maxiter >= 0, "variance must be positive, maxiter >= 0");
+    return sal_launch_corrnmf_sample_embeddings(h, auxT, a, b_mat, 1, L, U, m, variance, maxiter, (cudaStream_t)stream);
 }
 
 int sal_corrnmf_signature_embeddings(sal_handle_t h, const void* auxT, const void* a, const void* b, void* L, const void* U, int m,

@@ -234,14 +234,16 @@ struct SampleProblem {
     const double* others;    // [k][m] shared
     const double* s_others;  // [k]    shared
     const double* aux;       // [k]    local
-    double s, inv_var;
+    const double* s_vec;     // [k]    local: the sample's scaling for every "other" (one value repeated for a single
+                             //        modality; per-modality values in multimodal CorrNMF, mmcorrnmf.py:413-419)
+    double inv_var;
     int k, m;
     __device__ double f(const double* x) const {
         double acc = 0.0, nrm = 0.0;
         for (int i = 0; i < k; ++i) {
             double sp = 0.0;
             for (int j = 0; j < m; ++j) sp += others[i * m + j] * x[j];
-            acc += sp * aux[i] - exp(s + s_others[i] + sp);
+            acc += sp * aux[i] - exp(s_vec[i] + s_others[i] + sp);
         }
         for (int j = 0; j < m; ++j) nrm += x[j] * x[j];
         return -(acc - 0.5 * nrm * inv_var);
@@ -251,7 +253,7 @@ struct SampleProblem {
         for (int i = 0; i < k; ++i) {
             double sp = 0.0;
             for (int j = 0; j < m; ++j) sp += others[i * m + j] * x[j];
-            const double w = exp(s + s_others[i] + sp) - aux[i];
+            const double w = exp(s_vec[i] + s_others[i] + sp) - aux[i];
             for (int j = 0; j < m; ++j) g[j] += w * others[i * m + j];
         }
     }
@@ -261,16 +263,17 @@ struct SampleProblem {
         for (int i = 0; i < k; ++i) {
             double sp = 0.0;
             for (int j = 0; j < m; ++j) sp += others[i * m + j] * x[j];
-            const double w = exp(s + s_others[i] + sp);
+            const double w = exp(s_vec[i] + s_others[i] + sp);
             for (int p = 0; p < m; ++p)
                 for (int q = 0; q < m; ++q) A[p * m + q] += w * others[i * m + p] * others[i * m + q];
         }
     }
 };
 
+// b: [D] (b_is_matrix = 0, one scaling per sample) or [D][k] (b_is_matrix = 1, one per sample and signature)
 template <typename T>
-__global__ void __launch_bounds__(128) sample_embeddings_kernel(const T* auxT, const T* a, const T* b, const T* L, T* U, int64_t D,
-                                                               int k, int m, double variance, int maxiter) {
+__global__ void __launch_bounds__(128) sample_embeddings_kernel(const T* auxT, const T* a, const T* b, int b_is_matrix, const T* L, T* U,
+                                                               int64_t D, int k, int m, double variance, int maxiter) {
     __shared__ double sL[SAL_KMAX * MAXM];
     __shared__ double sa[SAL_KMAX];
     for (int i = threadIdx.x; i < k * m; i += blockDim.x) sL[i] = (double)L[i];
@@ -278,10 +281,10 @@ __global__ void __launch_bounds__(128) sample_embeddings_kernel(const T* auxT, c
     __syncthreads();
     const int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= D) return;
-    double aux[SAL_KMAX], x[MAXM];
-    for (int i = 0; i < k; ++i) aux[i] = (double)auxT[d * k + i];
+    double aux[SAL_KMAX], sv[SAL_KMAX], x[MAXM];
+    for (int i = 0; i < k; ++i) aux[i] = (double)auxT[d * k + i], sv[i] = (double)(b_is_matrix ? b[d * k + i] : b[d]);
     for (int j = 0; j < m; ++j) x[j] = (double)U[d * m + j];
-    SampleProblem p{sL, sa, aux, (double)b[d], 1.0 / variance, k, m};
+    SampleProblem p{sL, sa, aux, sv, 1.0 / variance, k, m};
     newton_cg(p, x, m, maxiter);
     for (int j = 0; j < m; ++j) U[d * m + j] = (T)snap_eps(x[j]);
 }
@@ -516,12 +519,12 @@ int sal_launch_corrnmf_signature_scalings_finish(sal_ctx* c, const double* sums,
     return 0;
 }
 
-int sal_launch_corrnmf_sample_embeddings(sal_ctx* c, const void* auxT, const void* a, const void* b, const void* L, void* U, int m,
-                                         double variance, int maxiter, cudaStream_t st) {
+int sal_launch_corrnmf_sample_embeddings(sal_ctx* c, const void* auxT, const void* a, const void* b, int b_is_matrix, const void* L,
+                                         void* U, int m, double variance, int maxiter, cudaStream_t st) {
     if (c->D == 0) return 0;
     const int grid = (int)((c->D + 127) / 128);
-    SAL_DISPATCH_T(c, (sample_embeddings_kernel<float><<<grid, 128, 0, st>>>((const float*)auxT, (const float*)a, (const float*)b, (const float*)L, (float*)U, c->D, c->k, m, variance, maxiter)),
-                   (sample_embeddings_kernel<double><<<grid, 128, 0, st>>>((const double*)auxT, (const double*)a, (const double*)b, (const double*)L, (double*)U, c->D, c->k, m, variance, maxiter)));
+    SAL_DISPATCH_T(c, (sample_embeddings_kernel<float><<<grid, 128, 0, st>>>((const float*)auxT, (const float*)a, (const float*)b, b_is_matrix, (const float*)L, (float*)U, c->D, c->k, m, variance, maxiter)),
+                   (sample_embeddings_kernel<double><<<grid, 128, 0, st>>>((const double*)auxT, (const double*)a, (const double*)b, b_is_matrix, (const double*)L, (double*)U, c->D, c->k, m, variance, maxiter)));
     SAL_CUDA(cudaGetLastError());
     c->launches++;
     return 0;

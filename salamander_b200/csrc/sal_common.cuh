@@ -86,8 +86,8 @@ int sal_launch_corrnmf_sample_scalings(sal_ctx* c, const void* xsum, const void*
 int sal_launch_corrnmf_signature_scalings_sums(sal_ctx* c, const void* auxT, const void* b, const void* L, const void* U, int m,
                                                double* sums, cudaStream_t st);
 int sal_launch_corrnmf_signature_scalings_finish(sal_ctx* c, const double* sums, void* a, cudaStream_t st);
-int sal_launch_corrnmf_sample_embeddings(sal_ctx* c, const void* auxT, const void* a, const void* b, const void* L, void* U, int m,
-                                         double variance, int maxiter, cudaStream_t st);
+int sal_launch_corrnmf_sample_embeddings(sal_ctx* c, const void* auxT, const void* a, const void* b, int b_is_matrix, const void* L,
+                                         void* U, int m, double variance, int maxiter, cudaStream_t st);
 int sal_launch_corrnmf_signature_embeddings(sal_ctx* c, const void* auxT, const void* a, const void* b, void* L, const void* U, int m,
                                             double variance, cudaStream_t st);
 int sal_launch_corrnmf_norms(sal_ctx* c, const void* L, const void* U, int m, const void* X_or_null, double* out, cudaStream_t st);

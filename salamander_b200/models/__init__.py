@@ -2,6 +2,7 @@
 
 from .corrnmf import CorrNMFDet
 from .klnmf import KLNMF
+from .mmcorrnmf import MultimodalCorrNMF
 from .mvnmf import MvNMF
 
-__all__ = ["CorrNMFDet", "KLNMF", "MvNMF"]
+__all__ = ["CorrNMFDet", "KLNMF", "MultimodalCorrNMF", "MvNMF"]

@@ -75,3 +75,50 @@ def test_own_newton_cg_equals_scipy_on_random_problems():
             b = corrnmf.update_embedding(e0, others, s, s_others, var, aux_vec, maxiter, "own")
             worst = max(worst, float(np.max(np.abs(a - b) / (np.abs(a) + 1e-6))))
     assert worst < 1e-6, worst
+
+
+# ---- multimodal correlated NMF (reference tests/test_mmcorrnmf.py:132-330, fixtures models/multimodal_corrnmf) -----
+PM = "models/multimodal_corrnmf"
+
+
+@pytest.fixture
+def mm():
+    from oracle import mmcorrnmf
+
+    ld = lambda name: np.load(golden_path(PM, f"{name}.npy"))  # noqa: E731
+    mods = []
+    for n in range(2):
+        mods.append(
+            dict(
+                X=load_counts(PM, f"model{n}_counts.csv").T.astype(float),
+                W=ld(f"model{n}_signatures_mat_init").T,
+                a=ld(f"model{n}_signature_scalings_init"),
+                b=ld(f"model{n}_sample_scalings_init"),
+                L=ld(f"model{n}_signature_embeddings_init").T,
+            )
+        )
+    U = ld("sample_embeddings_init").T
+    mmcorrnmf.compute_exposures(mods, U)
+    return dict(mods=mods, U=U, var=float(ld("variance_init")), ld=ld, mm=mmcorrnmf)
+
+
+def test_mm_elbo_and_aux(mm):
+    assert np.allclose(mm["mm"].elbo(mm["mods"], mm["U"], mm["var"]), mm["ld"]("objective_init"))
+    auxs = mm["mm"].compute_auxs(mm["mods"])
+    for n, (md, aux) in enumerate(zip(mm["mods"], auxs)):
+        p = mm["ld"](f"model{n}_p")  # (V, k, D)
+        assert np.allclose(aux, np.einsum("vd,vkd->kd", md["X"].T, p))
+
+
+@pytest.mark.parametrize("solver", ["scipy", "own"])
+def test_mm_updates(mm, solver):
+    mods, U, var, ld, M = mm["mods"], mm["U"], mm["var"], mm["ld"], mm["mm"]
+    auxs = [np.einsum("vd,vkd->kd", md["X"].T, ld(f"model{n}_p")) for n, md in enumerate(mods)]
+    for n, (md, aux) in enumerate(zip(mods, auxs)):
+        assert np.allclose(corrnmf.update_sample_scalings(md["X"], md["a"], md["L"], U), ld(f"model{n}_sample_scalings_updated"))
+        assert np.allclose(corrnmf.update_signature_scalings(aux, md["b"], md["L"], U), ld(f"model{n}_signature_scalings_updated"))
+        assert np.allclose(corrnmf.update_signature_embeddings(aux, md["a"], md["b"], md["L"], U, var, solver),
+                           ld(f"model{n}_signature_embeddings_updated").T)
+        assert np.allclose(klnmf.update_W(md["X"].T, md["W"].T, md["H"].T).T, ld(f"model{n}_signatures_mat_updated").T)
+    assert np.allclose(M.update_sample_embeddings(mods, auxs, U, var, solver), ld("sample_embeddings_updated").T)
+    assert np.allclose(M.update_variance(mods, U), ld("variance_updated"))
