@@ -80,6 +80,7 @@ int sal_destroy(sal_handle_t h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
     cudaFree(h->partial_wnum), cudaFree(h->partial_obj), cudaFree(h->partial_hsum);
+    if (h->norm_counter) cudaFree(h->norm_counter);
     if (h->ev) {
         for (cudaEvent_t e : *h->ev) cudaEventDestroy(e);
         delete h->ev;

@@ -14,7 +14,11 @@
 // line search with SciPy's defaults -- the third-party algorithm the reference calls at _utils_corrnmf.py:400-407;
 // oracle/corrnmf.py::newton_cg is the same restatement in numpy and is pinned against scipy itself.
 // All arithmetic is float64 whatever the handle's storage dtype.
+#include <cooperative_groups.h>
+
 #include "sal_common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -297,10 +301,12 @@ constexpr int SIG_THREADS = 256;
 template <typename T>
 struct SignatureProblem {
     const T *U, *b, *auxT;  // U [D][m], b [D], auxT [D][k]
-    double* red;            // shared [SIG_THREADS / 32][1 + MAXM + MAXM * MAXM] + result slot
+    double* red;            // shared [SIG_THREADS / 32][1 + MAXM + MAXM * MAXM]
+    double* cl;             // shared [1 + MAXM + MAXM * MAXM]: this CTA's totals, read by the other CTAs of the cluster
     double s, inv_var;
     int64_t D;
     int k, m, j;
+    int rank, nrank;        // position in the thread-block cluster that shares signature j (samples are interleaved)
 
     // fixed-order block reduction of n values per thread; result broadcast to all threads through shared memory
     __device__ void reduce(double* v, int n) const {
@@ -318,10 +324,22 @@ struct SignatureProblem {
             v[i] = t;
         }
         __syncthreads();
+        if (nrank > 1) {  // sum the CTAs' totals in rank order through distributed shared memory
+            cg::cluster_group cluster = cg::this_cluster();
+            if (threadIdx.x == 0)
+                for (int i = 0; i < n; ++i) cl[i] = v[i];
+            cluster.sync();
+            for (int i = 0; i < n; ++i) {
+                double t = 0.0;
+                for (int r = 0; r < nrank; ++r) t += cluster.map_shared_rank(cl, r)[i];
+                v[i] = t;
+            }
+            cluster.sync();
+        }
     }
     __device__ double f(const double* x) const {
         double acc = 0.0;
-        for (int64_t d = threadIdx.x; d < D; d += SIG_THREADS) {
+        for (int64_t d = (int64_t)rank * SIG_THREADS + threadIdx.x; d < D; d += (int64_t)nrank * SIG_THREADS) {
             double sp = 0.0;
             for (int q = 0; q < m; ++q) sp += (double)U[d * m + q] * x[q];
             acc += sp * (double)auxT[d * k + j] - exp(s + (double)b[d] + sp);
@@ -333,7 +351,7 @@ struct SignatureProblem {
     }
     __device__ void grad(const double* x, double* g) const {
         for (int q = 0; q < m; ++q) g[q] = 0.0;
-        for (int64_t d = threadIdx.x; d < D; d += SIG_THREADS) {
+        for (int64_t d = (int64_t)rank * SIG_THREADS + threadIdx.x; d < D; d += (int64_t)nrank * SIG_THREADS) {
             double sp = 0.0;
             for (int q = 0; q < m; ++q) sp += (double)U[d * m + q] * x[q];
             const double w = exp(s + (double)b[d] + sp) - (double)auxT[d * k + j];
@@ -344,7 +362,7 @@ struct SignatureProblem {
     }
     __device__ void hess(const double* x, double* A) const {
         for (int q = 0; q < m * m; ++q) A[q] = 0.0;
-        for (int64_t d = threadIdx.x; d < D; d += SIG_THREADS) {
+        for (int64_t d = (int64_t)rank * SIG_THREADS + threadIdx.x; d < D; d += (int64_t)nrank * SIG_THREADS) {
             double sp = 0.0;
             for (int q = 0; q < m; ++q) sp += (double)U[d * m + q] * x[q];
             const double w = exp(s + (double)b[d] + sp);
@@ -360,12 +378,16 @@ template <typename T>
 __global__ void __launch_bounds__(SIG_THREADS) signature_embeddings_kernel(const T* auxT, const T* a, const T* b, T* L, const T* U,
                                                                           int64_t D, int k, int m, double variance) {
     __shared__ double red[(SIG_THREADS / 32) * (1 + MAXM + MAXM * MAXM)];
-    const int j = blockIdx.x;
+    __shared__ double cl[1 + MAXM + MAXM * MAXM];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int nrank = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+    const int j = blockIdx.x / nrank;  // one cluster per signature; every CTA of it runs the same Newton-CG on the same numbers
     double x[MAXM];
     for (int q = 0; q < m; ++q) x[q] = (double)L[j * m + q];
-    SignatureProblem<T> p{U, b, auxT, red, (double)a[j], 1.0 / variance, D, k, m, j};
+    SignatureProblem<T> p{U, b, auxT, red, cl, (double)a[j], 1.0 / variance, D, k, m, j, rank, nrank};
+    if (nrank > 1) cluster.sync();  // nobody writes L[j] before everybody has read it
     newton_cg(p, x, m, 200 * m);
-    if (threadIdx.x == 0)
+    if (rank == 0 && threadIdx.x == 0)
         for (int q = 0; q < m; ++q) L[j * m + q] = (T)snap_eps(x[q]);
 }
 
@@ -443,20 +465,36 @@ __global__ void signature_scalings_finish_kernel(const double* sums, int k, T* a
     if (j < k) a[j] = (T)(log(sums[j]) - log(sums[k + j]));
 }
 
-// out[0] = sum L^2, out[1] = sum U^2 (this rank's samples), out[2] = sum_x lnGamma(1 + x) when X != null
+// out[0] = sum L^2, out[1] = sum U^2 (this rank's samples), out[2] = sum_x lnGamma(1 + x) when X != null.
+// blockIdx.y selects the quantity, NORM_BLOCKS blocks each leave a partial; the last block to finish adds them in order.
+constexpr int NORM_BLOCKS = 64;
 template <typename T>
-__global__ void __launch_bounds__(256) norms_kernel(const T* L, int64_t nL, const T* U, int64_t nU, const T* X, int64_t nX, double* out) {
+__global__ void __launch_bounds__(256) norms_kernel(const T* L, int64_t nL, const T* U, int64_t nU, const T* X, int64_t nX,
+                                                   double* partial, unsigned int* counter, double* out) {
     __shared__ double s_red[8];
+    __shared__ bool last;
+    const int q = blockIdx.y;
+    const T* src = q == 0 ? L : q == 1 ? U : X;
+    const int64_t n = q == 0 ? nL : q == 1 ? nU : nX;
     double s = 0.0;
-    const T* src = blockIdx.x == 0 ? L : blockIdx.x == 1 ? U : X;
-    const int64_t n = blockIdx.x == 0 ? nL : blockIdx.x == 1 ? nU : nX;
-    if (blockIdx.x < 2) {
-        for (int64_t i = threadIdx.x; i < n; i += 256) s += (double)src[i] * (double)src[i];
-    } else {
-        for (int64_t i = threadIdx.x; i < n; i += 256) s += lgamma(1.0 + (double)src[i]);
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)NORM_BLOCKS * 256) {
+        const double v = (double)src[i];
+        s += q < 2 ? v * v : lgamma(1.0 + v);
     }
     s = block_sum_256(s, s_red);
-    if (threadIdx.x == 0) out[blockIdx.x] = s;
+    if (threadIdx.x == 0) {
+        partial[q * NORM_BLOCKS + blockIdx.x] = s;
+        __threadfence();
+        last = atomicAdd(&counter[q], 1u) == NORM_BLOCKS - 1;
+    }
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        __threadfence();
+        double t = 0.0;
+        for (int b = 0; b < NORM_BLOCKS; ++b) t += ((volatile double*)partial)[q * NORM_BLOCKS + b];
+        out[q] = t;
+        counter[q] = 0;
+    }
 }
 
 }  // namespace
@@ -532,17 +570,37 @@ int sal_launch_corrnmf_sample_embeddings(sal_ctx* c, const void* auxT, const voi
 
 int sal_launch_corrnmf_signature_embeddings(sal_ctx* c, const void* auxT, const void* a, const void* b, void* L, const void* U, int m,
                                             double variance, cudaStream_t st) {
-    SAL_DISPATCH_T(c, (signature_embeddings_kernel<float><<<c->k, SIG_THREADS, 0, st>>>((const float*)auxT, (const float*)a, (const float*)b, (float*)L, (const float*)U, c->D, c->k, m, variance)),
-                   (signature_embeddings_kernel<double><<<c->k, SIG_THREADS, 0, st>>>((const double*)auxT, (const double*)a, (const double*)b, (double*)L, (const double*)U, c->D, c->k, m, variance)));
+    // one thread-block cluster per signature: 8 CTAs share the sums over samples once there is enough work for them
+    const int csize = c->D >= 8 * 4 * SIG_THREADS ? 8 : 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(c->k * csize), cfg.blockDim = dim3(SIG_THREADS), cfg.dynamicSmemBytes = 0, cfg.stream = st;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = csize, attr.val.clusterDim.y = 1, attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr, cfg.numAttrs = 1;
+    const int64_t D = c->D;
+    const int k = c->k;
+    if (c->dtype == SAL_F32)
+        SAL_CUDA(cudaLaunchKernelEx(&cfg, signature_embeddings_kernel<float>, (const float*)auxT, (const float*)a, (const float*)b, (float*)L,
+                                    (const float*)U, D, k, m, variance));
+    else
+        SAL_CUDA(cudaLaunchKernelEx(&cfg, signature_embeddings_kernel<double>, (const double*)auxT, (const double*)a, (const double*)b,
+                                    (double*)L, (const double*)U, D, k, m, variance));
     SAL_CUDA(cudaGetLastError());
     c->launches++;
     return 0;
 }
 
 int sal_launch_corrnmf_norms(sal_ctx* c, const void* L, const void* U, int m, const void* X_or_null, double* out, cudaStream_t st) {
-    const int blocks = X_or_null ? 3 : 2;
-    SAL_DISPATCH_T(c, (norms_kernel<float><<<blocks, 256, 0, st>>>((const float*)L, (int64_t)c->k * m, (const float*)U, c->D * m, (const float*)X_or_null, c->D * c->V, out)),
-                   (norms_kernel<double><<<blocks, 256, 0, st>>>((const double*)L, (int64_t)c->k * m, (const double*)U, c->D * m, (const double*)X_or_null, c->D * c->V, out)));
+    // scratch: the objective partials of the pass (>= 296 doubles) hold the 3 x 64 partials; the counters follow out[3]
+    static_assert(3 * NORM_BLOCKS <= 148 * SAL_KMAX, "partial_hsum has n_sm * SAL_KMAX slots at least");
+    if (!c->norm_counter) {
+        SAL_CUDA(cudaMalloc((void**)&c->norm_counter, 4 * sizeof(unsigned int)));
+        SAL_CUDA(cudaMemsetAsync(c->norm_counter, 0, 4 * sizeof(unsigned int), st));
+    }
+    const dim3 grid(NORM_BLOCKS, X_or_null ? 3 : 2);
+    SAL_DISPATCH_T(c, (norms_kernel<float><<<grid, 256, 0, st>>>((const float*)L, (int64_t)c->k * m, (const float*)U, c->D * m, (const float*)X_or_null, c->D * c->V, c->partial_hsum, c->norm_counter, out)),
+                   (norms_kernel<double><<<grid, 256, 0, st>>>((const double*)L, (int64_t)c->k * m, (const double*)U, c->D * m, (const double*)X_or_null, c->D * c->V, c->partial_hsum, c->norm_counter, out)));
     SAL_CUDA(cudaGetLastError());
     c->launches++;
     return 0;

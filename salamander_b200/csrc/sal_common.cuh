@@ -23,6 +23,7 @@ struct sal_ctx {
     double* partial_hsum;  // [grid_pass][SAL_KMAX]
     void* dbg;             // optional diagnostics buffer of the tensor-core pass (sal_set_debug_buffer)
     int64_t launches;
+    unsigned int* norm_counter;                       // ticket counters of the CorrNMF norms reduction
     int timing;                                       // sal_set_timing
     std::vector<cudaEvent_t>* ev;                     // event pairs around the UPDATE_H | WNUM pass kernels
     size_t ev_used;
