@@ -117,6 +117,23 @@ int sal_klnmf_update(sal_handle_t h, const void* X, const void* W_in, void* W_ou
                      double* objective, void* stream);
 
 /*
+ * Multi-GPU joint update (samples sharded over ranks): as sal_klnmf_update, but the kernel that
+ * reduces this rank's partials also performs the all-reduce of the 96 x k numerator (and of the objective scalar):
+ * every thread pushes its double as two sequence-tagged 8-byte words into all peers' receive buffers (NVLink
+ * peer stores) and polls its own buffer; the contributions are summed in rank order so that W stays bit-identical on
+ * all ranks; the W epilogue follows -- pass + ONE more kernel per iteration, no library collective.
+ *   peer_buffers : device array [n_ranks] of pointers to every rank's receive buffer of
+ *                  sal_p2p_exchange_bytes(k, n_ranks) bytes (zero-initialised symmetric / peer-mapped memory; entry
+ *                  `rank` is this rank's own buffer)
+ *   p2p_state    : device unsigned[2] = {1, 0} (sequence number, ticket), private to this rank
+ * All ranks must call it the same number of times; a missing peer traps after a bounded wait.
+ */
+int sal_klnmf_update_p2p(sal_handle_t h, const void* X, const void* W_in, void* W_out, const void* H_in, void* H_out,
+                         const void* w_kl, const void* w_lhalf, int n_given, int clip_given, void* Wnum, double* objective,
+                         const void* peer_buffers, void* p2p_state, int n_ranks, int rank, void* stream);
+size_t sal_p2p_exchange_bytes(int k, int n_ranks);
+
+/*
  * W epilogue: W_out = clip(colnorm(W_in * Wnum)) with given signatures restored.
  *   replaces the W tail of update_WH (_utils_klnmf.py:338-341, clip_given = 1: ALL columns
  *   clipped) and of update_W (:212-215, clip_given = 0: only non-given columns clipped).

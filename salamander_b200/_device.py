@@ -177,6 +177,33 @@ class Workspace:
             "sal_klnmf_update",
         )
 
+    def klnmf_update_p2p(self, X, W_in, W_out, H_in, H_out, n_given: int, clip_given: bool, Wnum, peers, state, n_ranks: int, rank: int,
+                         w_kl=None, w_lhalf=None, objective=None) -> None:
+        """Multi-GPU joint update: fused pass, then reduction + one-shot NVLink all-reduce + W epilogue in one kernel."""
+        V, D, k = self.V, self.D, self.k
+        _lib.check(
+            self.lib.sal_klnmf_update_p2p(
+                self._h,
+                self._ptr(X, D * V, "X"),
+                self._ptr(W_in, k * V, "W_in"),
+                self._ptr(W_out, k * V, "W_out"),
+                self._ptr(H_in, D * k, "H_in"),
+                self._ptr(H_out, D * k, "H_out"),
+                self._ptr(w_kl, D, "w_kl"),
+                self._ptr(w_lhalf, D, "w_lhalf"),
+                int(n_given),
+                int(bool(clip_given)),
+                self._ptr(Wnum, k * V, "Wnum"),
+                self._ptr(objective, 1, "objective", torch.float64),
+                self._ptr(peers, n_ranks, "peers", torch.int64),
+                self._ptr(state, 2, "state", torch.int32),
+                int(n_ranks),
+                int(rank),
+                self._stream(),
+            ),
+            "sal_klnmf_update_p2p",
+        )
+
     def w_epilogue(self, W_in, Wnum, n_given: int, clip_given: bool, W_out) -> None:
         kv = self.k * self.V
         _lib.check(

@@ -57,3 +57,22 @@ def broadcast_numpy(arr: np.ndarray, device: torch.device, src: int = 0) -> np.n
     t = torch.from_numpy(np.ascontiguousarray(arr)).to(device)
     dist.broadcast(t, src=src)
     return t.cpu().numpy()
+
+
+class PeerExchange:
+    """Symmetric (peer-mapped) exchange buffer for the one-shot all-reduce fused into the reduction kernel
+    (sal_klnmf_update_p2p): every rank allocates ``nbytes`` of zeroed symmetric memory, the ranks rendezvous and each
+    keeps the table of all ranks' buffer addresses as mapped into ITS address space."""
+
+    def __init__(self, nbytes: int, device: torch.device):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        group = dist.group.WORLD
+        self.buf = symm_mem.empty((nbytes + 3) // 4, dtype=torch.int32, device=device)
+        self.buf.zero_()
+        self.handle = symm_mem.rendezvous(self.buf, group)
+        self.rank, self.world = self.handle.rank, self.handle.world_size
+        self.peers = torch.tensor([int(p) for p in self.handle.buffer_ptrs], dtype=torch.int64, device=device)
+        self.state = torch.tensor([1, 0], dtype=torch.int32, device=device)
+        torch.cuda.synchronize(device)
+        dist.barrier()  # every buffer is zeroed and mapped before anybody publishes into it

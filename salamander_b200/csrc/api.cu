@@ -186,6 +186,29 @@ int sal_klnmf_update(sal_handle_t h, const void* X, const void* W_in, void* W_ou
     return sal_launch_pass_fma(h, a, st);
 }
 
+int sal_klnmf_update_p2p(sal_handle_t h, const void* X, const void* W_in, void* W_out, const void* H_in, void* H_out,
+                         const void* w_kl, const void* w_lhalf, int n_given, int clip_given, void* Wnum, double* objective,
+                         const void* peer_buffers, void* p2p_state, int n_ranks, int rank, void* stream) {
+    SAL_CHECK_ARG(h != nullptr, "handle is null");
+    SAL_CHECK_ARG(W_in && W_out && Wnum && (h->D == 0 || (X && H_in && H_out)), "null argument");
+    SAL_CHECK_ARG(W_in != W_out, "W_out must not alias W_in (the H step reads the old W)");
+    SAL_CHECK_ARG(n_given >= 0 && n_given < h->k, "n_given out of range (all signatures given: use sal_klnmf_pass)");
+    SAL_CHECK_ARG(peer_buffers && p2p_state && n_ranks >= 1 && n_ranks <= SAL_VMAX && rank >= 0 && rank < n_ranks, "bad exchange arguments");
+    SAL_CHECK_ARG(h->D > 0, "every rank needs at least one sample");
+    SAL_CUDA(cudaSetDevice(h->device));
+    PassArgs a;
+    a.X = X, a.W = W_in, a.H_in = H_in, a.w_kl = w_kl, a.w_lhalf = w_lhalf, a.h_scale = nullptr;
+    a.H_out = H_out, a.Wnum = Wnum, a.per_sample = nullptr, a.hsum = nullptr, a.objective = objective;
+    a.flags = SAL_PASS_UPDATE_H | SAL_PASS_WNUM | (objective ? SAL_PASS_OBJECTIVE : 0);
+    a.fuse_epilogue = 1, a.n_given = n_given, a.clip_given = clip_given, a.W_out = W_out;
+    a.p2p_peers = peer_buffers, a.p2p_state = p2p_state, a.p2p_n_ranks = n_ranks, a.p2p_rank = rank;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (h->math != SAL_MATH_FMA && sal_pass_tf32_supported(h, a)) return sal_launch_pass_tf32(h, a, st);
+    return sal_launch_pass_fma(h, a, st);
+}
+
+size_t sal_p2p_exchange_bytes(int k, int n_ranks) { return (size_t)2 * n_ranks * (k + 1) * SAL_VMAX * 16; }
+
 int sal_w_epilogue(sal_handle_t h, const void* W_in, const void* Wnum, int n_given, int clip_given,
                    void* W_out, void* stream) {
     SAL_CHECK_ARG(h != nullptr, "handle is null");

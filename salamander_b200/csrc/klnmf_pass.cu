@@ -354,6 +354,132 @@ __global__ void __launch_bounds__(FIN_THREADS) klnmf_finish_kernel(const T* part
     }
 }
 
+// ---- multi-GPU: reduction of the partials + one-shot all-reduce over NVLink peer memory + W epilogue, ONE kernel ----
+// Every rank owns a receive buffer that all peers have mapped (symmetric memory):
+//     uint2 recv[2][n_ranks][k + 1][VP][2];          slot = sequence number & 1; one (payload32, seq) word pair per double
+// Thread v of block j reduces this rank's partials of Wnum[j][v] and PUSHES the double, as two 8-byte words each tagged
+// with the sequence number (the "LL" idea: an 8-byte store is atomic, so data and flag arrive together and no fence is
+// needed), into recv[slot][my rank][j][v] of every peer -- remote stores, one NVLink hop.  It then polls its OWN buffer
+// until the words of every other rank carry the tag and sums the N contributions IN RANK ORDER, so every rank obtains
+// bit-identical sums, and applies the W epilogue.  Block k does the same for the objective scalar.  Two slots suffice:
+// a rank can be at most one update ahead of the slowest peer, because its next update needs that peer's words.
+// seq lives in device memory and is advanced by the last block to finish, so the kernel can sit in a CUDA graph.
+// The payload is 96 x k doubles: latency, not bandwidth.
+struct P2PExchange {
+    void* const* peers;   // device array [n_ranks] of the ranks' receive buffers (this process's mappings)
+    unsigned int* seq;    // device scalar, starts at 1
+    unsigned int* ticket; // device scalar, 0
+    int n_ranks, rank;
+};
+
+__device__ __forceinline__ void st_ll(uint2* p, unsigned int payload, unsigned int tag) {
+    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(payload), "r"(tag) : "memory");
+}
+__device__ __forceinline__ uint2 ld_ll(const uint2* p) {
+    uint2 v;
+    asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+    return v;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(FIN_THREADS) klnmf_finish_p2p_kernel(const T* partial_wnum, const double* partial_obj, int n_part,
+                                                                      int KP, int k, int V, int flags, T* Wnum, double* objective,
+                                                                      const T* W_in, T* W_out, int n_given, int clip_given,
+                                                                      P2PExchange x) {
+    __shared__ double s_part[FIN_PARTS][VP];
+    __shared__ double s_red[VP / 32];
+    __shared__ double s_obj[FIN_THREADS / 32];
+    const int j = blockIdx.x, tid = threadIdx.x;
+    const int part = tid / VP, v = tid - part * VP;
+    const unsigned int seq = *(volatile unsigned int*)x.seq;
+    const int slot = seq & 1;
+    const bool is_obj = j == k;
+    const bool active = is_obj ? (flags & SAL_PASS_OBJECTIVE) != 0 : (flags & SAL_PASS_WNUM) != 0;
+    if (active) {
+        // (1) this rank's contribution
+        double s = 0.0;
+        if (!is_obj) {
+            if (v < V) {
+                const T* src = partial_wnum + (size_t)j * VP + v;
+#pragma unroll 8
+                for (int b = part; b < n_part; b += FIN_PARTS) s += (double)src[(size_t)b * KP * VP];
+            }
+            s_part[part][v] = s;
+            __syncthreads();
+            s = ((s_part[0][v] + s_part[1][v]) + (s_part[2][v] + s_part[3][v])) + ((s_part[4][v] + s_part[5][v]) + (s_part[6][v] + s_part[7][v]));
+        } else {
+            for (int b = tid; b < n_part; b += FIN_THREADS) s += partial_obj[b];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if ((tid & 31) == 0) s_obj[tid >> 5] = s;
+            __syncthreads();
+            s = 0.0;
+            for (int w = 0; w < FIN_THREADS / 32; ++w) s += s_obj[w];
+        }
+        if (part == 0) {  // 96 threads carry on (named barrier 1 for the epilogue's block sum)
+            const int nv = is_obj ? 1 : V;
+            const size_t row = ((size_t)slot * x.n_ranks) * (k + 1) * VP;  // start of recv[slot]
+            double total = 0.0;
+            if (v < nv) {
+                // (2) push to every peer: two tagged 8-byte words per double
+                const unsigned long long bits = (unsigned long long)__double_as_longlong(s);
+                for (int r = 0; r < x.n_ranks; ++r) {
+                    if (r == x.rank) continue;
+                    uint2* dst = reinterpret_cast<uint2*>(x.peers[r]) + (row + ((size_t)x.rank * (k + 1) + j) * VP + v) * 2;
+                    st_ll(dst, (unsigned int)bits, seq);
+                    st_ll(dst + 1, (unsigned int)(bits >> 32), seq);
+                }
+                // (3) collect the peers' words from the local buffer, in rank order
+                const uint2* mine = reinterpret_cast<const uint2*>(x.peers[x.rank]);
+                for (int r = 0; r < x.n_ranks; ++r) {
+                    if (r == x.rank) {
+                        total += s;
+                        continue;
+                    }
+                    const uint2* src = mine + (row + ((size_t)r * (k + 1) + j) * VP + v) * 2;
+                    uint2 lo, hi;
+                    long long spins = 0;
+                    do {
+                        lo = ld_ll(src), hi = ld_ll(src + 1);
+                        if (++spins > 2000000000LL) __trap();  // a peer died: fail loudly instead of hanging the box
+                    } while (lo.y != seq || hi.y != seq);
+                    total += __longlong_as_double((long long)(((unsigned long long)hi.x << 32) | lo.x));
+                }
+            }
+            if (is_obj) {
+                if (v == 0) *objective = total;
+            } else {
+                const bool in = v < V;
+                if (in) Wnum[(size_t)j * V + v] = (T)total;
+                const double w = in ? (double)W_in[(size_t)j * V + v] : 0.0;
+                const double val = in ? w * (double)(T)total : 0.0;
+                double t = val;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+                if ((v & 31) == 0) s_red[v >> 5] = t;
+                asm volatile("bar.sync 1, %0;" ::"r"(VP));
+                t = s_red[0] + s_red[1] + s_red[2];
+                if (in) {
+                    double out = val / t;
+                    if (j < n_given) out = w;
+                    if (clip_given || j >= n_given) out = fmax(out, (double)SAL_EPS_F32);
+                    W_out[(size_t)j * V + v] = (T)out;
+                }
+            }
+        }
+    }
+    // (4) the last block to finish advances the sequence number for the next launch
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        if (atomicAdd(x.ticket, 1u) == gridDim.x - 1) {
+            *x.ticket = 0;
+            *(volatile unsigned int*)x.seq = seq + 1;
+            __threadfence();
+        }
+    }
+}
+
 // W epilogue: one CTA per signature.
 template <typename T>
 __global__ void __launch_bounds__(128) w_epilogue_kernel(const T* W_in, const T* Wnum, int V, int n_given,
@@ -450,6 +576,23 @@ int launch_pass_k(sal_ctx* c, const PassArgs& a, cudaStream_t st) {
 // Fixed-order sum of the per-CTA partials left by either flavour of the pass (n_part = its grid size).
 int sal_launch_pass_reduce(sal_ctx* c, const PassArgs& a, int n_part, cudaStream_t st) {
     if (!(a.flags & (SAL_PASS_WNUM | SAL_PASS_OBJECTIVE | SAL_PASS_POISSON | SAL_PASS_HSUM))) return 0;
+    if (a.p2p_peers) {
+        P2PExchange x;
+        x.peers = (void* const*)a.p2p_peers, x.seq = (unsigned int*)a.p2p_state, x.ticket = (unsigned int*)a.p2p_state + 1;
+        x.n_ranks = a.p2p_n_ranks, x.rank = a.p2p_rank;
+        const int grid = c->k + 1;
+        if (c->dtype == SAL_F32)
+            klnmf_finish_p2p_kernel<float><<<grid, FIN_THREADS, 0, st>>>((const float*)c->partial_wnum, c->partial_obj, n_part, c->KP, c->k,
+                                                                        c->V, a.flags, (float*)a.Wnum, a.objective, (const float*)a.W,
+                                                                        (float*)a.W_out, a.n_given, a.clip_given, x);
+        else
+            klnmf_finish_p2p_kernel<double><<<grid, FIN_THREADS, 0, st>>>((const double*)c->partial_wnum, c->partial_obj, n_part, c->KP, c->k,
+                                                                         c->V, a.flags, (double*)a.Wnum, a.objective, (const double*)a.W,
+                                                                         (double*)a.W_out, a.n_given, a.clip_given, x);
+        SAL_CUDA(cudaGetLastError());
+        c->launches++;
+        return 0;
+    }
     const bool need_tail = a.flags & (SAL_PASS_OBJECTIVE | SAL_PASS_POISSON | SAL_PASS_HSUM);
     const int grid = c->k + (need_tail ? 1 : 0);
     const int fuse = a.fuse_epilogue && (a.flags & SAL_PASS_WNUM);

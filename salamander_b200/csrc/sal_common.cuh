@@ -63,6 +63,10 @@ struct PassArgs {
     // optional W epilogue fused into the reduction of the partials (sal_klnmf_update)
     int fuse_epilogue = 0, n_given = 0, clip_given = 0;
     void* W_out = nullptr;
+    // multi-GPU one-shot all-reduce fused into the reduction (sal_klnmf_update_p2p)
+    const void* p2p_peers = nullptr;  // device array [n_ranks] of exchange-buffer pointers
+    void* p2p_state = nullptr;        // device unsigned[2]: {sequence number (starts at 1), ticket (0)}
+    int p2p_n_ranks = 0, p2p_rank = 0;
 };
 int sal_launch_pass_fma(sal_ctx* c, const PassArgs& a, cudaStream_t st);
 int sal_launch_pass_tf32(sal_ctx* c, const PassArgs& a, cudaStream_t st);  // tcgen05 path (fp32 only)

@@ -36,6 +36,9 @@ class KLNMF(StandardNMF):
         self.weights_kl = None
         self.weights_lhalf = None
         self.use_graphs = True  # capture the periods of the fit loop in CUDA graphs (see _fit_loop)
+        # multi-GPU all-reduce of the numerator: "auto" / "p2p" = one-shot NVLink exchange fused into the reduction
+        # kernel (sal_klnmf_update_p2p), "nccl" = library collective between separate kernels
+        self.allreduce = "auto"
 
     @property
     def objective(self) -> Literal["minimize", "maximize"]:
@@ -92,6 +95,13 @@ class KLNMF(StandardNMF):
         if st.world == 1:
             st.ws.klnmf_update(st.X, W_in, W_out, H_in, H_out, n_given, True, st.Wnum, w_kl=wk, w_lhalf=wl, objective=objective)
             return
+        px = self._peer_exchange(st) if n_given < st.k else None
+        if px is not None:
+            st.ws.klnmf_update_p2p(
+                st.X, W_in, W_out, H_in, H_out, n_given, True, st.Wnum, px.peers, px.state, px.world, px.rank,
+                w_kl=wk, w_lhalf=wl, objective=objective,
+            )
+            return
         flags = PASS_UPDATE_H | (PASS_WNUM if n_given < st.k else 0) | (PASS_OBJECTIVE if objective is not None else 0)
         st.ws.klnmf_pass(st.X, W_in, H_in, flags, H_out=H_out, w_kl=wk, w_lhalf=wl, Wnum=st.Wnum, objective=objective)
         if n_given < st.k:
@@ -99,6 +109,24 @@ class KLNMF(StandardNMF):
         if objective is not None:
             _dist.allreduce_sum_(objective)
         st.ws.w_epilogue(W_in, st.Wnum, n_given, True, W_out)
+
+    def _peer_exchange(self, st):
+        """The symmetric exchange buffer of the fused all-reduce, set up once per device state; ``None`` (NCCL path)
+        when ``allreduce = "nccl"`` was asked for or symmetric memory cannot be set up on this system."""
+        if self.allreduce == "nccl":
+            return None
+        if "peer_exchange" not in st.weights:
+            try:
+                nbytes = int(st.ws.lib.sal_p2p_exchange_bytes(st.k, st.world))
+                st.weights["peer_exchange"] = _dist.PeerExchange(nbytes, st.device)
+            except Exception as exc:  # pragma: no cover - depends on the system
+                if self.allreduce == "p2p":
+                    raise
+                import warnings
+
+                warnings.warn(f"peer-memory all-reduce unavailable ({exc}); using NCCL")
+                st.weights["peer_exchange"] = None
+        return st.weights["peer_exchange"]
 
     def _fit_loop(self, given_parameters, verbose, verbosity_freq):
         """Same iterates, history and stopping iteration as the reference loop (signature_nmf.py:361-380), run in
