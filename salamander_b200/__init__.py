@@ -7,8 +7,8 @@ Host code is Python + PyTorch (device memory, streams, torch.distributed); every
 step is hand-written CUDA behind the C ABI in include/salamander_b200.h.
 """
 
-from . import models
+from . import models, sweep
 from ._anndata import AnnData, MuData
 
 __version__ = "0.1.0"
-__all__ = ["models", "AnnData", "MuData"]
+__all__ = ["models", "sweep", "AnnData", "MuData"]

@@ -83,7 +83,7 @@ class KLNMF(StandardNMF):
                 Wnum=st.Wnum,
             )
             if n_given < st.k:
-                _dist.allreduce_sum_(st.Wnum)
+                st.allreduce(st.Wnum)
                 st.ws.w_epilogue(st.W, st.Wnum, n_given, True, st.W)
 
     # ---- device-side fit driver ------------------------------------------------------------------
@@ -105,9 +105,9 @@ class KLNMF(StandardNMF):
         flags = PASS_UPDATE_H | (PASS_WNUM if n_given < st.k else 0) | (PASS_OBJECTIVE if objective is not None else 0)
         st.ws.klnmf_pass(st.X, W_in, H_in, flags, H_out=H_out, w_kl=wk, w_lhalf=wl, Wnum=st.Wnum, objective=objective)
         if n_given < st.k:
-            _dist.allreduce_sum_(st.Wnum)
+            st.allreduce(st.Wnum)
         if objective is not None:
-            _dist.allreduce_sum_(objective)
+            st.allreduce(objective)
         st.ws.w_epilogue(W_in, st.Wnum, n_given, True, W_out)
 
     def _peer_exchange(self, st):

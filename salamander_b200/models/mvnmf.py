@@ -62,7 +62,7 @@ class MvNMF(StandardNMF):
         with self._resident() as st:
             st.ws.klnmf_pass(st.X, st.W, st.H, PASS_OBJECTIVE, objective=st.kl2[0:1])
             st.ws.mvnmf_logdet(st.W, self.delta, st.ld2[0:1])
-            _dist.allreduce_sum_(st.kl2[0:1])
+            st.allreduce(st.kl2[0:1])
             kl, ld = torch.stack([st.kl2[0], st.ld2[0]]).tolist()
             return kl + self.lam * ld
 
@@ -76,8 +76,8 @@ class MvNMF(StandardNMF):
         st.ws.klnmf_pass(
             st.X, st.W, st.H, PASS_WNUM | PASS_HSUM | PASS_OBJECTIVE, Wnum=st.Wnum, hsum=st.hsum, objective=st.kl2[0:1]
         )
-        _dist.allreduce_sum_(st.Wnum)
-        _dist.allreduce_sum_(st.hsum)
+        st.allreduce(st.Wnum)
+        st.allreduce(st.hsum)
         st.ws.mvnmf_logdet(st.W, self.delta, st.ld2[0:1])
         st.ws.mvnmf_w_unconstrained(st.W, st.Wnum, st.hsum, self.lam, self.delta, n_given_signatures, st.W_unc)
 
@@ -98,7 +98,7 @@ class MvNMF(StandardNMF):
         """Back-tracking on the penalised objective; the first trial ignores gamma (reference mvnmf.py:69-92)."""
         st = self._dev
         self._trial(-1.0)
-        _dist.allreduce_sum_(st.kl2)
+        st.allreduce(st.kl2)
         kl_prev, kl_new, ld_prev, ld_new = torch.cat([st.kl2, st.ld2]).tolist()
         prev_of_value = kl_prev + self.lam * ld_prev
         of_value = kl_new + self.lam * ld_new
@@ -106,7 +106,7 @@ class MvNMF(StandardNMF):
         while of_value > prev_of_value and gamma > 1e-16:
             gamma *= 0.8
             self._trial(gamma)
-            _dist.allreduce_sum_(st.kl2[1:2])
+            st.allreduce(st.kl2[1:2])
             kl_new, ld_new = torch.stack([st.kl2[1], st.ld2[1]]).tolist()
             of_value = kl_new + self.lam * ld_new
         self._gamma = min(1.0, 1.2 * gamma)

@@ -40,6 +40,7 @@ class SignatureNMF(ABC):
         dtype="float64",
         math: str = "fma",
         shard_input: bool = True,
+        replica: bool = False,
     ):
         value_checker("init_method", init_method, _INIT_METHODS)
         value_checker("math", math, ("fma", "tf32", "tf32_always"))
@@ -55,6 +56,8 @@ class SignatureNMF(ABC):
         # multi-GPU (torch.distributed initialised): True = ``adata`` holds the whole matrix on every rank and
         # each rank takes its contiguous row block; False = ``adata`` already holds only this rank's rows.
         self.shard_input = bool(shard_input)
+        # True: ignore an initialised process group -- this model is an independent replica (restarts / k-sweep)
+        self.replica = bool(replica)
         self.transfer_bytes = {"h2d": 0, "d2h": 0}  # host<->device bytes of the last fit / update
 
         # data / fitting dependent attributes (reference signature_nmf.py:182-185)

@@ -30,7 +30,7 @@ class StandardState:
         W_host = np.asarray(model.asignatures.X, dtype=np.float64)
         H_host = np.asarray(model.adata.obsm["exposures"])
         self.k = W_host.shape[0]
-        self.rank, self.world = _dist.world()
+        self.rank, self.world = (0, 1) if model.replica else _dist.world()
         if model.shard_input:
             self.D_total, self.V = X_host.shape
             self.lo, self.hi = _dist.shard_bounds(self.D_total, self.world, self.rank)
@@ -91,9 +91,15 @@ class StandardState:
             local = _dist.gather_rows(local, self.D_total)
         return self.download(local)
 
+    def allreduce(self, t: torch.Tensor) -> torch.Tensor:
+        """Sum over the ranks that share this fit (no-op for a single GPU or an independent replica)."""
+        if self.world > 1:
+            _dist.allreduce_sum_(t)
+        return t
+
     def objective_value(self) -> float:
         """Sum the device scalar over ranks and bring it to the host (one sync)."""
-        _dist.allreduce_sum_(self.obj)
+        self.allreduce(self.obj)
         return float(self.obj.item())
 
     def close(self) -> None:

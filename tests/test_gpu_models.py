@@ -228,3 +228,19 @@ def test_custom_init_rescaled_on_device_equals_host_path(monkeypatch):
         res.append((model.asignatures.X, model.adata.obsm["exposures"], model.history["objective_function"]))
     assert np.allclose(res[0][0], res[1][0], rtol=1e-13) and np.allclose(res[0][1], res[1][1], rtol=1e-13)
     assert np.allclose(res[0][2], res[1][2], rtol=1e-13)
+
+
+def test_sweep_over_k_and_restarts():
+    """Model-selection sweep (tutorial.ipynb:1975-2013 semantics): every (k, seed) job equals the stand-alone fit."""
+    from salamander_b200.sweep import error_curve, sweep_klnmf
+
+    adata = pcawg_adata()
+    table, best = sweep_klnmf(adata, [2, 3], n_restarts=2, seed0=5, min_iterations=40, max_iterations=40, dtype="float64")
+    assert list(table["n_signatures"]) == [2, 2, 3, 3] and list(table["seed"]) == [5, 6, 5, 6]
+    solo = sal.models.KLNMF(n_signatures=3, init_method="random", min_iterations=40, max_iterations=40, dtype="float64")
+    solo.fit(pcawg_adata(), init_kwargs={"seed": 6})
+    row = table[(table.n_signatures == 3) & (table.seed == 6)].iloc[0]
+    assert np.isclose(row.reconstruction_error, solo.reconstruction_error, rtol=1e-12)
+    curve = error_curve(table)
+    assert curve.loc[3] < curve.loc[2]
+    assert set(best) == {2, 3} and np.isclose(best[3].reconstruction_error, curve.loc[3])
