@@ -336,13 +336,16 @@ def run_ours(args):
     # ---- end to end through the public API: KLNMF.fit(adata) with host arrays --------------
     e2e_model = make_model(args.steps)
     H0_pin = torch.from_numpy(H0).pin_memory().numpy()
-    for rep in range(2):  # first repetition warms allocator / pinned staging, second is timed
+    fit_times = []
+    for rep in range(4):  # repetition 0 warms the allocator / graph capture paths; the median of the other three is reported
         adata2 = AnnData(X_host)
         barrier()
         t0 = time.perf_counter()
         e2e_model.fit(adata2, init_kwargs={"signatures_mat": W0, "exposures_mat": H0_pin})
         torch.cuda.synchronize()
-        t_fit = time.perf_counter() - t0
+        if rep:
+            fit_times.append(time.perf_counter() - t0)
+    t_fit = float(np.median(fit_times))
     t_fit = max_over_ranks(t_fit)
     h2d = e2e_model.transfer_bytes["h2d"]
     d2h = e2e_model.transfer_bytes["d2h"]
@@ -405,6 +408,7 @@ def run_ours(args):
                 "d2h_bytes_per_step": d2h / args.steps,
                 "what": f"KLNMF.fit(adata) of {args.steps} iterations from pinned host arrays: upload of X, W0, H0 and download of W, H inside the timed region (wall clock, max over ranks)",
                 "seconds": t_fit,
+                "seconds_all": fit_times,
             },
             "gpu_launches": int(launches),
             "roofline": {

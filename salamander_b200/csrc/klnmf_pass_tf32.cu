@@ -308,6 +308,7 @@ klnmf_pass_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
     const int n_my = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // tiles of this CTA (>= 1)
 
     // ---- one-time setup --------------------------------------------------------------------------
+    stamp(p.dbg, p.dbg != nullptr && blockIdx.x == 1 && tid == 0, 3, 0, 1);
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapX) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapH) : "memory");
@@ -332,14 +333,24 @@ klnmf_pass_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    // W operands as tf32 hi + lo (round to nearest), zero padding for signatures >= k; sHT zero fill
-    for (int i = tid; i < KP8 * VT; i += NTHREADS) {
-        const int j = i / VT, f = i - j * VT;
-        const float w = j < k ? p.W[(size_t)j * VT + f] : 0.f;
-        const float hi = tf32_rn(w), lo = tf32_rn(w - hi);
-        const uint32_t o1 = (j >> 2) * SW1_LBO + (f >> 3) * SW1_SBO + (f & 7) * 16 + (j & 3) * 4;
-        sts32(sW1hi + o1, hi), sts32(sW1lo + o1, lo);
-        if (DO_R) sts32(sW2 + (f >> 2) * q.sw2_lbo + (j >> 3) * SW2_SBO + (j & 7) * 16 + (f & 3) * 4, hi);
+    // W operands as tf32 hi + lo (round to nearest), zero padding for signatures >= k; sHT zero fill.
+    // KP8 * 96 = (KP8 / 4) * 384 elements: every thread first issues all its global loads, then converts and stores.
+    {
+        float wreg[KP8 / 4];
+#pragma unroll
+        for (int it = 0; it < KP8 / 4; ++it) {
+            const int i = tid + it * NTHREADS, j = i / VT, f = i - j * VT;
+            wreg[it] = j < k ? __ldg(p.W + (size_t)j * VT + f) : 0.f;
+        }
+#pragma unroll
+        for (int it = 0; it < KP8 / 4; ++it) {
+            const int i = tid + it * NTHREADS, j = i / VT, f = i - j * VT;
+            const float w = wreg[it];
+            const float hi = tf32_rn(w), lo = tf32_rn(w - hi);
+            const uint32_t o1 = (j >> 2) * SW1_LBO + (f >> 3) * SW1_SBO + (f & 7) * 16 + (j & 3) * 4;
+            sts32(sW1hi + o1, hi), sts32(sW1lo + o1, lo);
+            if (DO_R) sts32(sW2 + (f >> 2) * q.sw2_lbo + (j >> 3) * SW2_SBO + (j & 7) * 16 + (f & 3) * 4, hi);
+        }
     }
     if (DO_R)
         for (int i = tid; i < q.sht / 4; i += NTHREADS) sts32(sHT + 4 * i, 0.f);
@@ -348,6 +359,7 @@ klnmf_pass_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    stamp(p.dbg, p.dbg != nullptr && blockIdx.x == 1 && tid == 0, 3, 0, 2);
 
     double obj_acc = 0.0;
     const bool tl = p.dbg != nullptr && blockIdx.x == 1;  // diagnostics timeline (CTA 1: CTA 0 is busy dumping its first tile)
@@ -628,6 +640,7 @@ klnmf_pass_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TM_COLS) : "memory");
     }
+    stamp(p.dbg, p.dbg != nullptr && blockIdx.x == 1 && tid == 0, 3, 0, 3);
 }
 
 // ---- host side --------------------------------------------------------------------------------------

@@ -7,7 +7,7 @@ sys.path.insert(0, ".")
 from salamander_b200._device import PASS_UPDATE_H, PASS_WNUM, Workspace
 
 dev = torch.device("cuda:0")
-D, k = 1_000_000, 20
+D, k = (int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000), 20
 gen = torch.Generator(device=dev).manual_seed(0)
 W = torch.rand((k, 96), generator=gen, device=dev) + 0.01
 W /= W.sum(1, keepdim=True)
@@ -33,6 +33,7 @@ for i in range(16):
 print("MMA: tile | hready-seen  G1-issued  rready-seen  G2G3-issued")
 for i in range(16):
     print(f"   {i:2d} | {t[2, i, 0] - t0:8d} {t[2, i, 2] - t0:8d} {t[2, i, 1] - t0:8d} {t[2, i, 3] - t0:8d}")
+print("kernel entry, setup done, kernel exit (clk relative to the first TMA issue):", int(t[3, 0, 1] - t0), int(t[3, 0, 2] - t0), int(t[3, 0, 3] - t0))
 print("TMA: tile | issue")
 print("  ", [int(t[3, i, 0] - t0) for i in range(16, 32)])
 print("  ", [int(t[3, i, 0] - t0) for i in range(16)])
