@@ -134,6 +134,16 @@ int sal_klnmf_update_p2p(sal_handle_t h, const void* X, const void* W_in, void* 
 size_t sal_p2p_exchange_bytes(int k, int n_ranks);
 
 /*
+ * Small problems (D_local <= 256, state fits the shared memory of one SM -- BASELINE config 0, 96 x 192): n_iterations
+ * joint updates (update_WH, _utils_klnmf.py:281-361, unweighted) in ONE launch of a single persistent CTA; *objective
+ * (optional) receives the KL divergence of the INCOMING iterate (kl_divergence, :11-55).  W_out / H_out may alias the
+ * inputs.  sal_klnmf_small_supported returns 1 when the handle's shape qualifies.
+ */
+int sal_klnmf_small_supported(sal_handle_t h);
+int sal_klnmf_small_updates(sal_handle_t h, const void* X, const void* W_in, void* W_out, const void* H_in, void* H_out,
+                            int n_given, int n_iterations, double* objective, void* stream);
+
+/*
  * W epilogue: W_out = clip(colnorm(W_in * Wnum)) with given signatures restored.
  *   replaces the W tail of update_WH (_utils_klnmf.py:338-341, clip_given = 1: ALL columns
  *   clipped) and of update_W (:212-215, clip_given = 0: only non-given columns clipped).

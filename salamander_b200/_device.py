@@ -204,6 +204,28 @@ class Workspace:
             "sal_klnmf_update_p2p",
         )
 
+    def small_supported(self) -> bool:
+        return bool(self.lib.sal_klnmf_small_supported(self._h))
+
+    def klnmf_small_updates(self, X, W_in, W_out, H_in, H_out, n_given: int, n_iterations: int, objective=None) -> None:
+        """``n_iterations`` joint updates in one launch of a single persistent CTA (sal_klnmf_small_updates)."""
+        V, D, k = self.V, self.D, self.k
+        _lib.check(
+            self.lib.sal_klnmf_small_updates(
+                self._h,
+                self._ptr(X, D * V, "X"),
+                self._ptr(W_in, k * V, "W_in"),
+                self._ptr(W_out, k * V, "W_out"),
+                self._ptr(H_in, D * k, "H_in"),
+                self._ptr(H_out, D * k, "H_out"),
+                int(n_given),
+                int(n_iterations),
+                self._ptr(objective, 1, "objective", torch.float64),
+                self._stream(),
+            ),
+            "sal_klnmf_small_updates",
+        )
+
     def w_epilogue(self, W_in, Wnum, n_given: int, clip_given: bool, W_out) -> None:
         kv = self.k * self.V
         _lib.check(

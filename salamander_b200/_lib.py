@@ -35,6 +35,8 @@ SYMBOLS = {
     "sal_klnmf_update": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "sal_klnmf_update_p2p": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "sal_p2p_exchange_bytes": (C.c_size_t, [_i, _i]),
+    "sal_klnmf_small_supported": (_i, [_vp]),
+    "sal_klnmf_small_updates": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),
     "sal_w_epilogue": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),
     "sal_clip_counts": (_i, [_vp, _vp, _i64, _vp, _vp]),
     "sal_scale_clip_rows": (_i, [_vp, _vp, _vp, _vp]),

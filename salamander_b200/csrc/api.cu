@@ -209,6 +209,21 @@ int sal_klnmf_update_p2p(sal_handle_t h, const void* X, const void* W_in, void* 
 
 size_t sal_p2p_exchange_bytes(int k, int n_ranks) { return (size_t)2 * n_ranks * (k + 1) * SAL_VMAX * 16; }
 
+int sal_klnmf_small_supported(sal_handle_t h) { return h && sal_small_supported(h) ? 1 : 0; }
+
+int sal_klnmf_small_updates(sal_handle_t h, const void* X, const void* W_in, void* W_out, const void* H_in, void* H_out,
+                            int n_given, int n_iterations, double* objective, void* stream) {
+    SAL_CHECK_ARG(h != nullptr, "handle is null");
+    SAL_CHECK_ARG(X && W_in && W_out && H_in && H_out, "null argument");
+    SAL_CHECK_ARG(n_given >= 0 && n_given <= h->k && n_iterations >= 0, "n_given / n_iterations out of range");
+    if (!sal_small_supported(h)) {
+        sal_set_error("sal_klnmf_small_updates: problem does not fit one CTA (D <= 256 and ~220 KB of shared memory)");
+        return SAL_EUNSUPPORTED;
+    }
+    SAL_CUDA(cudaSetDevice(h->device));
+    return sal_launch_klnmf_small(h, X, W_in, W_out, H_in, H_out, n_given, n_iterations, objective, (cudaStream_t)stream);
+}
+
 int sal_w_epilogue(sal_handle_t h, const void* W_in, const void* Wnum, int n_given, int clip_given,
                    void* W_out, void* stream) {
     SAL_CHECK_ARG(h != nullptr, "handle is null");

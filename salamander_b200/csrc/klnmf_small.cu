@@ -1,0 +1,192 @@
+// Small-problem KL-NMF: the whole fit state lives in ONE CTA and a launch runs many joint updates.
+//
+// BASELINE config 0 (KLNMF on 96 x 192 PCAWG counts) is launch-latency bound: one update is ~0.3 MFLOP, a kernel
+// launch costs more than the arithmetic.  This kernel keeps X in registers (thread (d, q) owns 24 features of sample d),
+// W and H in shared memory, and performs `n_iter` updates of reference update_WH (_utils_klnmf.py:281-361) back to
+// back; the KL divergence of the INCOMING iterate (kl_divergence, :11-55) is produced on the way, which is what the
+// period-wise fit driver needs (KLNMF._fit_loop).  Unweighted, no l-half penalty; given signatures supported.
+// Arithmetic in the handle's dtype with fixed summation orders (deterministic).
+#include "sal_common.cuh"
+
+namespace {
+
+constexpr int NT = 1024;         // 4 threads per sample
+constexpr int DMAX = NT / 4;     // 256 samples
+constexpr int VQ = SAL_VMAX / 4; // 24 features per thread
+constexpr int RP = SAL_VMAX + 1; // pitch of the quotient tile (bank spread for the column reads of phase 2)
+
+template <typename T>
+__device__ __forceinline__ T tlog(T x);
+template <>
+__device__ __forceinline__ float tlog(float x) { return logf(x); }
+template <>
+__device__ __forceinline__ double tlog(double x) { return log(x); }
+
+// x / y.  fp64: reciprocal seed (>= 20 bits) + two Newton steps + one residual correction of the quotient -- a few
+// DFMAs instead of the ~25-instruction IEEE division sequence; the result differs from the correctly rounded quotient
+// by at most 1 ulp, far inside the 1e-9 trajectory tolerance.  y > 0 and normal here (WH >= k * eps^2).
+__device__ __forceinline__ float tdiv(float x, float y) { return x / y; }
+__device__ __forceinline__ double tdiv(double x, double y) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(y));
+    double e = fma(-y, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-y, r, 1.0);
+    r = fma(r, e, r);
+    const double q = x * r;
+    return fma(fma(-y, q, x), r, q);
+}
+
+template <typename T, int KT>  // KT >= k: unrolled signature loops, per-thread arrays stay in registers
+__global__ void __launch_bounds__(NT, 1)
+klnmf_small_kernel(const T* X, const T* W_in, T* W_out, const T* H_in, T* H_out, int D, int V, int k, int n_given, int n_iter,
+                   double* objective) {
+    extern __shared__ __align__(16) unsigned char raw[];
+    T* sR = reinterpret_cast<T*>(raw);    // [D][RP]   quotient X / (WH)
+    T* sH = sR + (size_t)D * RP;          // [D][k]
+    T* sW = sH + (size_t)D * k;           // [k][V]
+    T* sWn = sW + (size_t)k * SAL_VMAX;   // [k][V]    W * numerator before normalisation
+    __shared__ double s_red[NT / 32];
+    __shared__ T s_col[SAL_KMAX];
+    const int tid = threadIdx.x, d = tid >> 2, q = tid & 3, v0 = q * VQ;
+    const T eps = (T)SAL_EPS_F32;
+    const bool row = d < D;
+
+    T x[VQ];
+#pragma unroll
+    for (int i = 0; i < VQ; ++i) x[i] = (row && v0 + i < V) ? X[(size_t)d * V + v0 + i] : (T)0;
+    for (int i = tid; i < k * V; i += NT) sW[(i / V) * SAL_VMAX + i % V] = W_in[i];
+    for (int i = tid; i < D * k; i += NT) sH[i] = H_in[i];
+    __syncthreads();
+
+    const int n_pass = n_iter > 0 ? n_iter : (objective ? 1 : 0);  // n_iter == 0: only the objective of the iterate
+    for (int it = 0; it < n_pass; ++it) {
+        // ---- phase 1: quotient, H numerator (old W), optional KL of the incoming iterate
+        T hn[KT], hd[KT];
+        double kl = 0.0;
+#pragma unroll
+        for (int j = 0; j < KT; ++j) hn[j] = (T)0, hd[j] = (row && j < k) ? sH[d * k + j] : (T)0;
+        if (row) {
+#pragma unroll(KT <= 8 ? VQ : 2)
+            for (int i = 0; i < VQ; ++i) {
+                const int v = v0 + i;
+                if (v < V) {
+                    T wv[KT];
+                    T wh = (T)0;
+#pragma unroll
+                    for (int j = 0; j < KT; ++j) wv[j] = j < k ? sW[j * SAL_VMAX + v] : (T)0, wh += wv[j] * hd[j];
+                    const T r = tdiv(x[i], wh);
+                    sR[d * RP + v] = r;
+#pragma unroll
+                    for (int j = 0; j < KT; ++j) hn[j] += wv[j] * r;
+                    if (it == 0 && objective) kl += (double)(x[i] != (T)0 ? x[i] * tlog(r) - x[i] + wh : wh);
+                }
+            }
+        }
+        if (it == 0 && objective) {  // fixed-order block sum
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) kl += __shfl_xor_sync(0xffffffffu, kl, o);
+            if ((tid & 31) == 0) s_red[tid >> 5] = kl;
+            __syncthreads();
+            if (tid == 0) {
+                double t = 0.0;
+                for (int w = 0; w < NT / 32; ++w) t += s_red[w];
+                *objective = t;
+            }
+        }
+        if (it >= n_iter) break;  // objective-only call
+        // the four threads of a sample are adjacent lanes: add their partial H numerators
+#pragma unroll
+        for (int j = 0; j < KT; ++j) {
+            T t = hn[j];
+            t += __shfl_xor_sync(0xffffffffu, t, 1);
+            t += __shfl_xor_sync(0xffffffffu, t, 2);
+            hn[j] = t;
+        }
+        __syncthreads();  // sR complete, every read of the old sH / sW in phase 1 done
+        // ---- phase 2: W numerator  Wn[j][v] = W[j][v] * sum_d R[d][v] H[d][j]  (old H), thread <-> (j, v)
+        for (int i = tid; i < k * V; i += NT) {
+            const int j = i / V, v = i - j * V;
+            T a0 = (T)0, a1 = (T)0, a2 = (T)0, a3 = (T)0;  // four interleaved partial sums: short dependency chains
+            int dd = 0;
+            for (; dd + 3 < D; dd += 4) {
+                a0 += sR[dd * RP + v] * sH[dd * k + j];
+                a1 += sR[(dd + 1) * RP + v] * sH[(dd + 1) * k + j];
+                a2 += sR[(dd + 2) * RP + v] * sH[(dd + 2) * k + j];
+                a3 += sR[(dd + 3) * RP + v] * sH[(dd + 3) * k + j];
+            }
+            for (; dd < D; ++dd) a0 += sR[dd * RP + v] * sH[dd * k + j];
+            sWn[j * SAL_VMAX + v] = sW[j * SAL_VMAX + v] * ((a0 + a1) + (a2 + a3));
+        }
+        __syncthreads();
+        // ---- H update (one of the four threads of a sample writes), column sums of Wn (one warp per signature)
+        if (row && q == 0) {
+#pragma unroll
+            for (int j = 0; j < KT; ++j)
+                if (j < k) sH[d * k + j] = max(hd[j] * hn[j], eps);
+        }
+        {
+            const int w = tid >> 5, lane = tid & 31;
+            if (w < k) {
+                T t = (T)0;
+                for (int v = lane; v < V; v += 32) t += sWn[w * SAL_VMAX + v];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+                if (lane == 0) s_col[w] = t;
+            }
+        }
+        __syncthreads();
+        // ---- W epilogue: normalise, keep the given signatures, clip ALL columns (update_WH, :338-341)
+        if (n_given < k)
+            for (int i = tid; i < k * V; i += NT) {
+                const int j = i / V, v = i - j * V;
+                T out = sWn[j * SAL_VMAX + v] / s_col[j];
+                if (j < n_given) out = sW[j * SAL_VMAX + v];
+                sW[j * SAL_VMAX + v] = max(out, eps);
+            }
+        __syncthreads();
+    }
+    for (int i = tid; i < k * V; i += NT) W_out[i] = sW[(i / V) * SAL_VMAX + i % V];
+    for (int i = tid; i < D * k; i += NT) H_out[i] = sH[i];
+}
+
+template <typename T>
+size_t small_smem(int D, int k) {
+    return sizeof(T) * ((size_t)D * RP + (size_t)D * k + 2 * (size_t)k * SAL_VMAX);
+}
+
+}  // namespace
+
+bool sal_small_supported(const sal_ctx* c) {
+    if (c->D < 1 || c->D > DMAX || c->V > SAL_VMAX) return false;
+    const size_t need = c->dtype == SAL_F32 ? small_smem<float>((int)c->D, c->k) : small_smem<double>((int)c->D, c->k);
+    return need <= 220 * 1024;
+}
+
+template <typename T, int KT>
+int launch_small_t(sal_ctx* c, const void* X, const void* W_in, void* W_out, const void* H_in, void* H_out, int n_given, int n_iter,
+                   double* objective, cudaStream_t st) {
+    const int D = (int)c->D;
+    const size_t smem = small_smem<T>(D, c->k);
+    SAL_CUDA(cudaFuncSetAttribute(klnmf_small_kernel<T, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    klnmf_small_kernel<T, KT><<<1, NT, smem, st>>>((const T*)X, (const T*)W_in, (T*)W_out, (const T*)H_in, (T*)H_out, D, c->V, c->k, n_given,
+                                                  n_iter, objective);
+    SAL_CUDA(cudaGetLastError());
+    c->launches++;
+    return 0;
+}
+
+template <typename T>
+int launch_small_k(sal_ctx* c, const void* X, const void* W_in, void* W_out, const void* H_in, void* H_out, int n_given, int n_iter,
+                   double* objective, cudaStream_t st) {
+    if (c->k <= 4) return launch_small_t<T, 4>(c, X, W_in, W_out, H_in, H_out, n_given, n_iter, objective, st);
+    if (c->k <= 8) return launch_small_t<T, 8>(c, X, W_in, W_out, H_in, H_out, n_given, n_iter, objective, st);
+    if (c->k <= 16) return launch_small_t<T, 16>(c, X, W_in, W_out, H_in, H_out, n_given, n_iter, objective, st);
+    return launch_small_t<T, 32>(c, X, W_in, W_out, H_in, H_out, n_given, n_iter, objective, st);
+}
+
+int sal_launch_klnmf_small(sal_ctx* c, const void* X, const void* W_in, void* W_out, const void* H_in, void* H_out, int n_given,
+                           int n_iter, double* objective, cudaStream_t st) {
+    return c->dtype == SAL_F32 ? launch_small_k<float>(c, X, W_in, W_out, H_in, H_out, n_given, n_iter, objective, st)
+                               : launch_small_k<double>(c, X, W_in, W_out, H_in, H_out, n_given, n_iter, objective, st);
+}

@@ -96,3 +96,8 @@ int sal_launch_corrnmf_sample_embeddings(sal_ctx* c, const void* auxT, const voi
 int sal_launch_corrnmf_signature_embeddings(sal_ctx* c, const void* auxT, const void* a, const void* b, void* L, const void* U, int m,
                                             double variance, cudaStream_t st);
 int sal_launch_corrnmf_norms(sal_ctx* c, const void* L, const void* U, int m, const void* X_or_null, double* out, cudaStream_t st);
+
+// ---- small-problem persistent kernel (klnmf_small.cu) ----------------------------------------------------
+bool sal_small_supported(const sal_ctx* c);
+int sal_launch_klnmf_small(sal_ctx* c, const void* X, const void* W_in, void* W_out, const void* H_in, void* H_out, int n_given,
+                           int n_iter, double* objective, cudaStream_t st);
