@@ -337,7 +337,7 @@ def run_ours(args):
     e2e_model = make_model(args.steps)
     H0_pin = torch.from_numpy(H0).pin_memory().numpy()
     fit_times = []
-    for rep in range(4):  # repetition 0 warms the allocator / graph capture paths; the median of the other three is reported
+    for rep in range(6):  # repetition 0 warms the allocator caches; the median of the other five is reported
         adata2 = AnnData(X_host)
         barrier()
         t0 = time.perf_counter()

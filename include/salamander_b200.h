@@ -69,6 +69,8 @@ int sal_version(void);
  * scratch (per-CTA partial sums).  `device` is the CUDA ordinal. */
 int sal_create(sal_handle_t* out, int V, int64_t D_local, int k, int dtype, int device);
 int sal_destroy(sal_handle_t h);
+/* Free the scratch buffers that destroyed handles left on the per-device free list (sal_create reuses them otherwise). */
+int sal_trim_scratch(void);
 int sal_set_math(sal_handle_t h, int math_mode);
 /* Diagnostics of the tensor-core pass: when buf != NULL (device, >= 32768 floats) CTA 0 dumps the quotient tile
  * R[128][96] and Hn[128][32] of its first tile, then a clock64 timeline [role 4][tile 48][phase 8] (uint32) of

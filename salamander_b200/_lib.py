@@ -26,6 +26,7 @@ SYMBOLS = {
     "sal_version": (_i, []),
     "sal_create": (_i, [C.POINTER(_vp), _i, _i64, _i, _i, _i]),
     "sal_destroy": (_i, [_vp]),
+    "sal_trim_scratch": (_i, []),
     "sal_set_math": (_i, [_vp, _i]),
     "sal_launch_count": (_i64, [_vp]),
     "sal_set_timing": (_i, [_vp, _i]),

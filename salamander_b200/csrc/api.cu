@@ -5,6 +5,10 @@
 
 #include "sal_common.cuh"
 
+#include <algorithm>
+#include <mutex>
+#include <vector>
+
 static thread_local char g_err[512] = "";
 
 void sal_set_error(const char* fmt, ...) {
@@ -35,6 +39,38 @@ int sal_timing_end(sal_ctx* c, int flags, cudaStream_t st) {
     return 0;
 }
 
+// Per-device free list of workspace scratch buffers.  A fit creates and destroys one handle; cudaMalloc / cudaFree were
+// measured at up to 200 ms a call on a busy context (profiles/r01_e2e_phases.md), so released buffers are kept and handed to
+// the next handle that asks for the same size (sizes depend on the SM count and dtype only).  sal_trim_scratch() frees them.
+struct Scratch {
+    int device;
+    size_t bytes;
+    void* ptr;
+    bool in_use;
+};
+static std::vector<Scratch> g_scratch;
+static std::mutex g_scratch_mutex;
+
+static void* scratch_take(int device, size_t bytes) {
+    std::lock_guard<std::mutex> lock(g_scratch_mutex);
+    for (Scratch& b : g_scratch)
+        if (!b.in_use && b.device == device && b.bytes == bytes) {
+            b.in_use = true;
+            return b.ptr;
+        }
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) return nullptr;
+    g_scratch.push_back({device, bytes, p, true});
+    return p;
+}
+
+static void scratch_give(int device, void* p) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lock(g_scratch_mutex);
+    for (Scratch& b : g_scratch)
+        if (b.ptr == p && b.device == device) b.in_use = false;
+}
+
 extern "C" {
 
 const char* sal_last_error(void) { return g_err; }
@@ -49,28 +85,28 @@ int sal_create(sal_handle_t* out, int V, int64_t D_local, int k, int dtype, int 
         return SAL_EUNSUPPORTED;
     }
     SAL_CUDA(cudaSetDevice(device));
-    cudaDeviceProp prop;
-    SAL_CUDA(cudaGetDeviceProperties(&prop, device));
-    if (prop.major < 10) {
-        sal_set_error("libsalamander_b200 is built for sm_100a only; device %d is sm_%d%d", device, prop.major,
-                      prop.minor);
+    int cc_major = 0, n_sm = 0;
+    SAL_CUDA(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, device));
+    SAL_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
+    if (cc_major < 10) {
+        sal_set_error("libsalamander_b200 is built for sm_100a only; device %d has compute capability %d.x", device, cc_major);
         return SAL_EUNSUPPORTED;
     }
     sal_ctx* c = new sal_ctx();
     memset(c, 0, sizeof(*c));
     c->V = V, c->k = k, c->KP = sal_kpad(k), c->dtype = dtype, c->device = device, c->D = D_local;
     c->math = SAL_MATH_FMA;
-    c->n_sm = prop.multiProcessorCount;
+    c->n_sm = n_sm;
     c->grid_pass = c->n_sm * (dtype == SAL_F32 ? 2 : 1);
     const size_t es = dtype == SAL_F32 ? 4 : 8;
-    cudaError_t e = cudaMalloc(&c->partial_wnum, (size_t)c->grid_pass * SAL_KMAX * SAL_VMAX * es);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&c->partial_obj, (size_t)c->grid_pass * sizeof(double));
-    if (e == cudaSuccess) e = cudaMalloc((void**)&c->partial_hsum, (size_t)c->grid_pass * SAL_KMAX * sizeof(double));
-    if (e != cudaSuccess) {
-        sal_set_error("cudaMalloc of the workspace failed: %s", cudaGetErrorString(e));
-        cudaFree(c->partial_wnum), cudaFree(c->partial_obj), cudaFree(c->partial_hsum);
+    c->partial_wnum = scratch_take(device, (size_t)c->grid_pass * SAL_KMAX * SAL_VMAX * es);
+    c->partial_obj = (double*)scratch_take(device, (size_t)c->grid_pass * sizeof(double));
+    c->partial_hsum = (double*)scratch_take(device, (size_t)c->grid_pass * SAL_KMAX * sizeof(double));
+    if (!c->partial_wnum || !c->partial_obj || !c->partial_hsum) {
+        sal_set_error("cudaMalloc of the workspace failed: %s", cudaGetErrorString(cudaGetLastError()));
+        scratch_give(device, c->partial_wnum), scratch_give(device, c->partial_obj), scratch_give(device, c->partial_hsum);
         delete c;
-        return (int)e;
+        return (int)cudaErrorMemoryAllocation;
     }
     *out = c;
     return 0;
@@ -79,13 +115,29 @@ int sal_create(sal_handle_t* out, int V, int64_t D_local, int k, int dtype, int 
 int sal_destroy(sal_handle_t h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
-    cudaFree(h->partial_wnum), cudaFree(h->partial_obj), cudaFree(h->partial_hsum);
+    // the scratch buffers go back to the per-device free list (a later handle may reuse them on another stream), so
+    // everything that used them has to be complete -- the synchronisation cudaFree used to imply
+    cudaDeviceSynchronize();
+    scratch_give(h->device, h->partial_wnum), scratch_give(h->device, h->partial_obj), scratch_give(h->device, h->partial_hsum);
     if (h->norm_counter) cudaFree(h->norm_counter);
     if (h->ev) {
         for (cudaEvent_t e : *h->ev) cudaEventDestroy(e);
         delete h->ev;
     }
     delete h;
+    return 0;
+}
+
+int sal_trim_scratch(void) {
+    std::lock_guard<std::mutex> lock(g_scratch_mutex);
+    for (Scratch& b : g_scratch)
+        if (!b.in_use) {
+            cudaSetDevice(b.device);
+            cudaFree(b.ptr);
+            b.ptr = nullptr;
+        }
+    g_scratch.erase(std::remove_if(g_scratch.begin(), g_scratch.end(), [](const Scratch& b) { return b.ptr == nullptr; }),
+                    g_scratch.end());
     return 0;
 }
 

@@ -35,7 +35,11 @@ class KLNMF(StandardNMF):
         super().__init__(n_signatures, init_method, min_iterations, max_iterations, conv_test_freq, tol, **device_kwargs)
         self.weights_kl = None
         self.weights_lhalf = None
-        self.use_graphs = True  # capture the periods of the fit loop in CUDA graphs (see _fit_loop)
+        # capture the periods of the fit loop in CUDA graphs (see _fit_loop): True, False or "auto" = only when a shard is
+        # small enough for launch gaps to matter.  Measured on B200 (profiles/r01_e2e_phases.md): at 1M samples an eager
+        # period is within 2 % of a replayed one while capturing ~6 graphs per fit costs more than that and occasionally
+        # stalls in the driver; at 125k samples graphs are 12 % faster.
+        self.use_graphs: bool | str = "auto"
         self.use_small_kernel = True  # problems that fit one SM: persistent single-CTA kernel (see _fit_loop_small)
         # multi-GPU all-reduce of the numerator: "auto" / "p2p" = one-shot NVLink exchange fused into the reduction
         # kernel (sal_klnmf_update_p2p), "nccl" = library collective between separate kernels
@@ -184,6 +188,8 @@ class KLNMF(StandardNMF):
                 st.weights["peer_exchange"] = None
         return st.weights["peer_exchange"]
 
+    _GRAPH_MAX_SAMPLES = 400_000  # "auto": per-update kernel time below ~40 us
+
     def _fit_loop(self, given_parameters, verbose, verbosity_freq):
         """Same iterates, history and stopping iteration as the reference loop (signature_nmf.py:361-380), run in
         periods of ``conv_test_freq`` updates:
@@ -223,7 +229,10 @@ class KLNMF(StandardNMF):
             }
         Ws, Hs, obj_host, graphs = fl["Ws"], fl["Hs"], fl["obj_host"], fl["graphs"]
         seen = torch.cuda.Event()
-        use_graphs = self.use_graphs and not st.ws.timing
+        use_graphs = self.use_graphs
+        if use_graphs == "auto":
+            use_graphs = (st.hi - st.lo) <= self._GRAPH_MAX_SAMPLES
+        use_graphs = bool(use_graphs) and not st.ws.timing
 
         def plan(wi, hi, L):
             """Buffer indices of the L updates of a period that starts from (Ws[wi], Hs[hi])."""
@@ -248,12 +257,20 @@ class KLNMF(StandardNMF):
             key = (wi, hi, L)
             if use_graphs and periods_done >= 2 and key not in graphs:
                 # every kernel variant and the NCCL communicator have been exercised by the eager periods
-                torch.cuda.synchronize(st.device)
+                # (raw capture_begin / capture_end on a side stream: torch.cuda.graph() would synchronise the device and
+                # empty the device and pinned-host allocator caches at every capture)
                 g_head, g_tail = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g_head):
-                    run_head(steps[0])
-                with torch.cuda.graph(g_tail):
-                    run_tail(steps[1:])
+                main = torch.cuda.current_stream(st.device)
+                side = fl.setdefault("capture_stream", torch.cuda.Stream(st.device))
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    for g, body, arg in ((g_head, run_head, steps[0]), (g_tail, run_tail, steps[1:])):
+                        g.capture_begin(capture_error_mode="thread_local")
+                        try:
+                            body(arg)
+                        finally:
+                            g.capture_end()
+                main.wait_stream(side)
                 graphs[key] = (g_head, g_tail)
             if use_graphs and key in graphs:
                 graphs[key][0].replay()

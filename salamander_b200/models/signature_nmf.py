@@ -151,9 +151,12 @@ class SignatureNMF(ABC):
 
     def _release_device(self) -> None:
         if self._dev is not None:
+            tick = getattr(self, "_tick", None) or (lambda name: None)
             if getattr(self._dev, "fit_loop", None):
                 self._dev.fit_loop.clear()  # captured CUDA graphs (and the NCCL work they hold) go first
+            tick("release_graphs")
             self._dev.close()
+            tick("release_workspace")
             self._dev = None
 
     def _resolved_device(self):
@@ -175,15 +178,41 @@ class SignatureNMF(ABC):
 
         def __exit__(self, exc_type, exc, tb):
             if self.owner:
+                tick = getattr(self.m, "_tick", None) or (lambda name: None)
                 try:
                     if exc_type is None:
                         self.m._to_host()
+                        tick("download")
                 finally:
                     self.m._release_device()
+                    tick("release")
             return False
 
     def _resident(self):
         return SignatureNMF._Resident(self)
+
+    def _phase_clock(self):
+        """``model.profile_phases = True`` makes ``fit`` record wall-clock seconds per phase in ``model.phase_seconds``
+        (with a device synchronisation at every boundary, so leave it off when timing a whole fit)."""
+        self._tick = None
+        if not getattr(self, "profile_phases", False):
+            return lambda name: None
+        import time
+
+        import torch
+
+        self.phase_seconds = {}
+        last = [time.perf_counter()]
+
+        def tick(name):
+            if torch.cuda.is_available():
+                torch.cuda.synchronize()
+            now = time.perf_counter()
+            self.phase_seconds[name] = self.phase_seconds.get(name, 0.0) + now - last[0]
+            last[0] = now
+
+        self._tick = tick
+        return tick  # (fit() drops self._tick again: the closure refers to the model)
 
     def _fit_loop(self, given_parameters, verbose, verbosity_freq) -> tuple[list[float], int]:
         """The reference's iteration / convergence logic (signature_nmf.py:361-380); returns (of_values, n)."""
@@ -214,17 +243,23 @@ class SignatureNMF(ABC):
         verbose: Literal[0, 1] = 0,
         verbosity_freq: int = 1000,
     ) -> "SignatureNMF":
+        tick = self._phase_clock()
         self._setup_adata(adata)
+        tick("setup_adata")
         self._initialize(given_parameters, init_kwargs)
         self._setup_fitting_parameters(fitting_kwargs)
+        tick("initialize")
 
         with self._resident():
+            tick("upload")
             self._in_fit = True
             try:
                 of_values, n_iteration = self._fit_loop(given_parameters, verbose, verbosity_freq)
                 self.n_iterations = n_iteration
             finally:
                 self._in_fit = False
+            tick("fit_loop")
+        self._tick = None
 
         if history:
             self.history["objective_function"] = of_values[1:]

@@ -67,6 +67,8 @@ class StandardState:
         self.weights: dict[str, Any] = {}
         self.fit_loop: dict[str, Any] = {}  # spare buffers / CUDA graphs of the period-wise fit driver (KLNMF._fit_loop)
 
+    _STAGED_DOWNLOAD_MIN_BYTES = 1 << 22
+
     def upload(self, host) -> torch.Tensor:
         """Host array -> contiguous device tensor of the model dtype (async DMA when the array is pinned)."""
         t = torch.from_numpy(np.ascontiguousarray(host))
@@ -75,8 +77,22 @@ class StandardState:
 
     def download(self, t: torch.Tensor) -> np.ndarray:
         """Device tensor -> float64 host array (the dtype the reference leaves in the AnnData objects)."""
-        out = t.to(torch.float64).cpu().numpy()
-        self.model.transfer_bytes["d2h"] += out.nbytes
+        out = None
+        if t.numel() * 8 >= self._STAGED_DOWNLOAD_MIN_BYTES:
+            # large results: full-rate DMA in the model dtype into a page-locked staging buffer (kept by torch's
+            # pinned-host cache between fits), then a multi-threaded widening copy into the pageable result
+            try:
+                stage = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+                stage.copy_(t.contiguous(), non_blocking=True)
+                torch.cuda.current_stream(self.device).synchronize()
+                out = torch.empty(t.shape, dtype=torch.float64).copy_(stage).numpy()
+                moved = stage.numel() * stage.element_size()
+            except RuntimeError:
+                out = None  # page-locked memory exhausted: plain pageable copy below
+        if out is None:
+            out = t.to(torch.float64).cpu().numpy()
+            moved = out.nbytes
+        self.model.transfer_bytes["d2h"] += moved  # bytes that crossed the bus
         return out
 
     def shard(self, per_sample) -> torch.Tensor | None:

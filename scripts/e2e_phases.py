@@ -1,0 +1,39 @@
+"""Where does KLNMF.fit(adata) spend its wall-clock time at the bench workload?  (diagnostic; prints one JSON line)"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench  # noqa: E402
+from salamander_b200._anndata import AnnData  # noqa: E402
+from salamander_b200.models import KLNMF  # noqa: E402
+
+
+def main():
+    D = int(os.environ.get("D", 1_000_000))
+    k, steps = 20, int(os.environ.get("STEPS", 500))
+    X_host = torch.empty((D, 96), dtype=torch.float32).pin_memory().numpy()
+    bench.synth_rows(0, D, k, out=X_host)
+    W0, H0 = bench.init_rows(X_host, 0, k)
+    H0_pin = torch.from_numpy(H0).pin_memory().numpy()
+    out = []
+    for rep in range(int(os.environ.get('REPS', 8))):
+        m = KLNMF(n_signatures=k, init_method="custom", dtype="float32", math="tf32", min_iterations=steps,
+                  max_iterations=steps, shard_input=False)
+        m.use_graphs = {'1': True, '0': False}.get(os.environ.get('GRAPHS', 'auto'), 'auto')
+        m.profile_phases = rep >= int(os.environ.get('PROFILE_FROM', 6))
+        ad = AnnData(X_host)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        m.fit(ad, init_kwargs={"signatures_mat": W0, "exposures_mat": H0_pin})
+        torch.cuda.synchronize()
+        out.append({"rep": rep, "total_s": time.perf_counter() - t0, "phases": getattr(m, "phase_seconds", None)})
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
