@@ -58,8 +58,11 @@ enum {
     SAL_PASS_SAMPLEWISE = 8, /* write per_sample[d] = unweighted KL of sample d              */
     SAL_PASS_HSUM = 16,      /* write hsum[k] = sum_d H_in[d][k]                             */
     SAL_PASS_POISSON = 32,   /* objective = sum x ln(wh) - wh  (Poisson llh w/o ln Gamma)    */
-    SAL_PASS_NOCLIP = 64     /* with UPDATE_H: H_out = H * W^T A without the clip -- this is CorrNMF's
+    SAL_PASS_NOCLIP = 64,    /* with UPDATE_H: H_out = H * W^T A without the clip -- this is CorrNMF's
                                 aux^T [D][k] (compute_aux, _utils_corrnmf.py:28-52) when H_in holds the exposures */
+    SAL_PASS_PARTIALS_ONLY = 128 /* measurement aid: run the streaming kernel only and leave its per-CTA partial sums in
+                                the workspace (Wnum / objective / hsum are NOT written), so that a caller can time the
+                                kernel back to back between one pair of events (bench.py roofline leg) */
 };
 
 const char* sal_last_error(void);

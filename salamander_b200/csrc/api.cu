@@ -1,6 +1,7 @@
 // C ABI of libsalamander_b200.so -- argument checking, workspace ownership, dispatch.
 // Declarations and the reference sites each entry point replaces: include/salamander_b200.h
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "sal_common.cuh"
@@ -69,6 +70,14 @@ static void scratch_give(int device, void* p) {
     std::lock_guard<std::mutex> lock(g_scratch_mutex);
     for (Scratch& b : g_scratch)
         if (b.ptr == p && b.device == device) b.in_use = false;
+}
+
+bool sal_pdl_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("SAL_B200_NO_PDL");
+        return !(e && e[0] == '1');
+    }();
+    return on;
 }
 
 extern "C" {
@@ -187,9 +196,11 @@ int sal_klnmf_pass(sal_handle_t h, const void* X, const void* W, const void* H_i
                    double* objective, void* per_sample, void* hsum, void* stream) {
     SAL_CHECK_ARG(h != nullptr, "handle is null");
     SAL_CHECK_ARG(W && (h->D == 0 || (X && H_in)), "X, W, H_in must be non-null");
+    const int partials_only = flags & SAL_PASS_PARTIALS_ONLY;
+    flags &= ~SAL_PASS_PARTIALS_ONLY;
     SAL_CHECK_ARG(flags != 0, "flags == 0: nothing to do");
     SAL_CHECK_ARG(!(flags & SAL_PASS_UPDATE_H) || H_out || h->D == 0, "UPDATE_H needs H_out");
-    SAL_CHECK_ARG(!(flags & SAL_PASS_WNUM) || Wnum, "WNUM needs Wnum");
+    SAL_CHECK_ARG(!(flags & SAL_PASS_WNUM) || Wnum || partials_only, "WNUM needs Wnum");
     SAL_CHECK_ARG(!(flags & (SAL_PASS_OBJECTIVE | SAL_PASS_POISSON)) || objective, "OBJECTIVE needs objective");
     SAL_CHECK_ARG(!((flags & SAL_PASS_OBJECTIVE) && (flags & SAL_PASS_POISSON)), "OBJECTIVE and POISSON are exclusive");
     SAL_CHECK_ARG(!((flags & SAL_PASS_SAMPLEWISE) && (flags & SAL_PASS_POISSON)), "SAMPLEWISE and POISSON are exclusive");
@@ -207,7 +218,7 @@ int sal_klnmf_pass(sal_handle_t h, const void* X, const void* W, const void* H_i
     PassArgs a;
     a.X = X, a.W = W, a.H_in = H_in, a.w_kl = w_kl, a.w_lhalf = w_lhalf, a.h_scale = h_scale;
     a.H_out = H_out, a.Wnum = Wnum, a.per_sample = per_sample, a.hsum = hsum, a.objective = objective;
-    a.flags = flags;
+    a.flags = flags, a.partials_only = partials_only ? 1 : 0;
     if (h->math != SAL_MATH_FMA && sal_pass_tf32_supported(h, a)) return sal_launch_pass_tf32(h, a, st);
     return sal_launch_pass_fma(h, a, st);
 }

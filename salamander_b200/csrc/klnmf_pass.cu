@@ -306,6 +306,8 @@ __global__ void __launch_bounds__(FIN_THREADS) klnmf_finish_kernel(const T* part
     __shared__ double s_part[FIN_PARTS][VP];
     __shared__ double s_red[VP / 32];
     const int j = blockIdx.x, tid = threadIdx.x;
+    pdl_trigger();
+    pdl_wait();  // the partials come from the pass kernel this launch may have overtaken
     if (j < k) {
         if (!(flags & SAL_PASS_WNUM)) return;
         const int part = tid / VP, v = tid - part * VP;
@@ -391,6 +393,8 @@ __global__ void __launch_bounds__(FIN_THREADS) klnmf_finish_p2p_kernel(const T* 
     __shared__ double s_obj[FIN_THREADS / 32];
     const int j = blockIdx.x, tid = threadIdx.x;
     const int part = tid / VP, v = tid - part * VP;
+    pdl_trigger();
+    pdl_wait();  // partials, sequence number and W all come from kernels this launch may have overtaken
     const unsigned int seq = *(volatile unsigned int*)x.seq;
     const int slot = seq & 1;
     const bool is_obj = j == k;
@@ -575,20 +579,20 @@ int launch_pass_k(sal_ctx* c, const PassArgs& a, cudaStream_t st) {
 
 // Fixed-order sum of the per-CTA partials left by either flavour of the pass (n_part = its grid size).
 int sal_launch_pass_reduce(sal_ctx* c, const PassArgs& a, int n_part, cudaStream_t st) {
-    if (!(a.flags & (SAL_PASS_WNUM | SAL_PASS_OBJECTIVE | SAL_PASS_POISSON | SAL_PASS_HSUM))) return 0;
+    if (!(a.flags & (SAL_PASS_WNUM | SAL_PASS_OBJECTIVE | SAL_PASS_POISSON | SAL_PASS_HSUM)) || a.partials_only) return 0;
     if (a.p2p_peers) {
         P2PExchange x;
         x.peers = (void* const*)a.p2p_peers, x.seq = (unsigned int*)a.p2p_state, x.ticket = (unsigned int*)a.p2p_state + 1;
         x.n_ranks = a.p2p_n_ranks, x.rank = a.p2p_rank;
         const int grid = c->k + 1;
         if (c->dtype == SAL_F32)
-            klnmf_finish_p2p_kernel<float><<<grid, FIN_THREADS, 0, st>>>((const float*)c->partial_wnum, c->partial_obj, n_part, c->KP, c->k,
-                                                                        c->V, a.flags, (float*)a.Wnum, a.objective, (const float*)a.W,
-                                                                        (float*)a.W_out, a.n_given, a.clip_given, x);
+            SAL_CUDA(sal_launch_pdl(klnmf_finish_p2p_kernel<float>, grid, FIN_THREADS, 0, st, (const float*)c->partial_wnum, c->partial_obj,
+                                    n_part, c->KP, c->k, c->V, a.flags, (float*)a.Wnum, a.objective, (const float*)a.W, (float*)a.W_out,
+                                    a.n_given, a.clip_given, x));
         else
-            klnmf_finish_p2p_kernel<double><<<grid, FIN_THREADS, 0, st>>>((const double*)c->partial_wnum, c->partial_obj, n_part, c->KP, c->k,
-                                                                         c->V, a.flags, (double*)a.Wnum, a.objective, (const double*)a.W,
-                                                                         (double*)a.W_out, a.n_given, a.clip_given, x);
+            SAL_CUDA(sal_launch_pdl(klnmf_finish_p2p_kernel<double>, grid, FIN_THREADS, 0, st, (const double*)c->partial_wnum, c->partial_obj,
+                                    n_part, c->KP, c->k, c->V, a.flags, (double*)a.Wnum, a.objective, (const double*)a.W, (double*)a.W_out,
+                                    a.n_given, a.clip_given, x));
         SAL_CUDA(cudaGetLastError());
         c->launches++;
         return 0;
@@ -597,13 +601,13 @@ int sal_launch_pass_reduce(sal_ctx* c, const PassArgs& a, int n_part, cudaStream
     const int grid = c->k + (need_tail ? 1 : 0);
     const int fuse = a.fuse_epilogue && (a.flags & SAL_PASS_WNUM);
     if (c->dtype == SAL_F32)
-        klnmf_finish_kernel<float><<<grid, FIN_THREADS, 0, st>>>(
-            (const float*)c->partial_wnum, c->partial_obj, c->partial_hsum, n_part, c->KP, c->k, c->V, a.flags, (float*)a.Wnum,
-            a.objective, (float*)a.hsum, fuse, (const float*)a.W, (float*)a.W_out, a.n_given, a.clip_given);
+        SAL_CUDA(sal_launch_pdl(klnmf_finish_kernel<float>, grid, FIN_THREADS, 0, st, (const float*)c->partial_wnum, c->partial_obj,
+                                c->partial_hsum, n_part, c->KP, c->k, c->V, a.flags, (float*)a.Wnum, a.objective, (float*)a.hsum, fuse,
+                                (const float*)a.W, (float*)a.W_out, a.n_given, a.clip_given));
     else
-        klnmf_finish_kernel<double><<<grid, FIN_THREADS, 0, st>>>(
-            (const double*)c->partial_wnum, c->partial_obj, c->partial_hsum, n_part, c->KP, c->k, c->V, a.flags, (double*)a.Wnum,
-            a.objective, (double*)a.hsum, fuse, (const double*)a.W, (double*)a.W_out, a.n_given, a.clip_given);
+        SAL_CUDA(sal_launch_pdl(klnmf_finish_kernel<double>, grid, FIN_THREADS, 0, st, (const double*)c->partial_wnum, c->partial_obj,
+                                c->partial_hsum, n_part, c->KP, c->k, c->V, a.flags, (double*)a.Wnum, a.objective, (double*)a.hsum, fuse,
+                                (const double*)a.W, (double*)a.W_out, a.n_given, a.clip_given));
     SAL_CUDA(cudaGetLastError());
     c->launches++;
     return 0;

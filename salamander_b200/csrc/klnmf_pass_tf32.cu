@@ -308,6 +308,9 @@ klnmf_pass_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
     const int n_my = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // tiles of this CTA (>= 1)
 
     // ---- one-time setup --------------------------------------------------------------------------
+    // (programmatic dependent launch: everything down to pdl_wait() is independent of the previous kernels and
+    // overlaps the reduction kernel of the previous update)
+    pdl_trigger();
     stamp(p.dbg, p.dbg != nullptr && blockIdx.x == 1 && tid == 0, 3, 0, 1);
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapX) : "memory");
@@ -333,14 +336,28 @@ klnmf_pass_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    // W operands as tf32 hi + lo (round to nearest), zero padding for signatures >= k; sHT zero fill.
+    if (DO_R)
+        for (int i = tid; i < q.sht / 4; i += NTHREADS) sts32(sHT + 4 * i, 0.f);
+    __syncthreads();  // barriers initialised
+    // X never changes during a fit: the first S tiles of it are requested before the dependency wait, so the pipeline is
+    // already full when the previous update's reduction kernel retires
+    const int n_pre = n_my < S ? n_my : S;
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < n_pre; ++i) {
+            const int d0 = ((int)blockIdx.x + i * (int)gridDim.x) * TILE;
+            mbar_arrive_expect_tx(bar_full + 8 * i, XSTAGE_BYTES);
+            for (int c = 0; c < NBOX; ++c) tma_load_2d(sX + i * XSTAGE_BYTES + c * BOX_BYTES, &mapX, bar_full + 8 * i, c * 32, d0);
+        }
+    }
+    // W operands as tf32 hi + lo (round to nearest), zero padding for signatures >= k.
     // KP8 * 96 = (KP8 / 4) * 384 elements: every thread first issues all its global loads, then converts and stores.
+    pdl_wait();  // W (previous reduction kernel) and H (previous pass) are valid from here on
     {
         float wreg[KP8 / 4];
 #pragma unroll
         for (int it = 0; it < KP8 / 4; ++it) {
             const int i = tid + it * NTHREADS, j = i / VT, f = i - j * VT;
-            wreg[it] = j < k ? __ldg(p.W + (size_t)j * VT + f) : 0.f;
+            wreg[it] = j < k ? __ldcg(p.W + (size_t)j * VT + f) : 0.f;  // L2 only: W was written while this grid was resident
         }
 #pragma unroll
         for (int it = 0; it < KP8 / 4; ++it) {
@@ -352,8 +369,6 @@ klnmf_pass_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
             if (DO_R) sts32(sW2 + (f >> 2) * q.sw2_lbo + (j >> 3) * SW2_SBO + (j & 7) * 16 + (f & 3) * 4, hi);
         }
     }
-    if (DO_R)
-        for (int i = tid; i < q.sht / 4; i += NTHREADS) sts32(sHT + 4 * i, 0.f);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -373,6 +388,7 @@ klnmf_pass_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
                 mbar_wait(bar_hempty + 8 * hs, ((i / NH) & 1) ^ 1);
                 mbar_arrive_expect_tx(bar_hfull + 8 * hs, (uint32_t)(TILE * k * 4));
                 tma_load_2d(sHraw + hs * q.hraw, &mapH, bar_hfull + 8 * hs, 0, d0);
+                if (i < n_pre) continue;  // requested in the prologue
                 mbar_wait(bar_empty + 8 * st, ((i / S) & 1) ^ 1);
                 stamp(p.dbg, tl, 3, i, 0);
                 mbar_arrive_expect_tx(bar_full + 8 * st, XSTAGE_BYTES);
@@ -708,8 +724,7 @@ int launch_tc_v(sal_ctx* c, const PassArgs& a, cudaStream_t st) {
     p.n_tiles = (int)((c->D + TILE - 1) / TILE);
     const int grid = p.n_tiles < c->n_sm ? p.n_tiles : c->n_sm;
     if (int e = sal_timing_begin(c, a.flags, st)) return e;
-    klnmf_pass_tc_kernel<KP8, DO_R, DO_KL><<<grid, NTHREADS, q.total, st>>>(mapX, mapH, mapHout, p);
-    SAL_CUDA(cudaGetLastError());
+    SAL_CUDA(sal_launch_pdl(klnmf_pass_tc_kernel<KP8, DO_R, DO_KL>, grid, NTHREADS, q.total, st, mapX, mapH, mapHout, p));
     if (int e = sal_timing_end(c, a.flags, st)) return e;
     c->launches++;
     return sal_launch_pass_reduce(c, a, grid, st);

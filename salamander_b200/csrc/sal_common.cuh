@@ -2,6 +2,8 @@
 #pragma once
 
 #include <cuda_runtime.h>
+
+#include <utility>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -55,6 +57,30 @@ void sal_set_error(const char* fmt, ...);
 static inline int sal_kpad(int k) { return k <= 8 ? 8 : k <= 16 ? 16 : k <= 24 ? 24 : 32; }
 
 // ---- launchers implemented in the .cu files -------------------------------------------------
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------------------
+// The update is a chain pass -> finish -> pass -> ...; each kernel's set-up (barrier init, TMEM allocation, descriptor
+// prefetch, block scheduling) does not depend on its predecessor.  Kernels launched through sal_launch_pdl may start
+// while the previous kernel in the stream is still running; they MUST execute pdl_wait() before touching anything a
+// predecessor wrote (it returns once the predecessor grid has completed and its writes are visible) and call
+// pdl_trigger() early so that their own successor can be scheduled.  SAL_B200_NO_PDL=1 turns the attribute off.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+bool sal_pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t sal_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr, cfg.numAttrs = sal_pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
+#endif
+
 struct PassArgs {
     const void *X, *W, *H_in, *w_kl, *w_lhalf, *h_scale;
     void *H_out, *Wnum, *per_sample, *hsum;
@@ -67,6 +93,7 @@ struct PassArgs {
     const void* p2p_peers = nullptr;  // device array [n_ranks] of exchange-buffer pointers
     void* p2p_state = nullptr;        // device unsigned[2]: {sequence number (starts at 1), ticket (0)}
     int p2p_n_ranks = 0, p2p_rank = 0;
+    int partials_only = 0;  // SAL_PASS_PARTIALS_ONLY: skip the reduction kernel
 };
 int sal_launch_pass_fma(sal_ctx* c, const PassArgs& a, cudaStream_t st);
 int sal_launch_pass_tf32(sal_ctx* c, const PassArgs& a, cudaStream_t st);  // tcgen05 path (fp32 only)
