@@ -220,6 +220,11 @@ int sal_corrnmf_sample_embeddings_mm(sal_handle_t h, const void* auxT, const voi
                                      void* U, int m, double variance, int maxiter, void* stream);
 int sal_corrnmf_signature_embeddings(sal_handle_t h, const void* auxT, const void* a, const void* b, void* L,
                                      const void* U, int m, double variance, void* stream);
+/* The same update for the signatures sig_begin .. sig_begin + sig_count - 1 only; the other rows of L are left alone.
+ * Multi-GPU CorrNMF: the per-sample inputs are all-gathered and every rank solves its share of the signatures. */
+int sal_corrnmf_signature_embeddings_range(sal_handle_t h, const void* auxT, const void* a, const void* b, void* L,
+                                           const void* U, int m, double variance, int sig_begin, int sig_count,
+                                           void* stream);
 /* out[0] = sum L^2, out[1] = sum U^2 (update_variance corrnmf_det.py:60-69, ELBO priors _utils_corrnmf.py:93-98),
  * out[2] = sum lnGamma(1 + X) when X != NULL (constant of poisson_llh, _utils_klnmf.py:159) */
 int sal_corrnmf_norms(sal_handle_t h, const void* L, const void* U, int m, const void* X_or_null, double* out,

@@ -54,6 +54,7 @@ SYMBOLS = {
     "sal_corrnmf_sample_embeddings": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _d, _i, _vp]),
     "sal_corrnmf_sample_embeddings_mm": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _d, _i, _vp]),
     "sal_corrnmf_signature_embeddings": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _d, _vp]),
+    "sal_corrnmf_signature_embeddings_range": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _d, _i, _i, _vp]),
     "sal_corrnmf_norms": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp]),
 }
 

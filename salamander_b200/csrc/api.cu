@@ -396,7 +396,16 @@ int sal_corrnmf_signature_embeddings(sal_handle_t h, const void* auxT, const voi
     SAL_CORR_COMMON(m);
     SAL_CHECK_ARG(a && L && (h->D == 0 || (auxT && b && U)), "null argument");
     SAL_CHECK_ARG(variance > 0.0, "variance must be positive");
-    return sal_launch_corrnmf_signature_embeddings(h, auxT, a, b, L, U, m, variance, (cudaStream_t)stream);
+    return sal_launch_corrnmf_signature_embeddings(h, auxT, a, b, L, U, m, variance, 0, h->k, (cudaStream_t)stream);
+}
+
+int sal_corrnmf_signature_embeddings_range(sal_handle_t h, const void* auxT, const void* a, const void* b, void* L, const void* U,
+                                           int m, double variance, int sig_begin, int sig_count, void* stream) {
+    SAL_CORR_COMMON(m);
+    SAL_CHECK_ARG(a && L && (h->D == 0 || (auxT && b && U)), "null argument");
+    SAL_CHECK_ARG(variance > 0.0, "variance must be positive");
+    SAL_CHECK_ARG(sig_begin >= 0 && sig_count >= 0 && sig_begin + sig_count <= h->k, "signature range out of bounds");
+    return sal_launch_corrnmf_signature_embeddings(h, auxT, a, b, L, U, m, variance, sig_begin, sig_count, (cudaStream_t)stream);
 }
 
 int sal_corrnmf_norms(sal_handle_t h, const void* L, const void* U, int m, const void* X_or_null, double* out, void* stream) {

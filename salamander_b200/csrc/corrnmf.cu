@@ -99,6 +99,9 @@ __device__ void dcstep(StepState& s, double fp, double dp, double stpmin, double
 // ---------------------------------------------------------------------------------------------------------
 // Newton-CG.  Problem P provides (collectively for the calling threads; every thread gets the same values):
 //   double f(const double* x);  void grad(const double* x, double* g);  void hess(const double* x, double* A /*m*m*/)
+//   double f_grad(const double* x, double* g)   -- f and grad of the same point in one sweep (one exp per term)
+// SciPy evaluates fprime(xk) again at the top of every Newton iteration; xk is the accepted line-search point, whose
+// gradient DCSRCH has just used, so it is kept instead of recomputed (same function, same point).
 // ---------------------------------------------------------------------------------------------------------
 template <class P>
 __device__ void newton_cg(P& prob, double* x, int m, int maxiter) {
@@ -110,9 +113,14 @@ __device__ void newton_cg(P& prob, double* x, int m, int maxiter) {
     bool have_old_old = false;
     double update_l1 = 1.7976931348623157e308;
     int k = 0;
+    bool have_grad = false;
+    double gkeep[MAXM];
     while (update_l1 > xtol) {
         if (k >= maxiter) break;
-        prob.grad(x, gt);
+        if (have_grad)
+            for (int i = 0; i < m; ++i) gt[i] = gkeep[i];
+        else
+            prob.grad(x, gt);
         double maggrad = 0.0;
         for (int i = 0; i < m; ++i) b[i] = -gt[i], maggrad += fabs(b[i]);
         const double termcond = fmin(0.5, sqrt(maggrad)) * maggrad;
@@ -173,9 +181,8 @@ __device__ void newton_cg(P& prob, double* x, int m, int maxiter) {
             double stmin = 0.0, stmax = alpha1 + 4.0 * alpha1;
             for (int ls = 0; ls < 99; ++ls) {
                 for (int i = 0; i < m; ++i) xt[i] = x[i] + s.stp * xs[i];
-                const double f = prob.f(xt);
                 double gl[MAXM];
-                prob.grad(xt, gl);
+                const double f = prob.f_grad(xt, gl);
                 double g = 0.0;
                 for (int i = 0; i < m; ++i) g += gl[i] * xs[i];
                 const double ftest = finit + s.stp * gtest;
@@ -187,6 +194,7 @@ __device__ void newton_cg(P& prob, double* x, int m, int maxiter) {
                 if (s.stp == stpmin && (f > ftest || g >= gtest)) warn = true;
                 if (f <= ftest && fabs(g) <= gtol * -ginit) {
                     ok = true, fnew = f, stp_ok = s.stp;
+                    for (int i = 0; i < m; ++i) gkeep[i] = gl[i];
                     break;
                 }
                 if (warn) break;
@@ -216,10 +224,11 @@ __device__ void newton_cg(P& prob, double* x, int m, int maxiter) {
         old_old_fval = old_fval, have_old_old = true, old_fval = fnew;
         update_l1 = 0.0;
         for (int i = 0; i < m; ++i) {
-            const double u = stp_ok * xs[i];
-            x[i] += u;
-            update_l1 += fabs(u);
+            const double xn = x[i] + stp_ok * xs[i];  // the very expression the trial point was formed with
+            update_l1 += fabs(stp_ok * xs[i]);
+            x[i] = xn;
         }
+        have_grad = true;
         ++k;
     }
 }
@@ -260,6 +269,19 @@ struct SampleProblem {
             const double w = exp(s_vec[i] + s_others[i] + sp) - aux[i];
             for (int j = 0; j < m; ++j) g[j] += w * others[i * m + j];
         }
+    }
+    __device__ double f_grad(const double* x, double* g) const {
+        double acc = 0.0, nrm = 0.0;
+        for (int j = 0; j < m; ++j) g[j] = x[j] * inv_var, nrm += x[j] * x[j];
+        for (int i = 0; i < k; ++i) {
+            double sp = 0.0;
+            for (int j = 0; j < m; ++j) sp += others[i * m + j] * x[j];
+            const double e = exp(s_vec[i] + s_others[i] + sp);
+            acc += sp * aux[i] - e;
+            const double w = e - aux[i];
+            for (int j = 0; j < m; ++j) g[j] += w * others[i * m + j];
+        }
+        return -(acc - 0.5 * nrm * inv_var);
     }
     __device__ void hess(const double* x, double* A) const {
         for (int j = 0; j < m * m; ++j) A[j] = 0.0;
@@ -360,6 +382,22 @@ struct SignatureProblem {
         reduce(g, m);
         for (int q = 0; q < m; ++q) g[q] += x[q] * inv_var;
     }
+    __device__ double f_grad(const double* x, double* g) const {
+        double v[1 + MAXM];
+        for (int q = 0; q <= m; ++q) v[q] = 0.0;
+        for (int64_t d = (int64_t)rank * SIG_THREADS + threadIdx.x; d < D; d += (int64_t)nrank * SIG_THREADS) {
+            double sp = 0.0;
+            for (int q = 0; q < m; ++q) sp += (double)U[d * m + q] * x[q];
+            const double e = exp(s + (double)b[d] + sp), ax = (double)auxT[d * k + j];
+            v[0] += sp * ax - e;
+            const double w = e - ax;
+            for (int q = 0; q < m; ++q) v[1 + q] += w * (double)U[d * m + q];
+        }
+        reduce(v, 1 + m);
+        double nrm = 0.0;
+        for (int q = 0; q < m; ++q) nrm += x[q] * x[q], g[q] = v[1 + q] + x[q] * inv_var;
+        return -(v[0] - 0.5 * nrm * inv_var);
+    }
     __device__ void hess(const double* x, double* A) const {
         for (int q = 0; q < m * m; ++q) A[q] = 0.0;
         for (int64_t d = (int64_t)rank * SIG_THREADS + threadIdx.x; d < D; d += (int64_t)nrank * SIG_THREADS) {
@@ -376,12 +414,12 @@ struct SignatureProblem {
 
 template <typename T>
 __global__ void __launch_bounds__(SIG_THREADS) signature_embeddings_kernel(const T* auxT, const T* a, const T* b, T* L, const T* U,
-                                                                          int64_t D, int k, int m, double variance) {
+                                                                          int64_t D, int k, int m, double variance, int sig_begin) {
     __shared__ double red[(SIG_THREADS / 32) * (1 + MAXM + MAXM * MAXM)];
     __shared__ double cl[1 + MAXM + MAXM * MAXM];
     cg::cluster_group cluster = cg::this_cluster();
     const int nrank = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
-    const int j = blockIdx.x / nrank;  // one cluster per signature; every CTA of it runs the same Newton-CG on the same numbers
+    const int j = sig_begin + blockIdx.x / nrank;  // one cluster per signature; every CTA of it runs the same Newton-CG on the same numbers
     double x[MAXM];
     for (int q = 0; q < m; ++q) x[q] = (double)L[j * m + q];
     SignatureProblem<T> p{U, b, auxT, red, cl, (double)a[j], 1.0 / variance, D, k, m, j, rank, nrank};
@@ -441,22 +479,43 @@ __device__ double block_sum_256(double v, double* s_red) {
     return t;
 }
 
-// one CTA per signature: sums[j] = sum_d aux_dj, sums[k + j] = sum_d exp(b_d + l_j.u_d)  (this rank's samples)
+// sums[j] = sum_d aux_dj, sums[k + j] = sum_d exp(b_d + l_j.u_d)  (this rank's samples).  SCAL_BLOCKS CTAs per signature
+// (blockIdx.y = signature) each leave a partial pair; the last one to finish adds them in block order (deterministic).
+constexpr int SCAL_BLOCKS = 32;
 template <typename T>
 __global__ void __launch_bounds__(256) signature_scalings_kernel(const T* auxT, const T* b, const T* L, const T* U, int64_t D, int k, int m,
-                                                                double* sums) {
+                                                                double* partial, unsigned int* counter, double* sums) {
     __shared__ double s_red[8];
-    const int j = blockIdx.x;
+    __shared__ bool last;
+    const int j = blockIdx.y;
+    double l[MAXM];
+    for (int q = 0; q < m; ++q) l[q] = (double)L[j * m + q];
     double s1 = 0.0, s2 = 0.0;
-    for (int64_t d = threadIdx.x; d < D; d += 256) {
+    for (int64_t d = (int64_t)blockIdx.x * 256 + threadIdx.x; d < D; d += (int64_t)SCAL_BLOCKS * 256) {
         double sp = 0.0;
-        for (int q = 0; q < m; ++q) sp += (double)L[j * m + q] * (double)U[d * m + q];
+        for (int q = 0; q < m; ++q) sp += l[q] * (double)U[d * m + q];
         s1 += (double)auxT[d * k + j];
         s2 += exp((double)b[d] + sp);
     }
     s1 = block_sum_256(s1, s_red);
     s2 = block_sum_256(s2, s_red);
-    if (threadIdx.x == 0) sums[j] = s1, sums[k + j] = s2;
+    if (threadIdx.x == 0) {
+        partial[(2 * j) * SCAL_BLOCKS + blockIdx.x] = s1;
+        partial[(2 * j + 1) * SCAL_BLOCKS + blockIdx.x] = s2;
+        __threadfence();
+        last = atomicAdd(&counter[j], 1u) == SCAL_BLOCKS - 1;
+    }
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        __threadfence();
+        double t1 = 0.0, t2 = 0.0;
+        for (int i = 0; i < SCAL_BLOCKS; ++i) {
+            t1 += ((volatile double*)partial)[(2 * j) * SCAL_BLOCKS + i];
+            t2 += ((volatile double*)partial)[(2 * j + 1) * SCAL_BLOCKS + i];
+        }
+        sums[j] = t1, sums[k + j] = t2;
+        counter[j] = 0;
+    }
 }
 
 template <typename T>
@@ -540,10 +599,25 @@ int sal_launch_corrnmf_sample_scalings(sal_ctx* c, const void* xsum, const void*
     return 0;
 }
 
+// counters of the "last block adds the partials" reductions: [0..3] norms, [4..4 + SAL_KMAX) signature scalings
+static int ensure_counters(sal_ctx* c, cudaStream_t st) {
+    if (!c->norm_counter) {
+        SAL_CUDA(cudaMalloc((void**)&c->norm_counter, (4 + SAL_KMAX) * sizeof(unsigned int)));
+        SAL_CUDA(cudaMemsetAsync(c->norm_counter, 0, (4 + SAL_KMAX) * sizeof(unsigned int), st));
+    }
+    return 0;
+}
+
 int sal_launch_corrnmf_signature_scalings_sums(sal_ctx* c, const void* auxT, const void* b, const void* L, const void* U, int m,
                                                double* sums, cudaStream_t st) {
-    SAL_DISPATCH_T(c, (signature_scalings_kernel<float><<<c->k, 256, 0, st>>>((const float*)auxT, (const float*)b, (const float*)L, (const float*)U, c->D, c->k, m, sums)),
-                   (signature_scalings_kernel<double><<<c->k, 256, 0, st>>>((const double*)auxT, (const double*)b, (const double*)L, (const double*)U, c->D, c->k, m, sums)));
+    if (int e = ensure_counters(c, st)) return e;
+    // scratch: 2 * k * SCAL_BLOCKS doubles at the start of the W-numerator partials (no pass is in flight on this stream)
+    static_assert(2 * SAL_KMAX * SCAL_BLOCKS * sizeof(double) <= (size_t)148 * SAL_KMAX * SAL_VMAX * 4, "scratch too small");
+    double* partial = (double*)c->partial_wnum;
+    unsigned int* counter = c->norm_counter + 4;
+    const dim3 grid(SCAL_BLOCKS, c->k);
+    SAL_DISPATCH_T(c, (signature_scalings_kernel<float><<<grid, 256, 0, st>>>((const float*)auxT, (const float*)b, (const float*)L, (const float*)U, c->D, c->k, m, partial, counter, sums)),
+                   (signature_scalings_kernel<double><<<grid, 256, 0, st>>>((const double*)auxT, (const double*)b, (const double*)L, (const double*)U, c->D, c->k, m, partial, counter, sums)));
     SAL_CUDA(cudaGetLastError());
     c->launches++;
     return 0;
@@ -569,23 +643,37 @@ int sal_launch_corrnmf_sample_embeddings(sal_ctx* c, const void* auxT, const voi
 }
 
 int sal_launch_corrnmf_signature_embeddings(sal_ctx* c, const void* auxT, const void* a, const void* b, void* L, const void* U, int m,
-                                            double variance, cudaStream_t st) {
-    // one thread-block cluster per signature: 8 CTAs share the sums over samples once there is enough work for them
-    const int csize = c->D >= 8 * 4 * SIG_THREADS ? 8 : 1;
+                                            double variance, int sig_begin, int sig_count, cudaStream_t st) {
+    if (sig_count <= 0) return 0;
+    // one thread-block cluster per signature: 8 CTAs share the sums over samples once there is enough work for them, 16
+    // (non-portable size: one cluster per GPC, 8 GPCs) when there are few signatures and a lot of samples
+    int csize = c->D >= 8 * 4 * SIG_THREADS ? 8 : 1;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(c->k * csize), cfg.blockDim = dim3(SIG_THREADS), cfg.dynamicSmemBytes = 0, cfg.stream = st;
+    cfg.blockDim = dim3(SIG_THREADS), cfg.dynamicSmemBytes = 0, cfg.stream = st;
     cudaLaunchAttribute attr;
     attr.id = cudaLaunchAttributeClusterDimension;
-    attr.val.clusterDim.x = csize, attr.val.clusterDim.y = 1, attr.val.clusterDim.z = 1;
+    attr.val.clusterDim.y = 1, attr.val.clusterDim.z = 1;
     cfg.attrs = &attr, cfg.numAttrs = 1;
+    if (sig_count <= 8 && c->D >= 16 * 8 * SIG_THREADS) {
+        const void* fn = c->dtype == SAL_F32 ? (const void*)signature_embeddings_kernel<float> : (const void*)signature_embeddings_kernel<double>;
+        int n_active = 0;
+        attr.val.clusterDim.x = 16;
+        cfg.gridDim = dim3(sig_count * 16);
+        if (cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+            cudaOccupancyMaxActiveClusters(&n_active, fn, &cfg) == cudaSuccess && n_active >= sig_count)
+            csize = 16;
+        (void)cudaGetLastError();  // a refused query is not an error of this call: fall back to the portable size
+    }
+    attr.val.clusterDim.x = csize;
+    cfg.gridDim = dim3(sig_count * csize);
     const int64_t D = c->D;
     const int k = c->k;
     if (c->dtype == SAL_F32)
         SAL_CUDA(cudaLaunchKernelEx(&cfg, signature_embeddings_kernel<float>, (const float*)auxT, (const float*)a, (const float*)b, (float*)L,
-                                    (const float*)U, D, k, m, variance));
+                                    (const float*)U, D, k, m, variance, sig_begin));
     else
         SAL_CUDA(cudaLaunchKernelEx(&cfg, signature_embeddings_kernel<double>, (const double*)auxT, (const double*)a, (const double*)b,
-                                    (double*)L, (const double*)U, D, k, m, variance));
+                                    (double*)L, (const double*)U, D, k, m, variance, sig_begin));
     SAL_CUDA(cudaGetLastError());
     c->launches++;
     return 0;
@@ -594,10 +682,7 @@ int sal_launch_corrnmf_signature_embeddings(sal_ctx* c, const void* auxT, const 
 int sal_launch_corrnmf_norms(sal_ctx* c, const void* L, const void* U, int m, const void* X_or_null, double* out, cudaStream_t st) {
     // scratch: the objective partials of the pass (>= 296 doubles) hold the 3 x 64 partials; the counters follow out[3]
     static_assert(3 * NORM_BLOCKS <= 148 * SAL_KMAX, "partial_hsum has n_sm * SAL_KMAX slots at least");
-    if (!c->norm_counter) {
-        SAL_CUDA(cudaMalloc((void**)&c->norm_counter, 4 * sizeof(unsigned int)));
-        SAL_CUDA(cudaMemsetAsync(c->norm_counter, 0, 4 * sizeof(unsigned int), st));
-    }
+    if (int e = ensure_counters(c, st)) return e;
     const dim3 grid(NORM_BLOCKS, X_or_null ? 3 : 2);
     SAL_DISPATCH_T(c, (norms_kernel<float><<<grid, 256, 0, st>>>((const float*)L, (int64_t)c->k * m, (const float*)U, c->D * m, (const float*)X_or_null, c->D * c->V, c->partial_hsum, c->norm_counter, out)),
                    (norms_kernel<double><<<grid, 256, 0, st>>>((const double*)L, (int64_t)c->k * m, (const double*)U, c->D * m, (const double*)X_or_null, c->D * c->V, c->partial_hsum, c->norm_counter, out)));

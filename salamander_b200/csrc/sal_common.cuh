@@ -121,7 +121,7 @@ int sal_launch_corrnmf_signature_scalings_finish(sal_ctx* c, const double* sums,
 int sal_launch_corrnmf_sample_embeddings(sal_ctx* c, const void* auxT, const void* a, const void* b, int b_is_matrix, const void* L,
                                          void* U, int m, double variance, int maxiter, cudaStream_t st);
 int sal_launch_corrnmf_signature_embeddings(sal_ctx* c, const void* auxT, const void* a, const void* b, void* L, const void* U, int m,
-                                            double variance, cudaStream_t st);
+                                            double variance, int sig_begin, int sig_count, cudaStream_t st);
 int sal_launch_corrnmf_norms(sal_ctx* c, const void* L, const void* U, int m, const void* X_or_null, double* out, cudaStream_t st);
 
 // ---- small-problem persistent kernel (klnmf_small.cu) ----------------------------------------------------

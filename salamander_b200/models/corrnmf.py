@@ -29,40 +29,59 @@ from .signature_nmf import SignatureNMF
 
 
 class CorrState:
-    """Device-resident state: X [D][V], W [k][V], a [k], b [D], L [k][m], U [D][m], H / auxT [D][k]."""
+    """Device-resident state: X [D][V], W [k][V], a [k], b [D], L [k][m], U [D][m], H / auxT [D][k].
 
-    def __init__(self, model: "CorrNMF"):
+    Several GPUs: samples are sharded by contiguous row blocks -- X, b, U, H, aux are this rank's rows,
+    W, a, L and the variance are replicated.  Sample-side updates are local; the W numerator, the two k-vectors of the
+    signature scalings, sum |U|^2 and the log-likelihood are summed over ranks (NCCL all-reduce of a few KB); for the
+    signature embeddings the per-sample inputs (aux, b, U) are all-gathered and every rank runs the Newton-CG of ITS
+    share of the signatures on all samples, so that step is divided over the GPUs by signature instead of by sample and
+    needs no collective inside the solver."""
+
+    def __init__(self, model: "CorrNMF", allow_shard: bool = True):
         dev = model._resolved_device()
         dt = model.dtype
-        if _dist.world()[1] > 1:
-            raise NotImplementedError(
-                "CorrNMF on several GPUs is not built yet: the signature-embedding Newton-CG needs an all-reduce per "
-                "objective / gradient / Hessian evaluation (SURVEY.md 8(e))."
-            )
+        self.rank, self.world = (0, 1) if getattr(model, "replica", False) else _dist.world()
+        if self.world > 1 and not allow_shard:
+            raise NotImplementedError("MultimodalCorrNMF on several GPUs is not built yet (CorrNMFDet is).")
         model.transfer_bytes = {"h2d": 0, "d2h": 0}
         self.model, self.device, self.dtype = model, dev, dt
         X = np.asarray(model.adata.X)
-        self.D, self.V = X.shape
+        self.D_total, self.V = X.shape
+        self.lo, self.hi = _dist.shard_bounds(self.D_total, self.world, self.rank)
+        self.D = self.hi - self.lo
         self.k, self.m = int(model.n_signatures), int(model.dim_embeddings)
         self.ws = Workspace(self.V, self.D, self.k, dt, dev, math="fma")
+        # the gathered problem of the signature embeddings (all samples) has its own handle
+        self.ws_full = Workspace(self.V, self.D_total, self.k, dt, dev, math="fma") if self.world > 1 else self.ws
         self.lib = self.ws.lib
         if self.m > self.lib.sal_corrnmf_max_dim():
             raise NotImplementedError(f"dim_embeddings > {self.lib.sal_corrnmf_max_dim()} is not supported by the device kernels.")
         up = self.upload
-        self.X = up(X)
+        rows = slice(self.lo, self.hi)
+        self.X = up(X[rows])
         if model._clip_on_device:
             changed = torch.zeros(1, dtype=torch.int64, device=dev)
             self.ws.clip_counts(self.X, changed)
+            self.allreduce(changed)
             if int(changed.item()) > 0:
-                model.adata.X = self.download(self.X)
+                model.adata.X = self.rows_to_host(self.X)
             model._clip_on_device = False
         asig, adata = model.asignatures, model.adata
-        self.W = up(np.asarray(asig.X, dtype=np.float64))
-        self.a = up(np.asarray(asig.obs["scalings"].values, dtype=np.float64))
-        self.L = up(np.asarray(asig.obsm["embeddings"], dtype=np.float64))
-        self.b = up(np.asarray(adata.obs["scalings"].values, dtype=np.float64))
-        self.U = up(np.asarray(adata.obsm["embeddings"], dtype=np.float64))
-        self.H = up(np.asarray(adata.obsm["exposures"], dtype=np.float64)) if "exposures" in adata.obsm else torch.empty((self.D, self.k), dtype=dt, device=dev)
+
+        def host(arr):  # replicas must start bit-identical whatever the host initialisation did
+            arr = np.asarray(arr, dtype=np.float64)
+            return _dist.broadcast_numpy(arr, dev) if self.world > 1 else arr
+
+        self.W = up(host(asig.X))
+        self.a = up(host(asig.obs["scalings"].values))
+        self.L = up(host(asig.obsm["embeddings"]))
+        self.b = up(host(adata.obs["scalings"].values)[rows])
+        self.U = up(host(adata.obsm["embeddings"])[rows])
+        if "exposures" in adata.obsm:
+            self.H = up(host(adata.obsm["exposures"])[rows])
+        else:
+            self.H = torch.empty((self.D, self.k), dtype=dt, device=dev)
         self.auxT = torch.empty((self.D, self.k), dtype=dt, device=dev)
         self.Wnum = torch.empty((self.k, self.V), dtype=dt, device=dev)
         self.xsum = torch.empty(self.D, dtype=dt, device=dev)
@@ -71,6 +90,25 @@ class CorrState:
         self.obj = torch.zeros(1, dtype=torch.float64, device=dev)
         self.call("sal_row_sums", self.X, self.xsum)
         self.lgamma_sum = None  # sum lnGamma(1 + x), constant of the ELBO, computed at the first objective
+
+    # -- ranks -----------------------------------------------------------------------------------
+    def allreduce(self, t: torch.Tensor) -> torch.Tensor:
+        if self.world > 1:
+            _dist.allreduce_sum_(t)
+        return t
+
+    def rows_to_host(self, local: torch.Tensor) -> np.ndarray:
+        """Per-sample device rows -> host array over all samples (all-gather when sharded)."""
+        return self.download(_dist.gather_rows(local, self.D_total) if self.world > 1 else local)
+
+    def norms_all(self, with_lgamma: bool) -> list[float]:
+        """[sum L^2, sum U^2 over all samples, sum lnGamma(1 + X) over all samples]"""
+        self.call("sal_corrnmf_norms", self.L, self.U, self.m, self.X if with_lgamma else None, self.norms)
+        if self.world > 1:
+            if self.rank != 0:
+                self.norms[0] = 0.0  # L is replicated: count it once
+            self.allreduce(self.norms)
+        return self.norms.tolist()
 
     # -- plumbing ------------------------------------------------------------------------------
     def upload(self, host) -> torch.Tensor:
@@ -83,7 +121,7 @@ class CorrState:
         self.model.transfer_bytes["d2h"] += out.nbytes
         return out
 
-    def call(self, name: str, *args) -> None:
+    def call(self, name: str, *args, ws: Workspace | None = None) -> None:
         """Call ``name(handle, *args, stream)``: tensors become device pointers, ints / floats pass through."""
         conv = []
         for x in args:
@@ -94,9 +132,11 @@ class CorrState:
             else:
                 conv.append(x)
         stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-        _lib.check(getattr(self.lib, name)(self.ws._h, *conv, stream), name)
+        _lib.check(getattr(self.lib, name)((ws or self.ws)._h, *conv, stream), name)
 
     def close(self) -> None:
+        if self.ws_full is not self.ws:
+            self.ws_full.close()
         self.ws.close()
 
 
@@ -132,9 +172,9 @@ class CorrNMF(SignatureNMF):
         self.asignatures.X = st.download(st.W)
         self.asignatures.obs["scalings"] = st.download(st.a)
         self.asignatures.obsm["embeddings"] = st.download(st.L)
-        self.adata.obs["scalings"] = st.download(st.b)
-        self.adata.obsm["embeddings"] = st.download(st.U)
-        self.adata.obsm["exposures"] = st.download(st.H)
+        self.adata.obs["scalings"] = st.rows_to_host(st.b)
+        self.adata.obsm["embeddings"] = st.rows_to_host(st.U)
+        self.adata.obsm["exposures"] = st.rows_to_host(st.H)
 
     # ---- reference corrnmf.py:66-98 --------------------------------------------------------------
     def compute_exposures(self) -> None:
@@ -146,23 +186,23 @@ class CorrNMF(SignatureNMF):
             st.call("sal_corrnmf_exposures", st.a, st.b, st.L, st.U, st.m, st.H)
             out = torch.empty(st.D, dtype=st.dtype, device=st.device)
             st.ws.klnmf_pass(st.X, st.W, st.H, PASS_SAMPLEWISE, per_sample=out)
-            self.adata.obs["reconstruction_error"] = st.download(out)
+            self.adata.obs["reconstruction_error"] = st.rows_to_host(out)
 
     def objective_function(self, penalize_sample_embeddings: bool = True) -> float:
         """The evidence lower bound with the exposures as they are stored (reference corrnmf.py:86-98 ->
         _utils_corrnmf.py:55-100): Poisson log-likelihood minus the Gaussian priors of the embeddings."""
         with self._resident() as st:
             st.ws.klnmf_pass(st.X, st.W, st.H, PASS_POISSON, objective=st.obj)
+            st.allreduce(st.obj)
             need_lgamma = st.lgamma_sum is None
-            st.call("sal_corrnmf_norms", st.L, st.U, st.m, st.X if need_lgamma else None, st.norms)
-            vals = torch.cat([st.obj, st.norms]).tolist()
+            norms = st.norms_all(need_lgamma)
             if need_lgamma:
-                st.lgamma_sum = vals[3]
-            llh, sumL2, sumU2 = vals[0] - st.lgamma_sum, vals[1], vals[2]
+                st.lgamma_sum = norms[2]
+            llh, sumL2, sumU2 = float(st.obj.item()) - st.lgamma_sum, norms[0], norms[1]
             var, m = float(self.variance), st.m
             elbo = llh - 0.5 * m * st.k * np.log(2 * np.pi * var) - sumL2 / (2 * var)
             if penalize_sample_embeddings:
-                elbo -= 0.5 * m * st.D * np.log(2 * np.pi * var) + sumU2 / (2 * var)
+                elbo -= 0.5 * m * st.D_total * np.log(2 * np.pi * var) + sumU2 / (2 * var)
             return float(elbo)
 
     # ---- initialisation (reference corrnmf.py:104-136) -------------------------------------------
@@ -184,11 +224,12 @@ class CorrNMFDet(CorrNMF):
         """aux (and the raw W numerator) in one pass over X; returned as the (k, D) host array the reference uses."""
         with self._resident() as st:
             st.ws.klnmf_pass(st.X, st.W, st.H, PASS_UPDATE_H | PASS_WNUM | PASS_NOCLIP, H_out=st.auxT, Wnum=st.Wnum)
-            return None if self._in_fit else st.download(st.auxT).T
+            st.allreduce(st.Wnum)
+            return None if self._in_fit else st.rows_to_host(st.auxT).T
 
     def _aux_to_device(self, st, aux) -> None:
-        if aux is not None:
-            st.auxT = st.upload(np.asarray(aux, dtype=np.float64).T)
+        if aux is not None:  # (k, n_samples) host array over ALL samples, like the reference's
+            st.auxT = st.upload(np.asarray(aux, dtype=np.float64).T[st.lo : st.hi])
 
     def update_sample_scalings(self, given_parameters: dict[str, Any] | None = None) -> None:
         if given_parameters and "sample_scalings" in given_parameters:
@@ -202,15 +243,15 @@ class CorrNMFDet(CorrNMF):
         with self._resident() as st:
             self._aux_to_device(st, aux)
             st.call("sal_corrnmf_signature_scalings_sums", st.auxT, st.b, st.L, st.U, st.m, st.sums)
+            st.allreduce(st.sums)
             st.call("sal_corrnmf_signature_scalings_finish", st.sums, st.a)
 
     def update_variance(self, given_parameters: dict[str, Any] | None = None) -> None:
         if given_parameters and "variance" in given_parameters:
             return
         with self._resident() as st:
-            st.call("sal_corrnmf_norms", st.L, st.U, st.m, None, st.norms)
-            sumL2, sumU2 = st.norms[:2].tolist()
-            self.variance = float(np.clip((sumL2 + sumU2) / ((st.k + st.D) * st.m), _lib_eps(), None))
+            sumL2, sumU2 = st.norms_all(False)[:2]
+            self.variance = float(np.clip((sumL2 + sumU2) / ((st.k + st.D_total) * st.m), _lib_eps(), None))
 
     def update_signatures(self, given_parameters: dict[str, Any] | None = None) -> None:
         """update_W with the exposures as stored; only the non-given signatures are clipped (reference :71-86)."""
@@ -218,12 +259,27 @@ class CorrNMFDet(CorrNMF):
         with self._resident() as st:
             if not self._in_fit:  # standalone call: the numerator has to be computed first
                 st.ws.klnmf_pass(st.X, st.W, st.H, PASS_WNUM, Wnum=st.Wnum)
+                st.allreduce(st.Wnum)
             st.ws.w_epilogue(st.W, st.Wnum, n_given, False, st.W)
 
     def update_signature_embeddings(self, aux=None) -> None:
         with self._resident() as st:
             self._aux_to_device(st, aux)
-            st.call("sal_corrnmf_signature_embeddings", st.auxT, st.a, st.b, st.L, st.U, st.m, float(self.variance))
+            if st.world == 1:
+                st.call("sal_corrnmf_signature_embeddings", st.auxT, st.a, st.b, st.L, st.U, st.m, float(self.variance))
+                return
+            # every rank: all samples' aux / scalings / embeddings, Newton-CG for its share of the signatures; the rows
+            # of L are then exchanged by summing arrays that are zero outside the owner's rows (exact)
+            aux_all, b_all, U_all = (_dist.gather_rows(t, st.D_total) for t in (st.auxT, st.b, st.U))
+            j0, j1 = _dist.shard_bounds(st.k, st.world, st.rank)
+            st.call(
+                "sal_corrnmf_signature_embeddings_range", aux_all, st.a, b_all, st.L, U_all, st.m, float(self.variance),
+                j0, j1 - j0, ws=st.ws_full,
+            )
+            L_new = torch.zeros_like(st.L)
+            L_new[j0:j1] = st.L[j0:j1]
+            st.allreduce(L_new)
+            st.L.copy_(L_new)
 
     def update_sample_embeddings(self, aux=None) -> None:
         with self._resident() as st:

@@ -33,6 +33,7 @@ class _ModView:
         self.n_signatures, self.dim_embeddings = k, parent.dim_embeddings
         self.dtype, self._clip_on_device = parent.dtype, False
         self.transfer_bytes = parent.transfer_bytes
+        self.replica = getattr(parent, "replica", False)
         self._parent = parent
 
     def _resolved_device(self):
@@ -46,7 +47,7 @@ class _MMState:
         for mod_name, k in zip(model.mod_names, model.ns_signatures):
             adata = model.mdata[mod_name]
             adata.obsm["embeddings"] = U_host  # CorrState uploads it; replaced by the shared tensor below
-            st = CorrState(_ModView(model, mod_name, k))
+            st = CorrState(_ModView(model, mod_name, k), allow_shard=False)
             del adata.obsm["embeddings"]
             self.mods[mod_name] = st
         first = next(iter(self.mods.values()))

@@ -165,3 +165,38 @@ def test_iterations_match_the_oracle_on_pcawg():
     assert np.allclose(model.asignatures.obsm["embeddings"], L, rtol=1e-5, atol=1e-8)
     assert np.allclose(model.adata.obsm["embeddings"], U, rtol=1e-5, atol=1e-7)
     assert np.isclose(model.variance, var, rtol=1e-7)
+
+
+def test_iterations_match_the_oracle_on_synthetic_counts():
+    """6 whole iterations (k = 5, dim 4) on 2,000 synthetic samples of the bench generator: larger counts and far more
+    samples per signature problem than PCAWG, so the line searches and the CG inner loops take more varied paths."""
+    import bench
+
+    k, m, n_iter, D = 5, 4, 6, 2000
+    X0 = bench.synth_rows(0, D, k).astype(np.float64)
+    model = sal.models.CorrNMFDet(n_signatures=k, dim_embeddings=m, init_method="random", min_iterations=n_iter, max_iterations=n_iter,
+                                  conv_test_freq=1)
+    adata = AnnData(X0)
+    model._setup_adata(adata)
+    np.random.seed(0)
+    model._initialize(None, {"seed": 0})
+    X = np.asarray(adata.X, dtype=float)
+    W = np.array(model.asignatures.X)
+    a, b = np.array(model.asignatures.obs["scalings"].values, dtype=float), np.array(adata.obs["scalings"].values, dtype=float)
+    L, U = np.array(model.asignatures.obsm["embeddings"]), np.array(adata.obsm["embeddings"])
+    var = float(model.variance)
+    hist_ref = []
+    for _ in range(n_iter):
+        W, a, b, L, U, var, H = oracle.update_parameters(X, W, a, b, L, U, var)
+        hist_ref.append(oracle.elbo(X, W, H, L, U, var))
+    with model._resident():
+        model._in_fit = True
+        hist = []
+        for _ in range(n_iter):
+            model._update_parameters(None)
+            hist.append(model.objective_function())
+        model._in_fit = False
+    assert np.allclose(hist, hist_ref, rtol=1e-8), (hist, hist_ref)
+    assert np.allclose(model.asignatures.obsm["embeddings"], L, rtol=1e-5, atol=1e-8)
+    assert np.allclose(model.adata.obsm["embeddings"], U, rtol=1e-5, atol=1e-7)
+    assert np.isclose(model.variance, var, rtol=1e-7)
