@@ -16,6 +16,8 @@
 // All arithmetic is float64 whatever the handle's storage dtype.
 #include <cooperative_groups.h>
 
+#include <stdlib.h>
+
 #include "sal_common.cuh"
 
 namespace cg = cooperative_groups;
@@ -663,6 +665,10 @@ int sal_launch_corrnmf_signature_embeddings(sal_ctx* c, const void* auxT, const 
             cudaOccupancyMaxActiveClusters(&n_active, fn, &cfg) == cudaSuccess && n_active >= sig_count)
             csize = 16;
         (void)cudaGetLastError();  // a refused query is not an error of this call: fall back to the portable size
+    }
+    if (const char* e = getenv("SAL_B200_SIG_CLUSTER")) {  // diagnostics: force the cluster size (1, 8 or 16)
+        const int forced = atoi(e);
+        if (forced == 1 || forced == 8 || (forced == 16 && csize == 16)) csize = forced;
     }
     attr.val.clusterDim.x = csize;
     cfg.gridDim = dim3(sig_count * csize);
