@@ -1,7 +1,7 @@
 // Fused KL-NMF pass, tensor-core flavour (tcgen05 kind::tf32, fp32 accumulation in TMEM).
 //
 // Same contract as the FMA pass (klnmf_pass.cu; reference update_WH / update_H / update_W /
-// kl_divergence, models/_utils_klnmf.py:11-55, 164-361) for fp32 handles, V = 96, k % 4 == 0, no
+// kl_divergence, models/_utils_klnmf.py:11-55, 164-361) for fp32 handles, V = 96, any k <= 32, no
 // per-sample weights.  The three thin contractions of one 128-sample tile run on the 5th-gen tensor
 // cores; X is streamed from HBM exactly once by TMA and the quotient never leaves the SM:
 //
@@ -86,12 +86,14 @@ __host__ __device__ inline Plan make_plan(int k, int KP8) {
 
 struct TcParams {
     const float* W;
+    const float* H_in;
     float* H_out;
     float* partial_wnum;
     double* partial_obj;
     float* dbg;  // optional diagnostics buffer (see sal_set_debug_buffer)
     int64_t D;
     int k, flags, n_tiles;
+    int generic_k;  // k % 4 != 0: H rows are not 16-byte multiples, see the exposure loads below
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------
@@ -132,6 +134,21 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
         "l"(map), "r"(bar), "r"(c0), "r"(c1)
         : "memory");
+}
+
+// 3-D variants: with k % 4 != 0 a row of H (k floats) is not a multiple of 16 bytes, which a 2-D tensor map cannot
+// describe.  A tile of 128 samples is still one contiguous run of 128 k floats, so H is viewed as [tile][k][128]
+// (inner dimension 128 floats, then k with a 512-byte stride, then the tile) and box {128, k, 1} moves exactly that run.
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(src), "r"(c0),
+                 "r"(c1), "r"(c2)
+                 : "memory");
 }
 
 // one lane of a converged warp (the address arithmetic around it stays warp-uniform, i.e. in uniform registers)
@@ -198,6 +215,11 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
 __device__ __forceinline__ float4 lds128(uint32_t a) {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float lds32(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
     return v;
 }
 __device__ __forceinline__ void sts128(uint32_t a, float4 v) {
@@ -381,14 +403,34 @@ klnmf_pass_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
 
     if (warp == 0) {
         // ================= TMA producer =================
-        if (lane == 0) {
-            for (int i = 0; i < n_my; ++i) {
-                const int st = i % S, hs = i % NH;
-                const int d0 = ((int)blockIdx.x + i * (int)gridDim.x) * TILE;
+        // Lane 0 issues the bulk copies.  The last, partial tile of a generic-k problem cannot go through the 3-D map
+        // (it would describe memory past the end of H): the whole warp copies its rows with plain loads and zero-fills
+        // the rest of the slot, then lane 0 completes the slot's barrier phase with a plain arrive.
+        const bool gk = p.generic_k != 0;
+        for (int i = 0; i < n_my; ++i) {
+            const int st = i % S, hs = i % NH;
+            const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+            const int d0 = tile * TILE;
+            const bool ragged = gk && (int64_t)d0 + TILE > p.D;  // warp-uniform
+            if (lane == 0) {
                 mbar_wait(bar_hempty + 8 * hs, ((i / NH) & 1) ^ 1);
-                mbar_arrive_expect_tx(bar_hfull + 8 * hs, (uint32_t)(TILE * k * 4));
-                tma_load_2d(sHraw + hs * q.hraw, &mapH, bar_hfull + 8 * hs, 0, d0);
-                if (i < n_pre) continue;  // requested in the prologue
+                if (!ragged) {
+                    mbar_arrive_expect_tx(bar_hfull + 8 * hs, (uint32_t)(TILE * k * 4));
+                    if (gk)
+                        tma_load_3d(sHraw + hs * q.hraw, &mapH, bar_hfull + 8 * hs, 0, 0, tile);
+                    else
+                        tma_load_2d(sHraw + hs * q.hraw, &mapH, bar_hfull + 8 * hs, 0, d0);
+                }
+            }
+            if (ragged) {
+                __syncwarp();
+                const int n = (int)(p.D - d0) * k;
+                const float* src = p.H_in + (size_t)d0 * k;
+                for (int e = lane; e < TILE * k; e += 32) sts32(sHraw + hs * q.hraw + e * 4, e < n ? __ldcg(src + e) : 0.f);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_hfull + 8 * hs);
+            }
+            if (lane == 0 && i >= n_pre) {  // the first n_pre X tiles were requested in the prologue
                 mbar_wait(bar_empty + 8 * st, ((i / S) & 1) ^ 1);
                 stamp(p.dbg, tl, 3, i, 0);
                 mbar_arrive_expect_tx(bar_full + 8 * st, XSTAGE_BYTES);
@@ -466,19 +508,33 @@ klnmf_pass_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
     } else if (warp == 3) {
         // ================= exposure store =================
         // The epilogue leaves the updated exposures of tile i in raw-H slot i % NH; one thread streams them out with
-        // a TMA store (rows beyond D are clipped by the tensor map) and hands the slot back to the producer.
-        if (lane == 0) {
-            for (int i = 0; i < n_my; ++i) {
-                const int hs = i % NH;
-                mbar_wait(bar_hout + 8 * hs, (i / NH) & 1);
-                if (DO_R && do_h) {
-                    tma_store_2d(&mapHout, sHraw + hs * q.hraw, 0, ((int)blockIdx.x + i * (int)gridDim.x) * TILE);
+        // a TMA store (rows beyond D are clipped by the 2-D tensor map; the partial last tile of a generic-k problem is
+        // written by the whole warp with plain stores) and hands the slot back to the producer.
+        const bool gk = p.generic_k != 0;
+        for (int i = 0; i < n_my; ++i) {
+            const int hs = i % NH;
+            const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+            const int d0 = tile * TILE;
+            const bool ragged = gk && (int64_t)d0 + TILE > p.D;  // warp-uniform
+            if (lane == 0) mbar_wait(bar_hout + 8 * hs, (i / NH) & 1);
+            if (DO_R && do_h) {
+                if (ragged) {
+                    __syncwarp();
+                    const int n = (int)(p.D - d0) * k;
+                    float* dst = p.H_out + (size_t)d0 * k;
+                    for (int e = lane; e < n; e += 32) dst[e] = lds32(sHraw + hs * q.hraw + e * 4);
+                    __syncwarp();
+                } else if (lane == 0) {
+                    if (gk)
+                        tma_store_3d(&mapHout, sHraw + hs * q.hraw, 0, 0, tile);
+                    else
+                        tma_store_2d(&mapHout, sHraw + hs * q.hraw, 0, d0);
                     tma_store_commit_and_wait_read();
                 }
-                mbar_arrive(bar_hempty + 8 * hs);
             }
-            tma_store_wait_all();
+            if (lane == 0) mbar_arrive(bar_hempty + 8 * hs);
         }
+        if (lane == 0) tma_store_wait_all();
     } else if (warp >= 4) {
         // ================= epilogue warpgroups =================
         const int g = (warp - 4) >> 2, qw = warp & 3;
@@ -494,13 +550,21 @@ klnmf_pass_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
             mbar_wait(bar_hfull + 8 * hs, (i / NH) & 1);
             const uint32_t hrow = sHraw + hs * q.hraw + s * (k * 4);
             const uint32_t th = tmem + lane_off + (b ? TM_H1 : TM_H0);
+            if (p.generic_k) {  // rows are not 16-byte aligned: scalar loads
+#pragma unroll
+                for (int j = 0; j < KP8; ++j) h[j] = j < k ? lds32(hrow + j * 4) : 0.f;
+            } else {
+#pragma unroll
+                for (int j = 0; j < KP8; j += 8) {
+                    float4 t0 = make_float4(0.f, 0.f, 0.f, 0.f), t1 = t0;
+                    if (j < k) t0 = lds128(hrow + j * 4);
+                    if (j + 4 < k) t1 = lds128(hrow + j * 4 + 16);
+                    h[j] = t0.x, h[j + 1] = t0.y, h[j + 2] = t0.z, h[j + 3] = t0.w;
+                    h[j + 4] = t1.x, h[j + 5] = t1.y, h[j + 6] = t1.z, h[j + 7] = t1.w;
+                }
+            }
 #pragma unroll
             for (int j = 0; j < KP8; j += 8) {
-                float4 t0 = make_float4(0.f, 0.f, 0.f, 0.f), t1 = t0;
-                if (j < k) t0 = lds128(hrow + j * 4);
-                if (j + 4 < k) t1 = lds128(hrow + j * 4 + 16);
-                h[j] = t0.x, h[j + 1] = t0.y, h[j + 2] = t0.z, h[j + 3] = t0.w;
-                h[j + 4] = t1.x, h[j + 5] = t1.y, h[j + 6] = t1.z, h[j + 7] = t1.w;
                 uint32_t hi[8], lo[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
@@ -605,6 +669,11 @@ klnmf_pass_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
                 }
                 {
                     const uint32_t orow = sHraw + (i % NH) * q.hraw + s * (k * 4);
+                    if (p.generic_k) {
+#pragma unroll
+                        for (int j = 0; j < KP8; ++j)
+                            if (j < k) sts32(orow + j * 4, fmaxf(h[j] * __uint_as_float(v[j]), eps));
+                    } else
 #pragma unroll
                     for (int j = 0; j < KP8; j += 4)
                         if (j < k) {
@@ -698,6 +767,28 @@ int encode_2d(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t rows, 
     return 0;
 }
 
+// H [D][k] with k % 4 != 0 as [full tiles][k][128]: see tma_load_3d.  Only whole tiles are described.
+int encode_h3d(CUtensorMap* map, const void* ptr, int k, int64_t D) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) {
+        sal_set_error("cuTensorMapEncodeTiled is not available from this driver");
+        return SAL_EUNSUPPORTED;
+    }
+    const int64_t n_full = D / TILE;
+    const cuuint64_t dims[3] = {(cuuint64_t)TILE, (cuuint64_t)k, (cuuint64_t)(n_full > 0 ? n_full : 1)};
+    const cuuint64_t strides[2] = {(cuuint64_t)TILE * 4, (cuuint64_t)TILE * k * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)TILE, (cuuint32_t)k, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        sal_set_error("cuTensorMapEncodeTiled (3-D exposure view) failed with CUresult %d (k %d, D %lld)", (int)r, k, (long long)D);
+        return SAL_EINVAL;
+    }
+    return 0;
+}
+
 template <int KP8, bool DO_R, bool DO_KL>
 int launch_tc_v(sal_ctx* c, const PassArgs& a, cudaStream_t st) {
     const Plan q = make_plan(c->k, KP8);
@@ -713,11 +804,17 @@ int launch_tc_v(sal_ctx* c, const PassArgs& a, cudaStream_t st) {
     }
     CUtensorMap mapX, mapH, mapHout;
     if (int e = encode_2d(&mapX, a.X, VT, (uint64_t)c->D, 32, TILE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return e;
-    if (int e = encode_2d(&mapH, a.H_in, (uint64_t)c->k, (uint64_t)c->D, (uint32_t)c->k, TILE, CU_TENSOR_MAP_SWIZZLE_NONE)) return e;
     const void* hout = (a.flags & SAL_PASS_UPDATE_H) ? a.H_out : a.H_in;
-    if (int e = encode_2d(&mapHout, hout, (uint64_t)c->k, (uint64_t)c->D, (uint32_t)c->k, TILE, CU_TENSOR_MAP_SWIZZLE_NONE)) return e;
+    const bool generic_k = (c->k & 3) != 0;
+    if (generic_k) {
+        if (int e = encode_h3d(&mapH, a.H_in, c->k, c->D)) return e;
+        if (int e = encode_h3d(&mapHout, hout, c->k, c->D)) return e;
+    } else {
+        if (int e = encode_2d(&mapH, a.H_in, (uint64_t)c->k, (uint64_t)c->D, (uint32_t)c->k, TILE, CU_TENSOR_MAP_SWIZZLE_NONE)) return e;
+        if (int e = encode_2d(&mapHout, hout, (uint64_t)c->k, (uint64_t)c->D, (uint32_t)c->k, TILE, CU_TENSOR_MAP_SWIZZLE_NONE)) return e;
+    }
     TcParams p;
-    p.W = (const float*)a.W, p.H_out = (float*)a.H_out;
+    p.W = (const float*)a.W, p.H_in = (const float*)a.H_in, p.H_out = (float*)hout, p.generic_k = generic_k ? 1 : 0;
     p.partial_wnum = (float*)c->partial_wnum, p.partial_obj = c->partial_obj;
     p.dbg = (float*)c->dbg;
     p.D = c->D, p.k = c->k, p.flags = a.flags;
@@ -742,7 +839,7 @@ int launch_tc(sal_ctx* c, const PassArgs& a, cudaStream_t st) {
 
 bool sal_pass_tf32_supported(const sal_ctx* c, const PassArgs& a) {
     const int allowed = SAL_PASS_UPDATE_H | SAL_PASS_WNUM | SAL_PASS_OBJECTIVE;
-    if (c->dtype != SAL_F32 || c->V != VT || c->k % 4 != 0 || c->k > 32) return false;
+    if (c->dtype != SAL_F32 || c->V != VT || c->k > 32) return false;
     if ((a.flags & ~allowed) || a.w_kl || a.w_lhalf || a.h_scale) return false;
     if (((uintptr_t)a.X | (uintptr_t)a.H_in | (uintptr_t)a.H_out) & 15) return false;
     if (c->D >= (int64_t)1 << 31) return false;

@@ -75,7 +75,12 @@ def test_stage_by_stage_first_tile():
     assert e_w < RTOL, f"G3 / numerator wrong: {e_w}"
 
 
-@pytest.mark.parametrize("D,k", [(1, 4), (127, 8), (128, 12), (129, 16), (1000, 20), (4097, 24), (777, 28), (50_000, 32), (200_003, 20)])
+@pytest.mark.parametrize(
+    "D,k",
+    [(1, 4), (127, 8), (128, 12), (129, 16), (1000, 20), (4097, 24), (777, 28), (50_000, 32), (200_003, 20)]
+    # k % 4 != 0: exposure tiles go through the 3-D tensor-map view, the partial last tile through plain loads / stores
+    + [(1, 1), (100, 2), (128, 3), (129, 5), (1000, 7), (4096, 9), (4097, 13), (20_000, 17), (50_001, 21), (777, 26), (100_003, 30), (256, 31)],
+)
 def test_pass_matches_float64(D, k):
     dev = torch.device("cuda:0")
     X, W, H = _problem(D, k, 100 + k, dev)
@@ -114,14 +119,38 @@ def test_deterministic_and_in_place():
     ws.close()
 
 
-def test_unsupported_shapes_use_the_exact_kernels():
-    """k % 4 != 0, V != 96 or weights: the call still succeeds (exact FMA kernels) -- never a CPU fallback."""
+def test_generic_k_deterministic_and_in_place():
+    """k % 4 != 0 with a partial last tile: repeatable bit for bit, and H_out may alias H_in."""
     dev = torch.device("cuda:0")
-    X, W, H = _problem(500, 5, 3, dev)
-    Hout, Wnum, _, _ = _run(X, W, H, PASS_UPDATE_H | PASS_WNUM)
+    D, k = 70_001, 11
+    X, W, H = _problem(D, k, 9, dev)
+    a = _run(X, W, H, PASS_UPDATE_H | PASS_WNUM)
+    b = _run(X, W, H, PASS_UPDATE_H | PASS_WNUM)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    ws = Workspace(96, D, k, torch.float32, dev, math="tf32_always")
+    Hf = H.float().contiguous()
+    Wnum = torch.empty((k, 96), dtype=torch.float32, device=dev)
+    ws.klnmf_pass(X.float().contiguous(), W.float().contiguous(), Hf, PASS_UPDATE_H | PASS_WNUM, H_out=Hf, Wnum=Wnum)
+    torch.cuda.synchronize()
+    assert torch.equal(Hf.double(), a[0]) and torch.equal(Wnum.double(), a[1])
+    ws.close()
+
+
+def test_unsupported_shapes_use_the_exact_kernels():
+    """Weights (and V != 96): the call still succeeds through the exact FMA kernels -- never a CPU fallback."""
+    dev = torch.device("cuda:0")
+    X, W, H = _problem(500, 8, 3, dev)
+    w_kl = torch.rand(500, dtype=torch.float64, device=dev) + 0.5
+    ws = Workspace(96, 500, 8, torch.float32, dev, math="tf32_always")
+    Hout = torch.empty((500, 8), dtype=torch.float32, device=dev)
+    Wnum = torch.empty((8, 96), dtype=torch.float32, device=dev)
+    ws.klnmf_pass(X.float().contiguous(), W.float().contiguous(), H.float().contiguous(), PASS_UPDATE_H | PASS_WNUM, H_out=Hout,
+                  Wnum=Wnum, w_kl=w_kl.float())
+    torch.cuda.synchronize()
+    ws.close()
     R = X / (H @ W)
-    assert _relerr(Hout, (H * (R @ W.T)).clamp_min(EPS)) < 3e-5
-    assert _relerr(Wnum, H.T @ R) < 3e-5
+    assert _relerr(Hout.double(), (H * (R @ W.T)).clamp_min(EPS)) < 3e-5
+    assert _relerr(Wnum.double(), H.T @ (R * w_kl[:, None])) < 3e-5
 
 
 def _pcawg():
