@@ -21,7 +21,7 @@ import pandas as pd
 from .._anndata import AnnData
 from .._device import resolve_device, resolve_dtype
 from ..initialization.methods import _INIT_METHODS
-from ..utils import EPSILON, type_checker, value_checker
+from ..utils import EPSILON, match_signatures_pair, type_checker, value_checker
 
 
 class SignatureNMF(ABC):
@@ -94,6 +94,27 @@ class SignatureNMF(ABC):
         """Exposures as an (n_samples, n_signatures) frame, i.e. H^T."""
         assert "exposures" in self.adata.obsm, "Accessing the exposures requires fitting the NMF model."
         return pd.DataFrame(self.adata.obsm["exposures"], index=self.sample_names, columns=self.signature_names)
+
+    def compute_reconstruction(self) -> None:
+        """``adata.obsm['X_reconstructed'] = exposures @ signatures`` (reference signature_nmf.py:221-224); a host
+        product of the downloaded factors, outside the fitting path."""
+        self.adata.obsm["X_reconstructed"] = self.adata.obsm["exposures"] @ self.asignatures.X
+
+    @property
+    def data_reconstructed(self) -> pd.DataFrame:
+        if "X_reconstructed" not in self.adata.obsm:
+            self.compute_reconstruction()
+        return pd.DataFrame(self.adata.obsm["X_reconstructed"], index=self.sample_names, columns=self.mutation_types)
+
+    def reorder(self, asignatures_other: AnnData, metric: str = "cosine", keep_names: bool = False) -> None:
+        """Reorder signatures and exposure columns to match another collection of signatures
+        (reference signature_nmf.py:387-406) -- how restarts and the models of a sweep are aligned."""
+        names = self.asignatures.obs_names
+        order = match_signatures_pair(asignatures_other.to_df(), self.asignatures.to_df(), metric=metric)
+        self.asignatures = self.asignatures[order, :].copy()
+        self.adata.obsm["exposures"] = self.adata.obsm["exposures"][:, order]
+        if not keep_names:
+            self.asignatures.obs_names = names
 
     @abstractmethod
     def compute_reconstruction_errors(self) -> None:

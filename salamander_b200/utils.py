@@ -50,3 +50,22 @@ def normalize_WH(W: np.ndarray, H: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
     """
     s = np.sum(W, axis=0)
     return W / s, H * s[:, None]
+
+
+def match_to_catalog(signatures: pd.DataFrame, catalog: pd.DataFrame, metric: str = "cosine") -> pd.DataFrame:
+    """For every signature the closest catalog entry under ``metric`` (reference utils.py:161-170)."""
+    from sklearn.metrics import pairwise_distances
+
+    similarity = 1 - pairwise_distances(signatures, catalog, metric=metric)
+    return catalog.iloc[[int(np.argmax(row)) for row in similarity]]
+
+
+def match_signatures_pair(signatures1: pd.DataFrame, signatures2: pd.DataFrame, metric: str = "cosine") -> np.ndarray:
+    """Indices that reorder ``signatures2`` so that the summed pairwise distance to ``signatures1`` is minimal
+    (assignment problem; reference utils.py:173-192).  Used to align restarts and models of a k-sweep."""
+    from scipy.optimize import linear_sum_assignment
+    from sklearn.metrics import pairwise_distances
+
+    if signatures1.shape != signatures2.shape:
+        raise ValueError("The signatures must be of the same shape.")
+    return linear_sum_assignment(pairwise_distances(signatures1, signatures2, metric=metric))[1]

@@ -141,3 +141,38 @@ def test_shard_bounds_cover_everything():
             assert all(a[1] == b[0] for a, b in zip(edges, edges[1:]))
             sizes = [hi - lo for lo, hi in edges]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_signature_matching_and_reorder():
+    """match_signatures_pair / match_to_catalog / SignatureNMF.reorder / data_reconstructed (reference utils.py:161-192,
+    signature_nmf.py:221-235, 387-406): host-side helpers that align restarts and sweep models."""
+    import pandas as pd
+
+    from salamander_b200 import AnnData
+    from salamander_b200.models import KLNMF
+    from salamander_b200.utils import match_signatures_pair, match_to_catalog
+
+    rng = np.random.default_rng(0)
+    W = rng.dirichlet(np.ones(96), size=5)
+    perm = np.array([3, 0, 4, 1, 2])
+    noisy = W[perm] * (1 + 0.01 * rng.standard_normal((5, 96)))
+    s1 = pd.DataFrame(W, index=[f"a{i}" for i in range(5)])
+    s2 = pd.DataFrame(noisy, index=[f"b{i}" for i in range(5)])
+    order = match_signatures_pair(s1, s2)
+    assert np.array_equal(perm[order], np.arange(5))
+    assert list(match_to_catalog(s2, s1).index) == [f"a{i}" for i in perm]
+    with pytest.raises(ValueError):
+        match_signatures_pair(s1, s2.iloc[:4])
+
+    model = KLNMF(n_signatures=5)
+    H = rng.random((7, 5))
+    model.adata = AnnData(pd.DataFrame(H @ noisy))
+    model.adata.obsm["exposures"] = H.copy()
+    model.asignatures = AnnData(pd.DataFrame(noisy, index=list(s2.index)))
+    recon = model.data_reconstructed
+    assert np.allclose(recon.values, H @ noisy)
+    model.reorder(AnnData(s1))
+    assert np.allclose(model.asignatures.X, noisy[order])
+    assert np.allclose(model.adata.obsm["exposures"], H[:, order])
+    assert list(model.asignatures.obs_names) == list(s2.index)  # names stay in place unless keep_names
+    assert np.allclose(model.adata.obsm["exposures"] @ model.asignatures.X, H @ noisy)
