@@ -45,12 +45,18 @@ def initialize_mat(data_mat, n_signatures, method="nndsvd", given_signatures_mat
     ``H <- clip(H * colsum(W))``, is left to the device right after the upload (sal_scale_clip_rows); the
     column sums are returned in ``_defer['exposure_scale']`` and the exposures are handed back untouched."""
     value_checker("method", method, _INIT_METHODS)
+    init_device = kwargs.pop("_init_device", None)  # internal: torch.device for the NNDSVD family (models' init_device)
     if method == "custom":
         sigs, expo = init_custom(data_mat, n_signatures, **kwargs)
     elif method == "flat":
         sigs, expo = init_flat(data_mat, n_signatures)
     elif method in ("nndsvd", "nndsvda", "nndsvdar"):
-        sigs, expo = init_nndsvd(data_mat, n_signatures, method=method, **kwargs)
+        if init_device is not None:
+            from .device_nndsvd import init_nndsvd_device
+
+            sigs, expo = init_nndsvd_device(data_mat, n_signatures, method=method, device=init_device, **kwargs)
+        else:
+            sigs, expo = init_nndsvd(data_mat, n_signatures, method=method, **kwargs)
     elif method == "random":
         sigs, expo = init_random(data_mat, n_signatures, **kwargs)
     else:

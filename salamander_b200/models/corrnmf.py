@@ -208,6 +208,7 @@ class CorrNMF(SignatureNMF):
     # ---- initialisation (reference corrnmf.py:104-136) -------------------------------------------
     def _initialize(self, given_parameters=None, init_kwargs=None) -> None:
         init_kwargs = {} if init_kwargs is None else init_kwargs.copy()
+        init_kwargs.update(self._init_device_kwargs())
         self.asignatures, self.variance = initialize_corrnmf(
             self.adata, self.n_signatures, self.dim_embeddings, self.init_method, given_parameters, **init_kwargs
         )

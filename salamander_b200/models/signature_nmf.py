@@ -41,8 +41,10 @@ class SignatureNMF(ABC):
         math: str = "fma",
         shard_input: bool = True,
         replica: bool = False,
+        init_device: bool | str = False,
     ):
         value_checker("init_method", init_method, _INIT_METHODS)
+        value_checker("init_device", init_device, (True, False, "auto"))
         value_checker("math", math, ("fma", "tf32", "tf32_always"))
         self.n_signatures = n_signatures
         self.init_method = init_method
@@ -58,6 +60,9 @@ class SignatureNMF(ABC):
         self.shard_input = bool(shard_input)
         # True: ignore an initialised process group -- this model is an independent replica (restarts / k-sweep)
         self.replica = bool(replica)
+        # NNDSVD initialisations with the SVD on the device (initialization/device_nndsvd.py): True, False (scikit-learn's
+        # randomized SVD on the host, as the reference) or "auto" (device for matrices of at least 2^22 entries)
+        self.init_device = init_device
         self.transfer_bytes = {"h2d": 0, "d2h": 0}  # host<->device bytes of the last fit / update
 
         # data / fitting dependent attributes (reference signature_nmf.py:182-185)
@@ -182,6 +187,14 @@ class SignatureNMF(ABC):
 
     def _resolved_device(self):
         return resolve_device(self.device)
+
+    def _init_device_kwargs(self) -> dict[str, Any]:
+        """``{'_init_device': torch.device}`` when this fit's NNDSVD initialisation is to run on the device."""
+        if self.init_method not in ("nndsvd", "nndsvda", "nndsvdar") or self.init_device is False:
+            return {}
+        if self.init_device == "auto" and np.asarray(self.adata.X).size < self._DEVICE_CLIP_MIN_SIZE:
+            return {}
+        return {"_init_device": self._resolved_device()}
 
     class _Resident:
         """``with self._resident():`` -- run a block with state in HBM; outside ``fit`` this uploads before

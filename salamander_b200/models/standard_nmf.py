@@ -126,6 +126,7 @@ class StandardNMF(SignatureNMF):
     def _initialize(self, given_parameters=None, init_kwargs=None) -> None:
         """Initialise signatures and exposures; given signatures are kept fixed (reference :32-58)."""
         init_kwargs = {} if init_kwargs is None else init_kwargs.copy()
+        init_kwargs.update(self._init_device_kwargs())
         defer: dict[str, Any] = {}
         self.asignatures = initialize_standard_nmf(
             self.adata, self.n_signatures, self.init_method, given_parameters, _defer=defer, **init_kwargs

@@ -176,3 +176,21 @@ def test_signature_matching_and_reorder():
     assert np.allclose(model.adata.obsm["exposures"], H[:, order])
     assert list(model.asignatures.obs_names) == list(s2.index)  # names stay in place unless keep_names
     assert np.allclose(model.adata.obsm["exposures"] @ model.asignatures.X, H @ noisy)
+
+
+def test_gram_nndsvd_arithmetic_on_the_cpu_device():
+    """The NNDSVD construction of initialization/device_nndsvd.py, run with torch's CPU device so that the arithmetic is
+    checked without a GPU: equal to scikit-learn's route (what the reference calls, initialization/methods.py:69-86)."""
+    import pandas as pd
+    import torch
+
+    from salamander_b200.initialization.device_nndsvd import init_nndsvd_device
+    from salamander_b200.initialization.methods import init_nndsvd
+
+    X = pd.read_csv(os.path.join(ROOT, "salamander_b200", "data", "pcawg_breast_sbs.csv"), index_col=0).T.values.astype(float)
+    for method in ("nndsvd", "nndsvdar"):
+        s_ref, e_ref = init_nndsvd(X, 5, method=method, seed=2)
+        s_dev, e_dev = init_nndsvd_device(X, 5, method=method, seed=2, device=torch.device("cpu"))
+        assert np.array_equal(s_ref == 0, s_dev == 0) and np.array_equal(e_ref == 0, e_dev == 0)
+        assert np.abs(s_dev - s_ref).max() <= 1e-10 * np.abs(s_ref).max()
+        assert np.abs(e_dev - e_ref).max() <= 1e-10 * np.abs(e_ref).max()
