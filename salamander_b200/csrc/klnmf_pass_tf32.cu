@@ -87,6 +87,7 @@ __host__ __device__ inline Plan make_plan(int k, int KP8) {
 struct TcParams {
     const float* W;
     const float* H_in;
+    const float* h_scale;  // MvNMF line-search trial: exposures are read as clip(H * h_scale) and written back like that
     float* H_out;
     float* partial_wnum;
     double* partial_obj;
@@ -517,7 +518,7 @@ klnmf_pass_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
             const int d0 = tile * TILE;
             const bool ragged = gk && (int64_t)d0 + TILE > p.D;  // warp-uniform
             if (lane == 0) mbar_wait(bar_hout + 8 * hs, (i / NH) & 1);
-            if (DO_R && do_h) {
+            if (do_h) {
                 if (ragged) {
                     __syncwarp();
                     const int n = (int)(p.D - d0) * k;
@@ -562,6 +563,12 @@ klnmf_pass_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
                     h[j] = t0.x, h[j + 1] = t0.y, h[j + 2] = t0.z, h[j + 3] = t0.w;
                     h[j + 4] = t1.x, h[j + 5] = t1.y, h[j + 6] = t1.z, h[j + 7] = t1.w;
                 }
+            }
+            if (p.h_scale) {  // normalize_WH folded into the read (reference utils.py:155-158 as used by mvnmf.py:80-88)
+                const bool row_valid = (int64_t)((int)blockIdx.x + i * (int)gridDim.x) * TILE + s < p.D;
+#pragma unroll
+                for (int j = 0; j < KP8; ++j)
+                    if (j < k) h[j] = row_valid ? fmaxf(h[j] * __ldg(p.h_scale + j), eps) : 0.f;
             }
 #pragma unroll
             for (int j = 0; j < KP8; j += 8) {
@@ -688,6 +695,13 @@ klnmf_pass_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
                 }
                 tc_fence_before();
             }
+            if (!DO_R && do_h) {  // rescale mode: the exposures as they were read (scaled, clipped) are the output
+                const uint32_t orow = sHraw + (i % NH) * q.hraw + s * (k * 4);
+#pragma unroll
+                for (int j = 0; j < KP8; ++j)
+                    if (j < k) sts32(orow + j * 4, h[j]);
+                fence_proxy_async();
+            }
             mbar_arrive(bar_hout + 8 * (i % NH));  // slot i % NH: staged output ready (or simply no longer needed)
 #pragma unroll
             for (int j = 0; j < KP8; ++j) h[j] = hn[j];
@@ -726,6 +740,40 @@ klnmf_pass_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TM_COLS) : "memory");
     }
     stamp(p.dbg, p.dbg != nullptr && blockIdx.x == 1 && tid == 0, 3, 0, 3);
+}
+
+// Column sums of H [D][k] (SAL_PASS_HSUM, MvNMF's rowsums_H): block b owns a contiguous run of rows and reads it as a flat
+// array; HSUM_THREADS is rounded down to a multiple of k by masking, so a thread always meets the same column.  The
+// partials land in partial_hsum[b][SAL_KMAX]; the reduction kernel adds the blocks in order.
+constexpr int HSUM_THREADS = 256;
+__global__ void __launch_bounds__(HSUM_THREADS) hsum_partials_kernel(const float* H, int64_t D, int k, double* partial_hsum) {
+    __shared__ double s_acc[HSUM_THREADS];
+    const int tid = threadIdx.x;
+    const int active = (HSUM_THREADS / k) * k;
+    const int64_t rows_per = (D + gridDim.x - 1) / gridDim.x;
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per, r1 = r0 + rows_per < D ? r0 + rows_per : D;
+    double acc = 0.0;
+    if (tid < active && r0 < r1) {
+        const float* base = H + r0 * k;
+        const int64_t n = (r1 - r0) * k;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        int64_t e = tid;
+        for (; e + 3 * (int64_t)active < n; e += 4 * (int64_t)active) {
+            a0 += __ldg(base + e), a1 += __ldg(base + e + active), a2 += __ldg(base + e + 2 * (int64_t)active);
+            a3 += __ldg(base + e + 3 * (int64_t)active);
+            if (((e / active) & 63) == 60) acc += (double)((a0 + a1) + (a2 + a3)), a0 = a1 = a2 = a3 = 0.f;  // keep fp32 runs short
+        }
+        for (; e < n; e += active) a0 += __ldg(base + e);
+        acc += (double)((a0 + a1) + (a2 + a3));
+    }
+    s_acc[tid] = acc;
+    __syncthreads();
+    if (tid < SAL_KMAX) {
+        double t = 0.0;
+        if (tid < k)
+            for (int u = tid; u < active; u += k) t += s_acc[u];
+        partial_hsum[(size_t)blockIdx.x * SAL_KMAX + tid] = t;
+    }
 }
 
 // ---- host side --------------------------------------------------------------------------------------
@@ -815,6 +863,7 @@ int launch_tc_v(sal_ctx* c, const PassArgs& a, cudaStream_t st) {
     }
     TcParams p;
     p.W = (const float*)a.W, p.H_in = (const float*)a.H_in, p.H_out = (float*)hout, p.generic_k = generic_k ? 1 : 0;
+    p.h_scale = (const float*)a.h_scale;
     p.partial_wnum = (float*)c->partial_wnum, p.partial_obj = c->partial_obj;
     p.dbg = (float*)c->dbg;
     p.D = c->D, p.k = c->k, p.flags = a.flags;
@@ -824,12 +873,18 @@ int launch_tc_v(sal_ctx* c, const PassArgs& a, cudaStream_t st) {
     SAL_CUDA(sal_launch_pdl(klnmf_pass_tc_kernel<KP8, DO_R, DO_KL>, grid, NTHREADS, q.total, st, mapX, mapH, mapHout, p));
     if (int e = sal_timing_end(c, a.flags, st)) return e;
     c->launches++;
+    if (a.flags & SAL_PASS_HSUM) {  // column sums of H_in: per-block partials in the layout the reduction kernel expects
+        hsum_partials_kernel<<<grid, HSUM_THREADS, 0, st>>>((const float*)a.H_in, c->D, c->k, c->partial_hsum);
+        SAL_CUDA(cudaGetLastError());
+        c->launches++;
+    }
     return sal_launch_pass_reduce(c, a, grid, st);
 }
 
 template <int KP8>
 int launch_tc(sal_ctx* c, const PassArgs& a, cudaStream_t st) {
-    const bool r = a.flags & (SAL_PASS_UPDATE_H | SAL_PASS_WNUM), kl = a.flags & SAL_PASS_OBJECTIVE;
+    // with h_scale, UPDATE_H means "write the rescaled exposures" (no multiplicative update): the objective-only pipeline
+    const bool r = !a.h_scale && (a.flags & (SAL_PASS_UPDATE_H | SAL_PASS_WNUM)), kl = a.flags & SAL_PASS_OBJECTIVE;
     if (r && !kl) return launch_tc_v<KP8, true, false>(c, a, st);
     if (!r && kl) return launch_tc_v<KP8, false, true>(c, a, st);
     return launch_tc_v<KP8, true, true>(c, a, st);
@@ -838,9 +893,11 @@ int launch_tc(sal_ctx* c, const PassArgs& a, cudaStream_t st) {
 }  // namespace
 
 bool sal_pass_tf32_supported(const sal_ctx* c, const PassArgs& a) {
-    const int allowed = SAL_PASS_UPDATE_H | SAL_PASS_WNUM | SAL_PASS_OBJECTIVE;
+    const int allowed = SAL_PASS_UPDATE_H | SAL_PASS_WNUM | SAL_PASS_OBJECTIVE | SAL_PASS_HSUM;
     if (c->dtype != SAL_F32 || c->V != VT || c->k > 32) return false;
-    if ((a.flags & ~allowed) || a.w_kl || a.w_lhalf || a.h_scale) return false;
+    if ((a.flags & ~allowed) || a.w_kl || a.w_lhalf) return false;
+    if ((a.flags & SAL_PASS_HSUM) && !(a.flags & ~SAL_PASS_HSUM)) return false;  // row sums alone: not worth this kernel
+    if (a.h_scale && a.flags != (SAL_PASS_UPDATE_H | SAL_PASS_OBJECTIVE)) return false;  // the MvNMF trial pass only
     if (((uintptr_t)a.X | (uintptr_t)a.H_in | (uintptr_t)a.H_out) & 15) return false;
     if (c->D >= (int64_t)1 << 31) return false;
     if (c->math != SAL_MATH_TF32_ALWAYS && c->D < SAL_TF32_MIN_SAMPLES) return false;

@@ -204,3 +204,55 @@ def test_large_fit_tf32_matches_float64_fit():
     assert np.max(np.abs(ha[:n] - hb[:n]) / ha[:n]) < 1e-4
     assert abs(ha[-1] - hb[-1]) / ha[-1] < 1e-4
     assert cos.min() >= 0.9999
+
+
+@pytest.mark.parametrize("D,k", [(5000, 8), (70_001, 20), (33_333, 7)])
+def test_mvnmf_pass_variants(D, k):
+    """The two passes only MvNMF issues: WNUM | HSUM | OBJECTIVE (numerator, row sums of H, previous objective) and the
+    line-search trial OBJECTIVE | UPDATE_H with h_scale (H is read as clip(H * scale), written back like that)."""
+    from salamander_b200._device import PASS_HSUM
+
+    dev = torch.device("cuda:0")
+    X, W, H = _problem(D, k, 50 + k, dev)
+    ws = Workspace(96, D, k, torch.float32, dev, math="tf32_always")
+    Xf, Wf, Hf = X.float().contiguous(), W.float().contiguous(), H.float().contiguous()
+    Wnum = torch.empty((k, 96), dtype=torch.float32, device=dev)
+    hsum = torch.empty(k, dtype=torch.float32, device=dev)
+    obj = torch.zeros(1, dtype=torch.float64, device=dev)
+    n0 = ws.launches
+    ws.klnmf_pass(Xf, Wf, Hf, PASS_WNUM | PASS_HSUM | PASS_OBJECTIVE, Wnum=Wnum, hsum=hsum, objective=obj)
+    torch.cuda.synchronize()
+    assert ws.launches - n0 == 3  # tensor-core pass, row-sum partials, reduction -- not the FMA kernel (2 launches)
+    R = X / (H @ W)
+    kl_ref = float((X * torch.log(R) - X + H @ W).sum())
+    assert _relerr(Wnum.double(), H.T @ R) < RTOL
+    assert _relerr(hsum.double(), H.sum(0)) < 1e-5
+    assert abs(float(obj.item()) - kl_ref) / abs(kl_ref) < RTOL
+
+    scale = torch.rand(k, dtype=torch.float64, device=dev) + 0.5
+    Hs = (H * scale).clamp_min(EPS)
+    Hout = torch.full_like(Hf, -1.0)
+    ws.klnmf_pass(Xf, Wf, Hf, PASS_OBJECTIVE | PASS_UPDATE_H, H_out=Hout, h_scale=scale.float(), objective=obj)
+    torch.cuda.synchronize()
+    ws.close()
+    Rs = X / (Hs @ W)
+    kl_s = float((X * torch.log(Rs) - X + Hs @ W).sum())
+    assert _relerr(Hout.double(), Hs) < 1e-6
+    assert abs(float(obj.item()) - kl_s) / abs(kl_s) < 2e-5
+
+
+def test_mvnmf_fit_on_tensor_cores_tracks_float64():
+    """MvNMF with math='tf32' (all three passes of an iteration on the tensor-core kernel) against the float64 fit from
+    the same start: final penalised objective within 1e-4, signatures cosine >= 0.9999."""
+    import bench
+
+    X = bench.synth_rows(0, 20_000, 8).astype(np.float64)
+    out = {}
+    for name, kw in {"f64": dict(dtype="float64"), "tf32": dict(dtype="float32", math="tf32")}.items():
+        m = sal.models.MvNMF(n_signatures=8, init_method="random", lam=1.0, delta=1.0, min_iterations=150, max_iterations=150, **kw)
+        m.fit(AnnData(X.copy()), init_kwargs={"seed": 3})
+        out[name] = (m.history["objective_function"][-1], np.array(m.asignatures.X))
+    (o64, W64), (o32, W32) = out["f64"], out["tf32"]
+    assert abs(o32 - o64) / abs(o64) < 1e-4, (o32, o64)
+    cos = np.sum(W64 * W32, axis=1) / (np.linalg.norm(W64, axis=1) * np.linalg.norm(W32, axis=1))
+    assert cos.min() >= 0.9999, cos
