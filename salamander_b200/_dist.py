@@ -76,3 +76,21 @@ class PeerExchange:
         self.state = torch.tensor([1, 0], dtype=torch.int32, device=device)
         torch.cuda.synchronize(device)
         dist.barrier()  # every buffer is zeroed and mapped before anybody publishes into it
+
+
+_PEER_EXCHANGES: dict[tuple[int, int], PeerExchange] = {}
+
+
+def shared_peer_exchange(nbytes: int, device: torch.device) -> PeerExchange:
+    """One exchange buffer per process and device, created collectively at first use and kept: allocating symmetric
+    memory and the rendezvous cost ~100 ms, a fit at 8 GPUs lasts about as long.  Safe to share between consecutive fits:
+    the sequence number that tags every word lives with the buffer and only ever increases, so words left over from an
+    earlier fit (even one with another k, i.e. another layout) can never carry a tag a later update waits for.  Every
+    rank must ask for the same size in the same order (callers pass the size for the largest supported k)."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), world()[1])
+    px = _PEER_EXCHANGES.get(key)
+    if px is None or px.nbytes < nbytes:
+        px = PeerExchange(nbytes, device)
+        px.nbytes = nbytes
+        _PEER_EXCHANGES[key] = px
+    return px

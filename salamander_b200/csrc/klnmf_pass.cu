@@ -395,12 +395,15 @@ struct P2PExchange {
     int n_ranks, rank;
 };
 
-__device__ __forceinline__ void st_ll(uint2* p, unsigned int payload, unsigned int tag) {
-    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(payload), "r"(tag) : "memory");
+// both tagged words of a double in one 16-byte access {lo, tag, hi, tag}: half the NVLink transactions and a warp writes
+// 512 contiguous bytes; each 8-byte half still validates itself, so a torn 16-byte store cannot be mistaken for a whole one
+constexpr int P2P_BATCH = 8;
+__device__ __forceinline__ void st_ll4(uint4* p, unsigned int lo, unsigned int hi, unsigned int tag) {
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(lo), "r"(tag), "r"(hi), "r"(tag) : "memory");
 }
-__device__ __forceinline__ uint2 ld_ll(const uint2* p) {
-    uint2 v;
-    asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+__device__ __forceinline__ uint4 ld_ll4(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
     return v;
 }
 
@@ -450,25 +453,39 @@ __global__ void __launch_bounds__(FIN_THREADS) klnmf_finish_p2p_kernel(const T* 
                 const unsigned long long bits = (unsigned long long)__double_as_longlong(s);
                 for (int r = 0; r < x.n_ranks; ++r) {
                     if (r == x.rank) continue;
-                    uint2* dst = reinterpret_cast<uint2*>(x.peers[r]) + (row + ((size_t)x.rank * (k + 1) + j) * VP + v) * 2;
-                    st_ll(dst, (unsigned int)bits, seq);
-                    st_ll(dst + 1, (unsigned int)(bits >> 32), seq);
+                    uint4* dst = reinterpret_cast<uint4*>(x.peers[r]) + (row + ((size_t)x.rank * (k + 1) + j) * VP + v);
+                    st_ll4(dst, (unsigned int)bits, (unsigned int)(bits >> 32), seq);
                 }
-                // (3) collect the peers' words from the local buffer, in rank order
-                const uint2* mine = reinterpret_cast<const uint2*>(x.peers[x.rank]);
-                for (int r = 0; r < x.n_ranks; ++r) {
-                    if (r == x.rank) {
-                        total += s;
-                        continue;
-                    }
-                    const uint2* src = mine + (row + ((size_t)r * (k + 1) + j) * VP + v) * 2;
-                    uint2 lo, hi;
+                // (3) collect the peers' words from the local buffer.  The loads of up to P2P_BATCH ranks are issued
+                // together (one L2 round trip per batch instead of one per rank); the sum is still taken in rank order.
+                const uint4* mine = reinterpret_cast<const uint4*>(x.peers[x.rank]);
+                for (int r0 = 0; r0 < x.n_ranks; r0 += P2P_BATCH) {
+                    uint4 w[P2P_BATCH];
                     long long spins = 0;
+                    bool ready;
                     do {
-                        lo = ld_ll(src), hi = ld_ll(src + 1);
+#pragma unroll
+                        for (int u = 0; u < P2P_BATCH; ++u) {
+                            const int r = r0 + u;
+                            if (r < x.n_ranks && r != x.rank) w[u] = ld_ll4(mine + (row + ((size_t)r * (k + 1) + j) * VP + v));
+                        }
+                        ready = true;
+#pragma unroll
+                        for (int u = 0; u < P2P_BATCH; ++u) {
+                            const int r = r0 + u;
+                            if (r < x.n_ranks && r != x.rank) ready = ready && w[u].y == seq && w[u].w == seq;
+                        }
                         if (++spins > 2000000000LL) __trap();  // a peer died: fail loudly instead of hanging the box
-                    } while (lo.y != seq || hi.y != seq);
-                    total += __longlong_as_double((long long)(((unsigned long long)hi.x << 32) | lo.x));
+                    } while (!ready);
+#pragma unroll
+                    for (int u = 0; u < P2P_BATCH; ++u) {
+                        const int r = r0 + u;
+                        if (r >= x.n_ranks) break;
+                        if (r == x.rank)
+                            total += s;
+                        else
+                            total += __longlong_as_double((long long)(((unsigned long long)w[u].z << 32) | w[u].x));
+                    }
                 }
             }
             if (is_obj) {

@@ -177,8 +177,8 @@ class KLNMF(StandardNMF):
             return None
         if "peer_exchange" not in st.weights:
             try:
-                nbytes = int(st.ws.lib.sal_p2p_exchange_bytes(st.k, st.world))
-                st.weights["peer_exchange"] = _dist.PeerExchange(nbytes, st.device)
+                nbytes = int(st.ws.lib.sal_p2p_exchange_bytes(32, st.world))  # sized for the largest k: shared by all fits
+                st.weights["peer_exchange"] = _dist.shared_peer_exchange(nbytes, st.device)
             except Exception as exc:  # pragma: no cover - depends on the system
                 if self.allreduce == "p2p":
                     raise
