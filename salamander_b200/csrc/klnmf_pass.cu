@@ -397,7 +397,6 @@ struct P2PExchange {
 
 // both tagged words of a double in one 16-byte access {lo, tag, hi, tag}: half the NVLink transactions and a warp writes
 // 512 contiguous bytes; each 8-byte half still validates itself, so a torn 16-byte store cannot be mistaken for a whole one
-constexpr int P2P_BATCH = 8;
 __device__ __forceinline__ void st_ll4(uint4* p, unsigned int lo, unsigned int hi, unsigned int tag) {
     asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(lo), "r"(tag), "r"(hi), "r"(tag) : "memory");
 }
@@ -444,50 +443,45 @@ __global__ void __launch_bounds__(FIN_THREADS) klnmf_finish_p2p_kernel(const T* 
             s = 0.0;
             for (int w = 0; w < FIN_THREADS / 32; ++w) s += s_obj[w];
         }
-        if (part == 0) {  // 96 threads carry on (named barrier 1 for the epilogue's block sum)
-            const int nv = is_obj ? 1 : V;
-            const size_t row = ((size_t)slot * x.n_ranks) * (k + 1) * VP;  // start of recv[slot]
-            double total = 0.0;
-            if (v < nv) {
-                // (2) push to every peer: two tagged 8-byte words per double
-                const unsigned long long bits = (unsigned long long)__double_as_longlong(s);
-                for (int r = 0; r < x.n_ranks; ++r) {
-                    if (r == x.rank) continue;
+        // (2) + (3): the exchange is spread over the eight thread groups ("parts") of the block -- group p pushes this
+        // rank's value to peers p, p + 8, ... and collects the words of ranks p, p + 8, ..., one remote store and one
+        // polled load per thread instead of a serial loop over the peers; group 0 then adds the contributions in rank order.
+        const int nv = is_obj ? 1 : V;
+        const size_t row = ((size_t)slot * x.n_ranks) * (k + 1) * VP;  // start of recv[slot]
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(s);
+        if (v < nv)
+            for (int r = part; r < x.n_ranks; r += FIN_PARTS)
+                if (r != x.rank) {
                     uint4* dst = reinterpret_cast<uint4*>(x.peers[r]) + (row + ((size_t)x.rank * (k + 1) + j) * VP + v);
                     st_ll4(dst, (unsigned int)bits, (unsigned int)(bits >> 32), seq);
                 }
-                // (3) collect the peers' words from the local buffer.  The loads of up to P2P_BATCH ranks are issued
-                // together (one L2 round trip per batch instead of one per rank); the sum is still taken in rank order.
-                const uint4* mine = reinterpret_cast<const uint4*>(x.peers[x.rank]);
-                for (int r0 = 0; r0 < x.n_ranks; r0 += P2P_BATCH) {
-                    uint4 w[P2P_BATCH];
+        double total = 0.0;
+        const uint4* mine = reinterpret_cast<const uint4*>(x.peers[x.rank]);
+        __syncthreads();  // every thread has formed s from s_part / s_obj; s_part is reused for the received values
+        for (int r0 = 0; r0 < x.n_ranks; r0 += FIN_PARTS) {
+            const int r = r0 + part;
+            double val = 0.0;
+            if (v < nv && r < x.n_ranks) {
+                if (r == x.rank) {
+                    val = s;
+                } else {
+                    const uint4* src = mine + (row + ((size_t)r * (k + 1) + j) * VP + v);
+                    uint4 w;
                     long long spins = 0;
-                    bool ready;
                     do {
-#pragma unroll
-                        for (int u = 0; u < P2P_BATCH; ++u) {
-                            const int r = r0 + u;
-                            if (r < x.n_ranks && r != x.rank) w[u] = ld_ll4(mine + (row + ((size_t)r * (k + 1) + j) * VP + v));
-                        }
-                        ready = true;
-#pragma unroll
-                        for (int u = 0; u < P2P_BATCH; ++u) {
-                            const int r = r0 + u;
-                            if (r < x.n_ranks && r != x.rank) ready = ready && w[u].y == seq && w[u].w == seq;
-                        }
+                        w = ld_ll4(src);
                         if (++spins > 2000000000LL) __trap();  // a peer died: fail loudly instead of hanging the box
-                    } while (!ready);
-#pragma unroll
-                    for (int u = 0; u < P2P_BATCH; ++u) {
-                        const int r = r0 + u;
-                        if (r >= x.n_ranks) break;
-                        if (r == x.rank)
-                            total += s;
-                        else
-                            total += __longlong_as_double((long long)(((unsigned long long)w[u].z << 32) | w[u].x));
-                    }
+                    } while (w.y != seq || w.w != seq);
+                    val = __longlong_as_double((long long)(((unsigned long long)w.z << 32) | w.x));
                 }
             }
+            s_part[part][v] = val;
+            __syncthreads();
+            if (part == 0 && v < nv)
+                for (int u = 0; u < FIN_PARTS && r0 + u < x.n_ranks; ++u) total += s_part[u][v];
+            __syncthreads();
+        }
+        if (part == 0) {  // 96 threads carry on (named barrier 1 for the epilogue's block sum)
             if (is_obj) {
                 if (v == 0) *objective = total;
             } else {
