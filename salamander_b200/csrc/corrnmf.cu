@@ -100,35 +100,32 @@ __device__ void dcstep(StepState& s, double fp, double dp, double stpmin, double
 
 // ---------------------------------------------------------------------------------------------------------
 // Newton-CG.  Problem P provides (collectively for the calling threads; every thread gets the same values):
-//   double f(const double* x);  void grad(const double* x, double* g);  void hess(const double* x, double* A /*m*m*/)
-//   double f_grad(const double* x, double* g)   -- f and grad of the same point in one sweep (one exp per term)
-// SciPy evaluates fprime(xk) again at the top of every Newton iteration; xk is the accepted line-search point, whose
-// gradient DCSRCH has just used, so it is kept instead of recomputed (same function, same point).
+//   double f_grad_hess(const double* x, double* g, double* A)   -- all three at the same point in ONE sweep over the
+//                                                                  terms (one exp per term, one collective reduction)
+// SciPy evaluates fprime(xk) and fhess(xk) again at the top of every Newton iteration; xk is the line-search point that
+// was just accepted, where DCSRCH has already asked for f and f'.  Every trial therefore evaluates f, f' and the Hessian
+// together and the accepted trial's values are kept: one sweep per trial, none at the top of the iteration (same
+// functions at the same points, so the iterates are SciPy's).
 // ---------------------------------------------------------------------------------------------------------
 template <class P>
 __device__ void newton_cg(P& prob, double* x, int m, int maxiter) {
     const double ftol = 1e-4, gtol = 0.9, ls_xtol = 1e-14, stpmin = 1e-8, stpmax = 50.0, eps64 = 2.220446049250313e-16;
     const double xtol = m * 1e-5;
     const int cg_maxiter = 20 * m;
-    double b[MAXM], xs[MAXM], ri[MAXM], ps[MAXM], Ap[MAXM], xt[MAXM], gt[MAXM], A[MAXM * MAXM];
-    double old_fval = prob.f(x), old_old_fval = 0.0;
+    double b[MAXM], xs[MAXM], ri[MAXM], ps[MAXM], Ap[MAXM], xt[MAXM], gt[MAXM], gl[MAXM];
+    double Abuf0[MAXM * MAXM], Abuf1[MAXM * MAXM];
+    double *A = Abuf0, *Al = Abuf1;  // Hessian at the current point / at the trial point (swapped on acceptance)
+    double old_fval = prob.f_grad_hess(x, gt, A), old_old_fval = 0.0;
     bool have_old_old = false;
     double update_l1 = 1.7976931348623157e308;
     int k = 0;
-    bool have_grad = false;
-    double gkeep[MAXM];
     while (update_l1 > xtol) {
         if (k >= maxiter) break;
-        if (have_grad)
-            for (int i = 0; i < m; ++i) gt[i] = gkeep[i];
-        else
-            prob.grad(x, gt);
         double maggrad = 0.0;
         for (int i = 0; i < m; ++i) b[i] = -gt[i], maggrad += fabs(b[i]);
         const double termcond = fmin(0.5, sqrt(maggrad)) * maggrad;
         double dri0 = 0.0;
         for (int i = 0; i < m; ++i) xs[i] = 0.0, ri[i] = -b[i], ps[i] = b[i], dri0 += ri[i] * ri[i];
-        prob.hess(x, A);
         int it = 0;
         bool failed = true;
         for (int k2 = 0; k2 < cg_maxiter; ++k2) {
@@ -183,8 +180,7 @@ __device__ void newton_cg(P& prob, double* x, int m, int maxiter) {
             double stmin = 0.0, stmax = alpha1 + 4.0 * alpha1;
             for (int ls = 0; ls < 99; ++ls) {
                 for (int i = 0; i < m; ++i) xt[i] = x[i] + s.stp * xs[i];
-                double gl[MAXM];
-                const double f = prob.f_grad(xt, gl);
+                const double f = prob.f_grad_hess(xt, gl, Al);
                 double g = 0.0;
                 for (int i = 0; i < m; ++i) g += gl[i] * xs[i];
                 const double ftest = finit + s.stp * gtest;
@@ -196,7 +192,6 @@ __device__ void newton_cg(P& prob, double* x, int m, int maxiter) {
                 if (s.stp == stpmin && (f > ftest || g >= gtest)) warn = true;
                 if (f <= ftest && fabs(g) <= gtol * -ginit) {
                     ok = true, fnew = f, stp_ok = s.stp;
-                    for (int i = 0; i < m; ++i) gkeep[i] = gl[i];
                     break;
                 }
                 if (warn) break;
@@ -229,8 +224,12 @@ __device__ void newton_cg(P& prob, double* x, int m, int maxiter) {
             const double xn = x[i] + stp_ok * xs[i];  // the very expression the trial point was formed with
             update_l1 += fabs(stp_ok * xs[i]);
             x[i] = xn;
+            gt[i] = gl[i];
         }
-        have_grad = true;
+        {
+            double* t = A;
+            A = Al, Al = t;
+        }
         ++k;
     }
 }
@@ -253,28 +252,10 @@ struct SampleProblem {
                              //        modality; per-modality values in multimodal CorrNMF, mmcorrnmf.py:413-419)
     double inv_var;
     int k, m;
-    __device__ double f(const double* x) const {
+    __device__ double f_grad_hess(const double* x, double* g, double* A) const {
         double acc = 0.0, nrm = 0.0;
-        for (int i = 0; i < k; ++i) {
-            double sp = 0.0;
-            for (int j = 0; j < m; ++j) sp += others[i * m + j] * x[j];
-            acc += sp * aux[i] - exp(s_vec[i] + s_others[i] + sp);
-        }
-        for (int j = 0; j < m; ++j) nrm += x[j] * x[j];
-        return -(acc - 0.5 * nrm * inv_var);
-    }
-    __device__ void grad(const double* x, double* g) const {
-        for (int j = 0; j < m; ++j) g[j] = x[j] * inv_var;
-        for (int i = 0; i < k; ++i) {
-            double sp = 0.0;
-            for (int j = 0; j < m; ++j) sp += others[i * m + j] * x[j];
-            const double w = exp(s_vec[i] + s_others[i] + sp) - aux[i];
-            for (int j = 0; j < m; ++j) g[j] += w * others[i * m + j];
-        }
-    }
-    __device__ double f_grad(const double* x, double* g) const {
-        double acc = 0.0, nrm = 0.0;
-        for (int j = 0; j < m; ++j) g[j] = x[j] * inv_var, nrm += x[j] * x[j];
+        for (int j = 0; j < m * m; ++j) A[j] = 0.0;
+        for (int j = 0; j < m; ++j) g[j] = x[j] * inv_var, nrm += x[j] * x[j], A[j * m + j] = inv_var;
         for (int i = 0; i < k; ++i) {
             double sp = 0.0;
             for (int j = 0; j < m; ++j) sp += others[i * m + j] * x[j];
@@ -282,19 +263,10 @@ struct SampleProblem {
             acc += sp * aux[i] - e;
             const double w = e - aux[i];
             for (int j = 0; j < m; ++j) g[j] += w * others[i * m + j];
+            for (int p = 0; p < m; ++p)
+                for (int q = 0; q < m; ++q) A[p * m + q] += e * others[i * m + p] * others[i * m + q];
         }
         return -(acc - 0.5 * nrm * inv_var);
-    }
-    __device__ void hess(const double* x, double* A) const {
-        for (int j = 0; j < m * m; ++j) A[j] = 0.0;
-        for (int j = 0; j < m; ++j) A[j * m + j] = inv_var;
-        for (int i = 0; i < k; ++i) {
-            double sp = 0.0;
-            for (int j = 0; j < m; ++j) sp += others[i * m + j] * x[j];
-            const double w = exp(s_vec[i] + s_others[i] + sp);
-            for (int p = 0; p < m; ++p)
-                for (int q = 0; q < m; ++q) A[p * m + q] += w * others[i * m + p] * others[i * m + q];
-        }
     }
 };
 
@@ -361,56 +333,26 @@ struct SignatureProblem {
             cluster.sync();
         }
     }
-    __device__ double f(const double* x) const {
-        double acc = 0.0;
+    __device__ double f_grad_hess(const double* x, double* g, double* A) const {
+        double v[1 + MAXM + MAXM * MAXM];  // [f | gradient | Hessian]: one collective reduction for all of it
+        const int n = 1 + m + m * m;
+        for (int q = 0; q < n; ++q) v[q] = 0.0;
         for (int64_t d = (int64_t)rank * SIG_THREADS + threadIdx.x; d < D; d += (int64_t)nrank * SIG_THREADS) {
-            double sp = 0.0;
-            for (int q = 0; q < m; ++q) sp += (double)U[d * m + q] * x[q];
-            acc += sp * (double)auxT[d * k + j] - exp(s + (double)b[d] + sp);
-        }
-        reduce(&acc, 1);
-        double nrm = 0.0;
-        for (int q = 0; q < m; ++q) nrm += x[q] * x[q];
-        return -(acc - 0.5 * nrm * inv_var);
-    }
-    __device__ void grad(const double* x, double* g) const {
-        for (int q = 0; q < m; ++q) g[q] = 0.0;
-        for (int64_t d = (int64_t)rank * SIG_THREADS + threadIdx.x; d < D; d += (int64_t)nrank * SIG_THREADS) {
-            double sp = 0.0;
-            for (int q = 0; q < m; ++q) sp += (double)U[d * m + q] * x[q];
-            const double w = exp(s + (double)b[d] + sp) - (double)auxT[d * k + j];
-            for (int q = 0; q < m; ++q) g[q] += w * (double)U[d * m + q];
-        }
-        reduce(g, m);
-        for (int q = 0; q < m; ++q) g[q] += x[q] * inv_var;
-    }
-    __device__ double f_grad(const double* x, double* g) const {
-        double v[1 + MAXM];
-        for (int q = 0; q <= m; ++q) v[q] = 0.0;
-        for (int64_t d = (int64_t)rank * SIG_THREADS + threadIdx.x; d < D; d += (int64_t)nrank * SIG_THREADS) {
-            double sp = 0.0;
-            for (int q = 0; q < m; ++q) sp += (double)U[d * m + q] * x[q];
+            double u[MAXM], sp = 0.0;
+            for (int q = 0; q < m; ++q) u[q] = (double)U[d * m + q], sp += u[q] * x[q];
             const double e = exp(s + (double)b[d] + sp), ax = (double)auxT[d * k + j];
             v[0] += sp * ax - e;
             const double w = e - ax;
-            for (int q = 0; q < m; ++q) v[1 + q] += w * (double)U[d * m + q];
+            for (int q = 0; q < m; ++q) v[1 + q] += w * u[q];
+            for (int p = 0; p < m; ++p)
+                for (int q = 0; q < m; ++q) v[1 + m + p * m + q] += e * u[p] * u[q];
         }
-        reduce(v, 1 + m);
+        reduce(v, n);
         double nrm = 0.0;
         for (int q = 0; q < m; ++q) nrm += x[q] * x[q], g[q] = v[1 + q] + x[q] * inv_var;
-        return -(v[0] - 0.5 * nrm * inv_var);
-    }
-    __device__ void hess(const double* x, double* A) const {
-        for (int q = 0; q < m * m; ++q) A[q] = 0.0;
-        for (int64_t d = (int64_t)rank * SIG_THREADS + threadIdx.x; d < D; d += (int64_t)nrank * SIG_THREADS) {
-            double sp = 0.0;
-            for (int q = 0; q < m; ++q) sp += (double)U[d * m + q] * x[q];
-            const double w = exp(s + (double)b[d] + sp);
-            for (int p = 0; p < m; ++p)
-                for (int q = 0; q < m; ++q) A[p * m + q] += w * (double)U[d * m + p] * (double)U[d * m + q];
-        }
-        reduce(A, m * m);
+        for (int q = 0; q < m * m; ++q) A[q] = v[1 + m + q];
         for (int q = 0; q < m; ++q) A[q * m + q] += inv_var;
+        return -(v[0] - 0.5 * nrm * inv_var);
     }
 };
 
