@@ -306,7 +306,9 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8])
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%8], {%0, %1, %2, %3, %4, %5, %6, %7};" ::SAL_W8(v, 0), "r"(taddr) : "memory");
 }
 
-template <int KP8, bool DO_R, bool DO_KL>
+// GK: k % 4 != 0 (3-D exposure view, scalar staging accesses); HS: MvNMF trial pass (exposures rescaled on the way in and
+// written back).  Both are compile-time: as run-time branches in the per-tile loops they cost the common variant 10 %.
+template <int KP8, bool DO_R, bool DO_KL, bool GK, bool HS>
 __global__ void __launch_bounds__(NTHREADS, 1)
 klnmf_pass_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapH,
                      const __grid_constant__ CUtensorMap mapHout, TcParams p) {
@@ -407,35 +409,52 @@ klnmf_pass_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
         // Lane 0 issues the bulk copies.  The last, partial tile of a generic-k problem cannot go through the 3-D map
         // (it would describe memory past the end of H): the whole warp copies its rows with plain loads and zero-fills
         // the rest of the slot, then lane 0 completes the slot's barrier phase with a plain arrive.
-        const bool gk = p.generic_k != 0;
-        for (int i = 0; i < n_my; ++i) {
-            const int st = i % S, hs = i % NH;
-            const int tile = (int)blockIdx.x + i * (int)gridDim.x;
-            const int d0 = tile * TILE;
-            const bool ragged = gk && (int64_t)d0 + TILE > p.D;  // warp-uniform
+        if (!GK) {
             if (lane == 0) {
-                mbar_wait(bar_hempty + 8 * hs, ((i / NH) & 1) ^ 1);
-                if (!ragged) {
+                for (int i = 0; i < n_my; ++i) {
+                    const int st = i % S, hs = i % NH;
+                    const int d0 = ((int)blockIdx.x + i * (int)gridDim.x) * TILE;
+                    mbar_wait(bar_hempty + 8 * hs, ((i / NH) & 1) ^ 1);
                     mbar_arrive_expect_tx(bar_hfull + 8 * hs, (uint32_t)(TILE * k * 4));
-                    if (gk)
-                        tma_load_3d(sHraw + hs * q.hraw, &mapH, bar_hfull + 8 * hs, 0, 0, tile);
-                    else
-                        tma_load_2d(sHraw + hs * q.hraw, &mapH, bar_hfull + 8 * hs, 0, d0);
+                    tma_load_2d(sHraw + hs * q.hraw, &mapH, bar_hfull + 8 * hs, 0, d0);
+                    if (i < n_pre) continue;  // X tile requested in the prologue
+                    mbar_wait(bar_empty + 8 * st, ((i / S) & 1) ^ 1);
+                    stamp(p.dbg, tl, 3, i, 0);
+                    mbar_arrive_expect_tx(bar_full + 8 * st, XSTAGE_BYTES);
+                    for (int c = 0; c < NBOX; ++c) tma_load_2d(sX + st * XSTAGE_BYTES + c * BOX_BYTES, &mapX, bar_full + 8 * st, c * 32, d0);
                 }
             }
-            if (ragged) {
-                __syncwarp();
-                const int n = (int)(p.D - d0) * k;
-                const float* src = p.H_in + (size_t)d0 * k;
-                for (int e = lane; e < TILE * k; e += 32) sts32(sHraw + hs * q.hraw + e * 4, e < n ? __ldcg(src + e) : 0.f);
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_hfull + 8 * hs);
-            }
-            if (lane == 0 && i >= n_pre) {  // the first n_pre X tiles were requested in the prologue
-                mbar_wait(bar_empty + 8 * st, ((i / S) & 1) ^ 1);
-                stamp(p.dbg, tl, 3, i, 0);
-                mbar_arrive_expect_tx(bar_full + 8 * st, XSTAGE_BYTES);
-                for (int c = 0; c < NBOX; ++c) tma_load_2d(sX + st * XSTAGE_BYTES + c * BOX_BYTES, &mapX, bar_full + 8 * st, c * 32, d0);
+        } else {
+            constexpr bool gk = GK;
+            for (int i = 0; i < n_my; ++i) {
+                const int st = i % S, hs = i % NH;
+                const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+                const int d0 = tile * TILE;
+                const bool ragged = gk && (int64_t)d0 + TILE > p.D;  // warp-uniform
+                if (lane == 0) {
+                    mbar_wait(bar_hempty + 8 * hs, ((i / NH) & 1) ^ 1);
+                    if (!ragged) {
+                        mbar_arrive_expect_tx(bar_hfull + 8 * hs, (uint32_t)(TILE * k * 4));
+                        if (gk)
+                            tma_load_3d(sHraw + hs * q.hraw, &mapH, bar_hfull + 8 * hs, 0, 0, tile);
+                        else
+                            tma_load_2d(sHraw + hs * q.hraw, &mapH, bar_hfull + 8 * hs, 0, d0);
+                    }
+                }
+                if (ragged) {
+                    __syncwarp();
+                    const int n = (int)(p.D - d0) * k;
+                    const float* src = p.H_in + (size_t)d0 * k;
+                    for (int e = lane; e < TILE * k; e += 32) sts32(sHraw + hs * q.hraw + e * 4, e < n ? __ldcg(src + e) : 0.f);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_hfull + 8 * hs);
+                }
+                if (lane == 0 && i >= n_pre) {  // the first n_pre X tiles were requested in the prologue
+                    mbar_wait(bar_empty + 8 * st, ((i / S) & 1) ^ 1);
+                    stamp(p.dbg, tl, 3, i, 0);
+                    mbar_arrive_expect_tx(bar_full + 8 * st, XSTAGE_BYTES);
+                    for (int c = 0; c < NBOX; ++c) tma_load_2d(sX + st * XSTAGE_BYTES + c * BOX_BYTES, &mapX, bar_full + 8 * st, c * 32, d0);
+                }
             }
         }
     } else if (warp == 1) {
@@ -511,31 +530,46 @@ klnmf_pass_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
         // The epilogue leaves the updated exposures of tile i in raw-H slot i % NH; one thread streams them out with
         // a TMA store (rows beyond D are clipped by the 2-D tensor map; the partial last tile of a generic-k problem is
         // written by the whole warp with plain stores) and hands the slot back to the producer.
-        const bool gk = p.generic_k != 0;
-        for (int i = 0; i < n_my; ++i) {
-            const int hs = i % NH;
-            const int tile = (int)blockIdx.x + i * (int)gridDim.x;
-            const int d0 = tile * TILE;
-            const bool ragged = gk && (int64_t)d0 + TILE > p.D;  // warp-uniform
-            if (lane == 0) mbar_wait(bar_hout + 8 * hs, (i / NH) & 1);
-            if (do_h) {
-                if (ragged) {
-                    __syncwarp();
-                    const int n = (int)(p.D - d0) * k;
-                    float* dst = p.H_out + (size_t)d0 * k;
-                    for (int e = lane; e < n; e += 32) dst[e] = lds32(sHraw + hs * q.hraw + e * 4);
-                    __syncwarp();
-                } else if (lane == 0) {
-                    if (gk)
-                        tma_store_3d(&mapHout, sHraw + hs * q.hraw, 0, 0, tile);
-                    else
-                        tma_store_2d(&mapHout, sHraw + hs * q.hraw, 0, d0);
-                    tma_store_commit_and_wait_read();
+        if (!GK) {
+            if (lane == 0) {
+                for (int i = 0; i < n_my; ++i) {
+                    const int hs = i % NH;
+                    mbar_wait(bar_hout + 8 * hs, (i / NH) & 1);
+                    if (do_h) {
+                        tma_store_2d(&mapHout, sHraw + hs * q.hraw, 0, ((int)blockIdx.x + i * (int)gridDim.x) * TILE);
+                        tma_store_commit_and_wait_read();
+                    }
+                    mbar_arrive(bar_hempty + 8 * hs);
                 }
+                tma_store_wait_all();
             }
-            if (lane == 0) mbar_arrive(bar_hempty + 8 * hs);
+        } else {
+            constexpr bool gk = GK;
+            for (int i = 0; i < n_my; ++i) {
+                const int hs = i % NH;
+                const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+                const int d0 = tile * TILE;
+                const bool ragged = gk && (int64_t)d0 + TILE > p.D;  // warp-uniform
+                if (lane == 0) mbar_wait(bar_hout + 8 * hs, (i / NH) & 1);
+                if (do_h) {
+                    if (ragged) {
+                        __syncwarp();
+                        const int n = (int)(p.D - d0) * k;
+                        float* dst = p.H_out + (size_t)d0 * k;
+                        for (int e = lane; e < n; e += 32) dst[e] = lds32(sHraw + hs * q.hraw + e * 4);
+                        __syncwarp();
+                    } else if (lane == 0) {
+                        if (gk)
+                            tma_store_3d(&mapHout, sHraw + hs * q.hraw, 0, 0, tile);
+                        else
+                            tma_store_2d(&mapHout, sHraw + hs * q.hraw, 0, d0);
+                        tma_store_commit_and_wait_read();
+                    }
+                }
+                if (lane == 0) mbar_arrive(bar_hempty + 8 * hs);
+            }
+            if (lane == 0) tma_store_wait_all();
         }
-        if (lane == 0) tma_store_wait_all();
     } else if (warp >= 4) {
         // ================= epilogue warpgroups =================
         const int g = (warp - 4) >> 2, qw = warp & 3;
@@ -551,27 +585,25 @@ klnmf_pass_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
             mbar_wait(bar_hfull + 8 * hs, (i / NH) & 1);
             const uint32_t hrow = sHraw + hs * q.hraw + s * (k * 4);
             const uint32_t th = tmem + lane_off + (b ? TM_H1 : TM_H0);
-            if (p.generic_k) {  // rows are not 16-byte aligned: scalar loads
+            bool row_valid = true;
+            if (HS) row_valid = (int64_t)((int)blockIdx.x + i * (int)gridDim.x) * TILE + s < p.D;
 #pragma unroll
-                for (int j = 0; j < KP8; ++j) h[j] = j < k ? lds32(hrow + j * 4) : 0.f;
-            } else {
+            for (int j = 0; j < KP8; j += 8) {
+                if (GK) {  // rows are not 16-byte aligned: scalar loads
 #pragma unroll
-                for (int j = 0; j < KP8; j += 8) {
+                    for (int e = 0; e < 8; ++e) h[j + e] = j + e < k ? lds32(hrow + (j + e) * 4) : 0.f;
+                } else {
                     float4 t0 = make_float4(0.f, 0.f, 0.f, 0.f), t1 = t0;
                     if (j < k) t0 = lds128(hrow + j * 4);
                     if (j + 4 < k) t1 = lds128(hrow + j * 4 + 16);
                     h[j] = t0.x, h[j + 1] = t0.y, h[j + 2] = t0.z, h[j + 3] = t0.w;
                     h[j + 4] = t1.x, h[j + 5] = t1.y, h[j + 6] = t1.z, h[j + 7] = t1.w;
                 }
-            }
-            if (p.h_scale) {  // normalize_WH folded into the read (reference utils.py:155-158 as used by mvnmf.py:80-88)
-                const bool row_valid = (int64_t)((int)blockIdx.x + i * (int)gridDim.x) * TILE + s < p.D;
+                if (HS) {  // normalize_WH folded into the read (reference utils.py:155-158 as used by mvnmf.py:80-88)
 #pragma unroll
-                for (int j = 0; j < KP8; ++j)
-                    if (j < k) h[j] = row_valid ? fmaxf(h[j] * __ldg(p.h_scale + j), eps) : 0.f;
-            }
-#pragma unroll
-            for (int j = 0; j < KP8; j += 8) {
+                    for (int e = 0; e < 8; ++e)
+                        if (j + e < k) h[j + e] = row_valid ? fmaxf(h[j + e] * __ldg(p.h_scale + j + e), eps) : 0.f;
+                }
                 uint32_t hi[8], lo[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
@@ -676,7 +708,7 @@ klnmf_pass_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
                 }
                 {
                     const uint32_t orow = sHraw + (i % NH) * q.hraw + s * (k * 4);
-                    if (p.generic_k) {
+                    if (GK) {
 #pragma unroll
                         for (int j = 0; j < KP8; ++j)
                             if (j < k) sts32(orow + j * 4, fmaxf(h[j] * __uint_as_float(v[j]), eps));
@@ -695,7 +727,7 @@ klnmf_pass_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
                 }
                 tc_fence_before();
             }
-            if (!DO_R && do_h) {  // rescale mode: the exposures as they were read (scaled, clipped) are the output
+            if (HS && !DO_R && do_h) {  // rescale mode: the exposures as they were read (scaled, clipped) are the output
                 const uint32_t orow = sHraw + (i % NH) * q.hraw + s * (k * 4);
 #pragma unroll
                 for (int j = 0; j < KP8; ++j)
@@ -837,23 +869,23 @@ int encode_h3d(CUtensorMap* map, const void* ptr, int k, int64_t D) {
     return 0;
 }
 
-template <int KP8, bool DO_R, bool DO_KL>
+template <int KP8, bool DO_R, bool DO_KL, bool GK, bool HS>
 int launch_tc_v(sal_ctx* c, const PassArgs& a, cudaStream_t st) {
     const Plan q = make_plan(c->k, KP8);
     if (q.total > SMEM_LIMIT) {
         sal_set_error("tensor-core pass: shared-memory plan of %d bytes exceeds the limit", q.total);
         return SAL_EUNSUPPORTED;
     }
-    static bool attr_set[16] = {false};
+    static bool attr_set[16] = {false};  // (one flag array per instantiation)
     if (!attr_set[c->device & 15]) {
-        SAL_CUDA(cudaFuncSetAttribute(klnmf_pass_tc_kernel<KP8, DO_R, DO_KL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        SAL_CUDA(cudaFuncSetAttribute(klnmf_pass_tc_kernel<KP8, DO_R, DO_KL, GK, HS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       SMEM_LIMIT));
         attr_set[c->device & 15] = true;
     }
     CUtensorMap mapX, mapH, mapHout;
     if (int e = encode_2d(&mapX, a.X, VT, (uint64_t)c->D, 32, TILE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return e;
     const void* hout = (a.flags & SAL_PASS_UPDATE_H) ? a.H_out : a.H_in;
-    const bool generic_k = (c->k & 3) != 0;
+    constexpr bool generic_k = GK;
     if (generic_k) {
         if (int e = encode_h3d(&mapH, a.H_in, c->k, c->D)) return e;
         if (int e = encode_h3d(&mapHout, hout, c->k, c->D)) return e;
@@ -870,7 +902,7 @@ int launch_tc_v(sal_ctx* c, const PassArgs& a, cudaStream_t st) {
     p.n_tiles = (int)((c->D + TILE - 1) / TILE);
     const int grid = p.n_tiles < c->n_sm ? p.n_tiles : c->n_sm;
     if (int e = sal_timing_begin(c, a.flags, st)) return e;
-    SAL_CUDA(sal_launch_pdl(klnmf_pass_tc_kernel<KP8, DO_R, DO_KL>, grid, NTHREADS, q.total, st, mapX, mapH, mapHout, p));
+    SAL_CUDA(sal_launch_pdl(klnmf_pass_tc_kernel<KP8, DO_R, DO_KL, GK, HS>, grid, NTHREADS, q.total, st, mapX, mapH, mapHout, p));
     if (int e = sal_timing_end(c, a.flags, st)) return e;
     c->launches++;
     if (a.flags & SAL_PASS_HSUM) {  // column sums of H_in: per-block partials in the layout the reduction kernel expects
@@ -885,9 +917,11 @@ template <int KP8>
 int launch_tc(sal_ctx* c, const PassArgs& a, cudaStream_t st) {
     // with h_scale, UPDATE_H means "write the rescaled exposures" (no multiplicative update): the objective-only pipeline
     const bool r = !a.h_scale && (a.flags & (SAL_PASS_UPDATE_H | SAL_PASS_WNUM)), kl = a.flags & SAL_PASS_OBJECTIVE;
-    if (r && !kl) return launch_tc_v<KP8, true, false>(c, a, st);
-    if (!r && kl) return launch_tc_v<KP8, false, true>(c, a, st);
-    return launch_tc_v<KP8, true, true>(c, a, st);
+    const bool gk = (c->k & 3) != 0;
+    if (a.h_scale) return gk ? launch_tc_v<KP8, false, true, true, true>(c, a, st) : launch_tc_v<KP8, false, true, false, true>(c, a, st);
+    if (r && !kl) return gk ? launch_tc_v<KP8, true, false, true, false>(c, a, st) : launch_tc_v<KP8, true, false, false, false>(c, a, st);
+    if (!r && kl) return gk ? launch_tc_v<KP8, false, true, true, false>(c, a, st) : launch_tc_v<KP8, false, true, false, false>(c, a, st);
+    return gk ? launch_tc_v<KP8, true, true, true, false>(c, a, st) : launch_tc_v<KP8, true, true, false, false>(c, a, st);
 }
 
 }  // namespace
