@@ -41,7 +41,7 @@ def initialize_mat(data_mat, n_signatures, method="nndsvd", given_signatures_mat
     """(signatures_mat (k,V), exposures_mat (D,k)): method dispatch, given signatures written over the
     first rows, then normalise columns of W and clip both to EPSILON (reference initialize.py:44-119).
 
-    ``_defer`` (a dict, internal): for large custom exposure matrices the second half of that last step,
+    ``_defer`` (a dict, internal): for large custom exposure matrices (and device-drawn random ones) the second half of that last step,
     ``H <- clip(H * colsum(W))``, is left to the device right after the upload (sal_scale_clip_rows); the
     column sums are returned in ``_defer['exposure_scale']`` and the exposures are handed back untouched."""
     value_checker("method", method, _INIT_METHODS)
@@ -58,7 +58,12 @@ def initialize_mat(data_mat, n_signatures, method="nndsvd", given_signatures_mat
         else:
             sigs, expo = init_nndsvd(data_mat, n_signatures, method=method, **kwargs)
     elif method == "random":
-        sigs, expo = init_random(data_mat, n_signatures, **kwargs)
+        if init_device is not None:
+            from .device_nndsvd import init_random_device
+
+            sigs, expo = init_random_device(data_mat, n_signatures, device=init_device, **kwargs)
+        else:
+            sigs, expo = init_random(data_mat, n_signatures, **kwargs)
     else:
         sigs, expo = init_separableNMF(data_mat, n_signatures, **kwargs)
 
@@ -71,7 +76,9 @@ def initialize_mat(data_mat, n_signatures, method="nndsvd", given_signatures_mat
             raise ValueError("The given signature matrix contains too many signatures.")
         sigs[:n_given, :] = given_signatures_mat.copy()
 
-    if _defer is not None and method == "custom" and expo.size >= DEFER_MIN_SIZE:
+    if _defer is not None and (
+        (method == "custom" and expo.size >= DEFER_MIN_SIZE) or (method == "random" and init_device is not None)
+    ):
         scale = np.sum(sigs, axis=1)
         _defer["exposure_scale"] = scale
         return (sigs / scale[:, None]).clip(EPSILON), expo

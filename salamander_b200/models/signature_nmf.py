@@ -61,8 +61,12 @@ class SignatureNMF(ABC):
         # True: ignore an initialised process group -- this model is an independent replica (restarts / k-sweep)
         self.replica = bool(replica)
         # NNDSVD initialisations with the SVD on the device (initialization/device_nndsvd.py): True, False (scikit-learn's
-        # randomized SVD on the host, as the reference) or "auto" (device for matrices of at least 2^22 entries)
+        # randomized SVD on the host, as the reference) or "auto" (device for matrices of at least 2^22 entries).  True also
+        # draws the exposures of init_method="random" on the device (same distribution, not numpy's stream)
         self.init_device = init_device
+        # True: fit() also leaves the per-sample reconstruction errors in adata.obs (the reference computes them lazily on
+        # first access, which here would mean a second upload of X); the k-sweep driver sets it
+        self.errors_in_fit = False
         self.transfer_bytes = {"h2d": 0, "d2h": 0}  # host<->device bytes of the last fit / update
 
         # data / fitting dependent attributes (reference signature_nmf.py:182-185)
@@ -190,8 +194,10 @@ class SignatureNMF(ABC):
 
     def _init_device_kwargs(self) -> dict[str, Any]:
         """``{'_init_device': torch.device}`` when this fit's NNDSVD initialisation is to run on the device."""
-        if self.init_method not in ("nndsvd", "nndsvda", "nndsvdar") or self.init_device is False:
+        if self.init_method not in ("nndsvd", "nndsvda", "nndsvdar", "random") or self.init_device is False:
             return {}
+        if self.init_method == "random" and self.init_device == "auto":
+            return {}  # device-drawn exposures are not numpy's draws: only on explicit request
         if self.init_device == "auto" and np.asarray(self.adata.X).size < self._DEVICE_CLIP_MIN_SIZE:
             return {}
         return {"_init_device": self._resolved_device()}
@@ -293,6 +299,9 @@ class SignatureNMF(ABC):
             finally:
                 self._in_fit = False
             tick("fit_loop")
+            if self.errors_in_fit:  # while X and the factors are still resident (a later call would upload them again)
+                self.compute_reconstruction_errors()
+                tick("reconstruction_errors")
         self._tick = None
 
         if history:

@@ -21,6 +21,16 @@ from . import _dist
 from .models.klnmf import KLNMF
 
 
+def _shallow_copy(adata):
+    """A fresh container around the SAME count matrix: a fit only ever rebinds ``adata.X`` (when clipping changes an
+    entry), it does not write into the array, so the fits of a sweep can share it instead of copying it every time."""
+    from ._anndata import AnnData
+
+    new = AnnData(np.asarray(adata.X))
+    new.obs_names, new.var_names = adata.obs_names, adata.var_names
+    return new
+
+
 def sweep_klnmf(
     adata,
     ns_signatures: Iterable[int],
@@ -43,7 +53,8 @@ def sweep_klnmf(
         if idx % world != rank:
             continue
         model = KLNMF(n_signatures=k, init_method="random", replica=True, **model_kwargs)
-        model.fit(adata.copy(), init_kwargs={"seed": seed})
+        model.errors_in_fit = True
+        model.fit(_shallow_copy(adata), init_kwargs={"seed": seed})
         err = model.reconstruction_error
         rows.append((k, seed, model.n_iterations, float(model.history["objective_function"][-1]), float(err), rank))
         if keep_best and (k not in best or err < best[k].reconstruction_error):

@@ -56,3 +56,20 @@ def test_large_matrix_and_fit_from_device_init():
     h0, h1 = (np.array(m.history["objective_function"]) for m in fits)
     assert np.allclose(h0, h1, rtol=1e-9, atol=0)
     assert np.allclose(fits[0].asignatures.X, fits[1].asignatures.X, rtol=1e-6, atol=1e-12)
+
+
+def test_fit_from_device_random_initialisation():
+    """init_method='random' with init_device=True: exposures drawn on the device (reproducible for a seed), rescaled and
+    clipped on the device; the fit behaves like one from the host initialisation (same final objective within 1 %)."""
+    import bench
+
+    X = bench.synth_rows(0, 30_000, 6).astype(np.float64)
+    finals = {}
+    for name, kw in {"host": {}, "dev1": {"init_device": True}, "dev2": {"init_device": True}}.items():
+        model = sal.models.KLNMF(n_signatures=6, init_method="random", dtype="float64", min_iterations=300, max_iterations=300, **kw)
+        model.fit(AnnData(X.copy()), init_kwargs={"seed": 5})
+        hist = model.history["objective_function"]
+        assert hist[-1] < hist[0]
+        finals[name] = (hist[-1], np.array(model.adata.obsm["exposures"]))
+    assert finals["dev1"][0] == finals["dev2"][0] and np.array_equal(finals["dev1"][1], finals["dev2"][1])
+    assert abs(finals["dev1"][0] - finals["host"][0]) / finals["host"][0] < 1e-2

@@ -194,3 +194,26 @@ def test_gram_nndsvd_arithmetic_on_the_cpu_device():
         assert np.array_equal(s_ref == 0, s_dev == 0) and np.array_equal(e_ref == 0, e_dev == 0)
         assert np.abs(s_dev - s_ref).max() <= 1e-10 * np.abs(s_ref).max()
         assert np.abs(e_dev - e_ref).max() <= 1e-10 * np.abs(e_ref).max()
+
+
+def test_device_random_initialisation_contract_on_the_cpu_device():
+    """init_random_device (opt-in, models' init_device=True): signatures are the reference's numpy draws for the seed, the
+    exposures are reproducible, have the samples' totals as row sums and Dirichlet(1_k) shares -- but are not numpy's draws."""
+    import torch
+
+    from salamander_b200.initialization.device_nndsvd import init_random_device
+    from salamander_b200.initialization.initialize import initialize_mat
+    from salamander_b200.initialization.methods import init_random
+
+    X = np.random.default_rng(0).poisson(5.0, size=(20_000, 96)).astype(np.float64)
+    s_ref, e_ref = init_random(X, 6, seed=11)
+    s1, e1 = init_random_device(X, 6, seed=11, device=torch.device("cpu"))
+    s2, e2 = init_random_device(X, 6, seed=11, device=torch.device("cpu"))
+    assert np.array_equal(s1, s_ref) and np.array_equal(e1, e2) and not np.allclose(e1, e_ref)
+    assert np.allclose(e1.sum(axis=1), X.sum(axis=1), rtol=1e-12)
+    share1, share_ref = e1 / e1.sum(1, keepdims=True), e_ref / e_ref.sum(1, keepdims=True)
+    assert np.allclose(share1.mean(0), 1 / 6, atol=5e-3) and np.isclose(share1.var(0).mean(), share_ref.var(0).mean(), rtol=0.05)
+    defer = {}
+    W, H = initialize_mat(X, 6, "random", None, _defer=defer, seed=11, _init_device=torch.device("cpu"))
+    assert "exposure_scale" in defer and np.array_equal(H, e1)  # the rescale / clip of H is left to the device
+    assert np.allclose(W.sum(axis=1), 1.0, atol=1e-5)
