@@ -37,7 +37,7 @@ enum { SAL_F32 = 0, SAL_F64 = 1 };
 enum {
     SAL_MATH_FMA = 0,  /* CUDA-core FMA in the handle's dtype (exact fp32 / fp64)          */
     SAL_MATH_TF32 = 1, /* tcgen05 kind::tf32 tensor-core contractions, fp32 accumulation:
-                          used by sal_klnmf_pass when V == 96, k <= 32, no weights / h_scale and flags within
+                          used by sal_klnmf_pass when V == 96, k <= 32 and flags within
                           UPDATE_H | WNUM | OBJECTIVE and D_local >= SAL_TF32_MIN_SAMPLES (below that the pass is
                           latency bound and the tf32 noise of the numerator no longer averages out over samples);
                           every other call runs the exact FMA kernels (still on the GPU)                      */

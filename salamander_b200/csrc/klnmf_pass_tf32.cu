@@ -87,6 +87,8 @@ __host__ __device__ inline Plan make_plan(int k, int KP8) {
 struct TcParams {
     const float* W;
     const float* H_in;
+    const float* w_kl;     // per-sample weights of the KL term (weights_kl) or null
+    const float* w_lhalf;  // per-sample l-half penalty weights (weights_lhalf) or null
     const float* h_scale;  // MvNMF line-search trial: exposures are read as clip(H * h_scale) and written back like that
     float* H_out;
     float* partial_wnum;
@@ -308,7 +310,10 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8])
 
 // GK: k % 4 != 0 (3-D exposure view, scalar staging accesses); HS: MvNMF trial pass (exposures rescaled on the way in and
 // written back).  Both are compile-time: as run-time branches in the per-tile loops they cost the common variant 10 %.
-template <int KP8, bool DO_R, bool DO_KL, bool GK, bool HS>
+// WT: per-sample weights (weights_kl / weights_lhalf, reference _utils_klnmf.py:333-360, klnmf.py:75-79): the KL weight scales
+// the sample's row of the H^T operand of G3 and its objective term, the l-half weight switches the H update to its
+// closed form and adds lambda_d * sum_k sqrt(h_dk) to the objective.  Per-row work only; the quotient loop is untouched.
+template <int KP8, bool DO_R, bool DO_KL, bool GK, bool HS, bool WT>
 __global__ void __launch_bounds__(NTHREADS, 1)
 klnmf_pass_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapH,
                      const __grid_constant__ CUtensorMap mapHout, TcParams p) {
@@ -673,7 +678,24 @@ klnmf_pass_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
                     for (int e = 0; e < 32; ++e) p.dbg[(size_t)s * VT + 64 + e] = __uint_as_float(v0[e]);
                 }
             }
-            if (DO_KL && valid) obj_acc += (double)kl;
+            float wk = 1.f, lam = 0.f;
+            if (WT && valid) {
+                if (p.w_kl) wk = __ldg(p.w_kl + d0 + s);
+                if (p.w_lhalf) lam = __ldg(p.w_lhalf + d0 + s);
+            }
+            if (DO_KL && valid) {
+                if (WT) {
+                    float sq = 0.f;
+                    if (p.w_lhalf) {
+#pragma unroll
+                        for (int j = 0; j < KP8; ++j)
+                            if (j < k) sq += sqrtf(h[j]);
+                    }
+                    obj_acc += (double)kl * (double)wk + (double)lam * (double)sq;
+                } else {
+                    obj_acc += (double)kl;
+                }
+            }
             stamp(p.dbg, tlw, g, i, 4);
             if (DO_R) {
                 if (i > 0) mbar_wait(bar_shtfree, (i - 1) & 1);  // G3(i-1) has read sHT
@@ -681,7 +703,7 @@ klnmf_pass_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
                 const uint32_t tbase = sHT + (s >> 2) * SHT_LBO + (s & 3) * 4;
 #pragma unroll
                 for (int j = 0; j < KP8; ++j)
-                    if (j < k) sts32(tbase + (j >> 3) * SHT_SBO + (j & 7) * 16, tf32_rn(h[j]));
+                    if (j < k) sts32(tbase + (j >> 3) * SHT_SBO + (j & 7) * 16, tf32_rn(WT ? h[j] * wk : h[j]));
                 tc_wait_st();
                 stamp(p.dbg, tlw, g, i, 6);
                 fence_proxy_async();
@@ -708,6 +730,22 @@ klnmf_pass_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
                 }
                 {
                     const uint32_t orow = sHraw + (i % NH) * q.hraw + s * (k * 4);
+                    if (WT && p.w_lhalf) {
+                        // closed form of the l-half penalised update (reference _utils_klnmf.py:349-360); the result takes the
+                        // place of the plain product below by rewriting v[] so that h * v equals it
+                        const float wsq = p.w_kl ? wk * wk : 1.f;
+#pragma unroll
+                        for (int j = 0; j < KP8; ++j)
+                            if (j < k) {
+                                float t = 4.f * h[j] * __uint_as_float(v[j]);
+                                if (p.w_kl) t *= wsq;
+                                const float root = 0.5f * lam - sqrtf(0.25f * lam * lam + t);
+                                float o = 0.25f * root * root;
+                                if (p.w_kl) o = o / wsq;
+                                h[j] = fmaxf(o, eps);
+                                v[j] = __float_as_uint(1.f);
+                            }
+                    }
                     if (GK) {
 #pragma unroll
                         for (int j = 0; j < KP8; ++j)
@@ -869,7 +907,7 @@ int encode_h3d(CUtensorMap* map, const void* ptr, int k, int64_t D) {
     return 0;
 }
 
-template <int KP8, bool DO_R, bool DO_KL, bool GK, bool HS>
+template <int KP8, bool DO_R, bool DO_KL, bool GK, bool HS, bool WT>
 int launch_tc_v(sal_ctx* c, const PassArgs& a, cudaStream_t st) {
     const Plan q = make_plan(c->k, KP8);
     if (q.total > SMEM_LIMIT) {
@@ -878,7 +916,7 @@ int launch_tc_v(sal_ctx* c, const PassArgs& a, cudaStream_t st) {
     }
     static bool attr_set[16] = {false};  // (one flag array per instantiation)
     if (!attr_set[c->device & 15]) {
-        SAL_CUDA(cudaFuncSetAttribute(klnmf_pass_tc_kernel<KP8, DO_R, DO_KL, GK, HS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        SAL_CUDA(cudaFuncSetAttribute(klnmf_pass_tc_kernel<KP8, DO_R, DO_KL, GK, HS, WT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       SMEM_LIMIT));
         attr_set[c->device & 15] = true;
     }
@@ -895,14 +933,14 @@ int launch_tc_v(sal_ctx* c, const PassArgs& a, cudaStream_t st) {
     }
     TcParams p;
     p.W = (const float*)a.W, p.H_in = (const float*)a.H_in, p.H_out = (float*)hout, p.generic_k = generic_k ? 1 : 0;
-    p.h_scale = (const float*)a.h_scale;
+    p.h_scale = (const float*)a.h_scale, p.w_kl = (const float*)a.w_kl, p.w_lhalf = (const float*)a.w_lhalf;
     p.partial_wnum = (float*)c->partial_wnum, p.partial_obj = c->partial_obj;
     p.dbg = (float*)c->dbg;
     p.D = c->D, p.k = c->k, p.flags = a.flags;
     p.n_tiles = (int)((c->D + TILE - 1) / TILE);
     const int grid = p.n_tiles < c->n_sm ? p.n_tiles : c->n_sm;
     if (int e = sal_timing_begin(c, a.flags, st)) return e;
-    SAL_CUDA(sal_launch_pdl(klnmf_pass_tc_kernel<KP8, DO_R, DO_KL, GK, HS>, grid, NTHREADS, q.total, st, mapX, mapH, mapHout, p));
+    SAL_CUDA(sal_launch_pdl(klnmf_pass_tc_kernel<KP8, DO_R, DO_KL, GK, HS, WT>, grid, NTHREADS, q.total, st, mapX, mapH, mapHout, p));
     if (int e = sal_timing_end(c, a.flags, st)) return e;
     c->launches++;
     if (a.flags & SAL_PASS_HSUM) {  // column sums of H_in: per-block partials in the layout the reduction kernel expects
@@ -917,11 +955,15 @@ template <int KP8>
 int launch_tc(sal_ctx* c, const PassArgs& a, cudaStream_t st) {
     // with h_scale, UPDATE_H means "write the rescaled exposures" (no multiplicative update): the objective-only pipeline
     const bool r = !a.h_scale && (a.flags & (SAL_PASS_UPDATE_H | SAL_PASS_WNUM)), kl = a.flags & SAL_PASS_OBJECTIVE;
-    const bool gk = (c->k & 3) != 0;
-    if (a.h_scale) return gk ? launch_tc_v<KP8, false, true, true, true>(c, a, st) : launch_tc_v<KP8, false, true, false, true>(c, a, st);
-    if (r && !kl) return gk ? launch_tc_v<KP8, true, false, true, false>(c, a, st) : launch_tc_v<KP8, true, false, false, false>(c, a, st);
-    if (!r && kl) return gk ? launch_tc_v<KP8, false, true, true, false>(c, a, st) : launch_tc_v<KP8, false, true, false, false>(c, a, st);
-    return gk ? launch_tc_v<KP8, true, true, true, false>(c, a, st) : launch_tc_v<KP8, true, true, false, false>(c, a, st);
+    const bool gk = (c->k & 3) != 0, wt = a.w_kl || a.w_lhalf;
+#define SAL_TC(R_, KL_, HS_)                                                                               \
+    (gk ? (wt ? launch_tc_v<KP8, R_, KL_, true, HS_, true>(c, a, st) : launch_tc_v<KP8, R_, KL_, true, HS_, false>(c, a, st)) \
+        : (wt ? launch_tc_v<KP8, R_, KL_, false, HS_, true>(c, a, st) : launch_tc_v<KP8, R_, KL_, false, HS_, false>(c, a, st)))
+    if (a.h_scale) return gk ? launch_tc_v<KP8, false, true, true, true, false>(c, a, st) : launch_tc_v<KP8, false, true, false, true, false>(c, a, st);
+    if (r && !kl) return SAL_TC(true, false, false);
+    if (!r && kl) return SAL_TC(false, true, false);
+    return SAL_TC(true, true, false);
+#undef SAL_TC
 }
 
 }  // namespace
@@ -929,7 +971,8 @@ int launch_tc(sal_ctx* c, const PassArgs& a, cudaStream_t st) {
 bool sal_pass_tf32_supported(const sal_ctx* c, const PassArgs& a) {
     const int allowed = SAL_PASS_UPDATE_H | SAL_PASS_WNUM | SAL_PASS_OBJECTIVE | SAL_PASS_HSUM;
     if (c->dtype != SAL_F32 || c->V != VT || c->k > 32) return false;
-    if ((a.flags & ~allowed) || a.w_kl || a.w_lhalf) return false;
+    if (a.flags & ~allowed) return false;
+    if ((a.w_kl || a.w_lhalf) && (a.h_scale || (a.flags & SAL_PASS_HSUM))) return false;  // weights are a KLNMF feature
     if ((a.flags & SAL_PASS_HSUM) && !(a.flags & ~SAL_PASS_HSUM)) return false;  // row sums alone: not worth this kernel
     if (a.h_scale && a.flags != (SAL_PASS_UPDATE_H | SAL_PASS_OBJECTIVE)) return false;  // the MvNMF trial pass only
     if (((uintptr_t)a.X | (uintptr_t)a.H_in | (uintptr_t)a.H_out) & 15) return false;

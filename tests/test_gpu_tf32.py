@@ -137,20 +137,24 @@ def test_generic_k_deterministic_and_in_place():
 
 
 def test_unsupported_shapes_use_the_exact_kernels():
-    """Weights (and V != 96): the call still succeeds through the exact FMA kernels -- never a CPU fallback."""
+    """V != 96 (and per-sample KL, Poisson likelihood ...): the call still succeeds through the exact FMA kernels -- never a
+    CPU fallback."""
     dev = torch.device("cuda:0")
-    X, W, H = _problem(500, 8, 3, dev)
-    w_kl = torch.rand(500, dtype=torch.float64, device=dev) + 0.5
-    ws = Workspace(96, 500, 8, torch.float32, dev, math="tf32_always")
-    Hout = torch.empty((500, 8), dtype=torch.float32, device=dev)
-    Wnum = torch.empty((8, 96), dtype=torch.float32, device=dev)
-    ws.klnmf_pass(X.float().contiguous(), W.float().contiguous(), H.float().contiguous(), PASS_UPDATE_H | PASS_WNUM, H_out=Hout,
-                  Wnum=Wnum, w_kl=w_kl.float())
+    D, k, V = 500, 8, 83
+    gen = torch.Generator(device=dev).manual_seed(3)
+    W = torch.rand((k, V), generator=gen, device=dev, dtype=torch.float64) + 0.01
+    W /= W.sum(1, keepdim=True)
+    H = torch.rand((D, k), generator=gen, device=dev, dtype=torch.float64) * 400 + 1.0
+    X = torch.poisson(H @ W, generator=gen).clamp_min(EPS)
+    ws = Workspace(V, D, k, torch.float32, dev, math="tf32_always")
+    Hout = torch.empty((D, k), dtype=torch.float32, device=dev)
+    Wnum = torch.empty((k, V), dtype=torch.float32, device=dev)
+    ws.klnmf_pass(X.float().contiguous(), W.float().contiguous(), H.float().contiguous(), PASS_UPDATE_H | PASS_WNUM, H_out=Hout, Wnum=Wnum)
     torch.cuda.synchronize()
     ws.close()
     R = X / (H @ W)
     assert _relerr(Hout.double(), (H * (R @ W.T)).clamp_min(EPS)) < 3e-5
-    assert _relerr(Wnum.double(), H.T @ (R * w_kl[:, None])) < 3e-5
+    assert _relerr(Wnum.double(), H.T @ R) < 3e-5
 
 
 def _pcawg():
@@ -256,3 +260,39 @@ def test_mvnmf_fit_on_tensor_cores_tracks_float64():
     assert abs(o32 - o64) / abs(o64) < 1e-4, (o32, o64)
     cos = np.sum(W64 * W32, axis=1) / (np.linalg.norm(W64, axis=1) * np.linalg.norm(W32, axis=1))
     assert cos.min() >= 0.9999, cos
+
+
+@pytest.mark.parametrize("use_kl,use_lhalf", [(True, False), (False, True), (True, True)])
+@pytest.mark.parametrize("D,k", [(9000, 8), (40_001, 13)])
+def test_weighted_pass_on_tensor_cores(D, k, use_kl, use_lhalf):
+    """weights_kl / weights_lhalf (reference _utils_klnmf.py:333-360, klnmf.py:75-79) through the tensor-core kernel: weighted
+    numerator, weighted objective + l-half term, closed-form H update."""
+    dev = torch.device("cuda:0")
+    X, W, H = _problem(D, k, 70 + k, dev)
+    gen = torch.Generator(device=dev).manual_seed(1)
+    w = torch.rand(D, generator=gen, device=dev, dtype=torch.float64) + 0.5 if use_kl else None
+    lam = torch.rand(D, generator=gen, device=dev, dtype=torch.float64) * 3.0 if use_lhalf else None
+    ws = Workspace(96, D, k, torch.float32, dev, math="tf32_always")
+    Hout = torch.full((D, k), -1.0, dtype=torch.float32, device=dev)
+    Wnum = torch.empty((k, 96), dtype=torch.float32, device=dev)
+    obj = torch.zeros(1, dtype=torch.float64, device=dev)
+    n0 = ws.launches
+    ws.klnmf_pass(X.float().contiguous(), W.float().contiguous(), H.float().contiguous(), PASS_UPDATE_H | PASS_WNUM | PASS_OBJECTIVE,
+                  H_out=Hout, Wnum=Wnum, objective=obj, w_kl=None if w is None else w.float(), w_lhalf=None if lam is None else lam.float())
+    torch.cuda.synchronize()
+    assert ws.launches - n0 == 2
+    ws.close()
+    A = X / (H @ W)
+    wd = torch.ones(D, dtype=torch.float64, device=dev) if w is None else w
+    Hn = A @ W.T
+    if lam is None:
+        H_ref = (H * Hn).clamp_min(EPS)
+    else:
+        wsq = (wd * wd)[:, None]
+        root = 0.5 * lam[:, None] - torch.sqrt(0.25 * lam[:, None] ** 2 + 4.0 * H * Hn * wsq)
+        H_ref = (0.25 * root * root / wsq).clamp_min(EPS)
+    kl_rows = (X * torch.log(A) - X + H @ W).sum(1)
+    obj_ref = float((wd * kl_rows).sum()) + (0.0 if lam is None else float((lam[:, None] * torch.sqrt(H)).sum()))
+    assert _relerr(Wnum.double(), (H * wd[:, None]).T @ A) < RTOL
+    assert _relerr(Hout.double(), H_ref) < (2e-2 if use_lhalf else RTOL)  # the closed form amplifies tf32 noise where root ~ 0
+    assert abs(float(obj.item()) - obj_ref) / abs(obj_ref) < RTOL
