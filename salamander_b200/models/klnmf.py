@@ -36,7 +36,7 @@ class KLNMF(StandardNMF):
         self.weights_kl = None
         self.weights_lhalf = None
         # capture the periods of the fit loop in CUDA graphs (see _fit_loop): True, False or "auto" = only when a shard is
-        # small enough for launch gaps to matter.  Measured on B200 (profiles/r01_e2e_phases.md): at 1M samples an eager
+        # small enough for launch gaps and host time to matter (_GRAPH_MAX_SAMPLES).  Measured on B200 (profiles/r01_e2e_phases.md): at 1M samples an eager
         # period is within 2 % of a replayed one while capturing ~6 graphs per fit costs more than that and occasionally
         # stalls in the driver; at 125k samples graphs are 12 % faster.
         self.use_graphs: bool | str = "auto"
@@ -188,7 +188,10 @@ class KLNMF(StandardNMF):
                 st.weights["peer_exchange"] = None
         return st.weights["peer_exchange"]
 
-    _GRAPH_MAX_SAMPLES = 400_000  # "auto": per-update kernel time below ~40 us
+    # "auto": graphs while an update takes less than ~80 us of GPU time.  An eager update costs the host ~50-60 us (ctypes
+    # marshalling, tensor-map encodes, two launches): hidden behind the GPU at 1M samples per shard, not at 500k (measured
+    # at 2 GPUs: 65.8 us per update eager vs 60.8 us replayed)
+    _GRAPH_MAX_SAMPLES = 800_000
 
     def _fit_loop(self, given_parameters, verbose, verbosity_freq):
         """Same iterates, history and stopping iteration as the reference loop (signature_nmf.py:361-380), run in
