@@ -217,3 +217,31 @@ def test_device_random_initialisation_contract_on_the_cpu_device():
     W, H = initialize_mat(X, 6, "random", None, _defer=defer, seed=11, _init_device=torch.device("cpu"))
     assert "exposure_scale" in defer and np.array_equal(H, e1)  # the rescale / clip of H is left to the device
     assert np.allclose(W.sum(axis=1), 1.0, atol=1e-5)
+
+
+def test_init_device_routing_and_sweep_containers():
+    """Host logic around the optional device initialisation and the sweep: which fits ask for it, and that the fits of a
+    sweep share the count matrix instead of copying it."""
+    from salamander_b200 import AnnData
+    from salamander_b200.models import KLNMF
+    from salamander_b200.sweep import _shallow_copy
+
+    X = np.random.default_rng(1).poisson(3.0, size=(50, 96)).astype(np.float64)
+    ad = AnnData(X)
+    for kwargs in (dict(init_method="nndsvd"), dict(init_method="nndsvd", init_device="auto"), dict(init_method="random", init_device="auto"),
+                   dict(init_method="flat", init_device=True)):
+        m = KLNMF(n_signatures=3, **kwargs)
+        m.adata = ad
+        assert m._init_device_kwargs() == {}, kwargs  # host initialisation: default, small matrices, other methods
+    with pytest.raises(ValueError):
+        KLNMF(n_signatures=3, init_device="yes")
+    if not torch.cuda.is_available():  # asking for it without a GPU fails loudly, like every device step
+        m = KLNMF(n_signatures=3, init_method="nndsvd", init_device=True)
+        m.adata = ad
+        with pytest.raises(Exception):
+            m._init_device_kwargs()
+    shallow = _shallow_copy(ad)
+    assert shallow is not ad and np.shares_memory(np.asarray(shallow.X), X)
+    assert list(shallow.obs_names) == list(ad.obs_names) and list(shallow.var_names) == list(ad.var_names)
+    shallow.obsm["exposures"] = np.zeros((50, 3))
+    assert "exposures" not in ad.obsm
