@@ -104,6 +104,11 @@ int64_t sal_launch_count(sal_handle_t h);
  *                   (MvNMF line-search trial: normalize_WH + clip, utils.py:155-158,
  *                   mvnmf.py:80-81) and, with UPDATE_H, writes that H to H_out unchanged.
  *   H_out may alias H_in.  Wnum / objective / per_sample / hsum may be NULL if not flagged.
+ *   Stream ordering: the tensor-core pass is launched as a programmatic dependent launch and requests its first tiles
+ *   of X before it waits for the previous kernel of the stream (X is constant during a fit).  W, H, weights and every
+ *   output are only touched after that wait.  Hence X must not be written by the KERNEL that directly precedes a pass on
+ *   the same stream (a memcpy, an event or a host synchronisation in between restores full ordering; the models
+ *   synchronise after sal_clip_counts, the only kernel of this library that writes X).
  */
 int sal_klnmf_pass(sal_handle_t h, const void* X, const void* W, const void* H_in, void* H_out,
                    const void* w_kl, const void* w_lhalf, const void* h_scale, int flags,
