@@ -92,6 +92,63 @@ def mvnmf_case(tag, k, seed, **ctor):
     print(tag, "history:", len(model.history["objective_function"]), "final:", model.history["objective_function"][-1], "gamma", model._gamma)
 
 
+def corrnmf_case(tag, k, dim, seed, n_iter):
+    """CorrNMFDet of the live reference: the state right after its own initialisation and ``n_iter`` whole iterations
+    (ELBO after each one, final parameters)."""
+    sal = rl.load_package()
+    kw = dict(n_signatures=k, dim_embeddings=dim, init_method="random", min_iterations=n_iter, max_iterations=n_iter, conv_test_freq=1)
+    model = sal.models.CorrNMFDet(**kw)
+    adata = _adata()
+    model._setup_adata(adata)
+    np.random.seed(seed)
+    model._initialize(None, {"seed": seed})
+    start = dict(
+        W0=np.array(model.asignatures.X),
+        a0=np.array(model.asignatures.obs["scalings"].values, dtype=float),
+        b0=np.array(adata.obs["scalings"].values, dtype=float),
+        L0=np.array(model.asignatures.obsm["embeddings"]),
+        U0=np.array(adata.obsm["embeddings"]),
+        var0=float(model.variance),
+    )
+    model2 = sal.models.CorrNMFDet(**kw)
+    adata2 = _adata()
+    np.random.seed(seed)
+    model2.fit(adata2, init_kwargs={"seed": seed})
+    np.savez_compressed(
+        os.path.join(OUT, f"{tag}.npz"),
+        **start,
+        history=np.array(model2.history["objective_function"]),
+        W=np.array(model2.asignatures.X),
+        a=np.array(model2.asignatures.obs["scalings"].values, dtype=float),
+        b=np.array(adata2.obs["scalings"].values, dtype=float),
+        L=np.array(model2.asignatures.obsm["embeddings"]),
+        U=np.array(adata2.obsm["embeddings"]),
+        H=np.array(adata2.obsm["exposures"]),
+        var=float(model2.variance),
+        k=k, dim=dim, seed=seed, n_iter=n_iter,
+    )
+    print(f"{tag}: ELBO history {model2.history['objective_function']}")
+
+
+def init_cases(tag="init_pcawg"):
+    """W0 / H0 of the live reference's ``initialize_mat`` for every initialisation method (bit-for-bit targets of
+    salamander_b200.initialization)."""
+    import importlib
+
+    sal = rl.load_package()
+    ref_init = importlib.import_module(sal.__name__ + ".initialization.initialize")
+    X = np.asarray(_adata().X, dtype=float).clip(np.finfo(np.float32).eps)
+    out = {}
+    for method, seed in (("random", 3), ("nndsvd", 2), ("nndsvda", 2), ("nndsvdar", 2), ("flat", None), ("separableNMF", 5)):
+        for k in (3, 7):
+            kw = {} if seed is None else {"seed": seed}
+            W0, H0 = ref_init.initialize_mat(X.copy(), k, method, **kw)
+            out[f"{method}_k{k}_W"], out[f"{method}_k{k}_H"] = W0, H0
+            out[f"{method}_k{k}_seed"] = -1 if seed is None else seed
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", f"{tag}.npz"), **out)
+    print(f"{tag}: {len(out) // 3} initialisations")
+
+
 def main():
     if not rl.available():
         raise SystemExit("live reference not mounted; nothing to do")
@@ -116,6 +173,10 @@ def main():
     # C2: MvNMF k=10 on the same data, lam = delta = 1
     mvnmf_case("mvnmf_pcawg_k10_seed0", 10, 0, min_iterations=600, max_iterations=600)
     mvnmf_case("mvnmf_pcawg_k3_lam50", 3, 3, lam=50.0, delta=0.5, min_iterations=300, max_iterations=300)
+    # CorrNMFDet (config 4's model on the PCAWG SBS counts): whole iterations incl. both Newton-CG embedding updates
+    corrnmf_case("corrnmf_pcawg_k4_dim3_seed3", 4, 3, 3, 6)
+    corrnmf_case("corrnmf_pcawg_k6_dim2_seed8", 6, 2, 8, 4)
+    init_cases()
 
 
 if __name__ == "__main__":

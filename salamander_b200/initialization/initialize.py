@@ -13,7 +13,7 @@ from typing import Any
 import numpy as np
 
 from .._anndata import AnnData, concat
-from ..utils import EPSILON, dict_checker, normalize_WH, shape_checker, type_checker, value_checker
+from ..utils import EPSILON, column_sums_sequential, dict_checker, normalize_WH, shape_checker, type_checker, value_checker
 from .methods import (
     _INIT_METHODS,
     init_custom,
@@ -79,7 +79,7 @@ def initialize_mat(data_mat, n_signatures, method="nndsvd", given_signatures_mat
     if _defer is not None and (
         (method == "custom" and expo.size >= DEFER_MIN_SIZE) or (method == "random" and init_device is not None)
     ):
-        scale = np.sum(sigs, axis=1)
+        scale = column_sums_sequential(sigs.T)  # same summation order as normalize_WH
         _defer["exposure_scale"] = scale
         return (sigs / scale[:, None]).clip(EPSILON), expo
     W, H = normalize_WH(sigs.T, expo.T)

@@ -48,8 +48,18 @@ def normalize_WH(W: np.ndarray, H: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
     The per-iteration use inside MvNMF's line search runs on the device
     (sal_mvnmf_trial + the h_scale argument of sal_klnmf_pass).
     """
-    s = np.sum(W, axis=0)
+    # the reference's normalize_WH is numba-compiled: its np.sum(axis=0) adds the rows one after the other, whereas numpy
+    # sums pairwise -- the last bit can differ.  Same order here, so a seed gives the reference's W0, H0 bit for bit.
+    s = column_sums_sequential(W)
     return W / s, H * s[:, None]
+
+
+def column_sums_sequential(W: np.ndarray) -> np.ndarray:
+    """``sum_v W[v, j]`` with the rows added one after the other (the order of numba's ``np.sum(W, axis=0)``)."""
+    s = np.zeros(W.shape[1], dtype=np.result_type(W.dtype, np.float64))
+    for row in np.asarray(W):
+        s += row
+    return s
 
 
 def match_to_catalog(signatures: pd.DataFrame, catalog: pd.DataFrame, metric: str = "cosine") -> pd.DataFrame:

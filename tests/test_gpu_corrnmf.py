@@ -200,3 +200,26 @@ def test_iterations_match_the_oracle_on_synthetic_counts():
     assert np.allclose(model.asignatures.obsm["embeddings"], L, rtol=1e-5, atol=1e-8)
     assert np.allclose(model.adata.obsm["embeddings"], U, rtol=1e-5, atol=1e-7)
     assert np.isclose(model.variance, var, rtol=1e-7)
+
+
+@pytest.mark.parametrize("tag", ["corrnmf_pcawg_k4_dim3_seed3", "corrnmf_pcawg_k6_dim2_seed8"])
+def test_fit_matches_the_live_reference_trajectory(tag):
+    """``CorrNMFDet.fit`` against whole iterations of the LIVE reference (tests/golden/trajectories, written by
+    oracle/make_golden.py::corrnmf_case in the build container): same seed, same start, ELBO after every iteration within
+    1e-8, final parameters within the Newton-CG tolerances."""
+    z = np.load(os.path.join(ROOT, "tests", "golden", "trajectories", f"{tag}.npz"))
+    k, dim, seed, n_iter = int(z["k"]), int(z["dim"]), int(z["seed"]), int(z["n_iter"])
+    cnt = pd.read_csv(os.path.join(ROOT, "salamander_b200", "data", "pcawg_breast_sbs.csv"), index_col=0).T
+    model = sal.models.CorrNMFDet(n_signatures=k, dim_embeddings=dim, init_method="random", min_iterations=n_iter, max_iterations=n_iter,
+                                  conv_test_freq=1)
+    np.random.seed(seed)
+    model.fit(AnnData(cnt), init_kwargs={"seed": seed})
+    hist = np.array(model.history["objective_function"])
+    assert hist.shape == z["history"].shape
+    assert np.allclose(hist, z["history"], rtol=1e-8, atol=0), (hist, z["history"])
+    assert np.allclose(model.asignatures.X, z["W"], rtol=1e-6, atol=1e-12)
+    assert np.allclose(model.asignatures.obs["scalings"].values, z["a"], rtol=1e-6)
+    assert np.allclose(model.adata.obs["scalings"].values, z["b"], rtol=1e-6)
+    assert np.allclose(model.asignatures.obsm["embeddings"], z["L"], rtol=1e-5, atol=1e-8)
+    assert np.allclose(model.adata.obsm["embeddings"], z["U"], rtol=1e-5, atol=1e-7)
+    assert np.isclose(model.variance, float(z["var"]), rtol=1e-7)

@@ -245,3 +245,25 @@ def test_init_device_routing_and_sweep_containers():
     assert list(shallow.obs_names) == list(ad.obs_names) and list(shallow.var_names) == list(ad.var_names)
     shallow.obsm["exposures"] = np.zeros((50, 3))
     assert "exposures" not in ad.obsm
+
+
+def test_initialisation_is_bit_identical_to_the_live_reference():
+    """tests/golden/init_pcawg.npz: W0 / H0 of the reference's own ``initialize_mat`` (run in the build container by
+    oracle/make_golden.py::init_cases) for every method -- ours must be equal bit for bit, including the numba summation
+    order of normalize_WH."""
+    import pandas as pd
+
+    from salamander_b200.initialization.initialize import initialize_mat
+
+    z = np.load(os.path.join(ROOT, "tests", "golden", "init_pcawg.npz"))
+    X = pd.read_csv(os.path.join(ROOT, "salamander_b200", "data", "pcawg_breast_sbs.csv"), index_col=0).T.values.astype(float)
+    X = X.clip(EPSILON)
+    keys = sorted(k[:-2] for k in z.files if k.endswith("_W"))
+    assert len(keys) == 12
+    for key in keys:
+        method, k = key.rsplit("_k", 1)
+        seed = int(z[f"{key}_seed"])
+        kw = {} if seed < 0 else {"seed": seed}
+        W0, H0 = initialize_mat(X.copy(), int(k), method, **kw)
+        assert np.array_equal(W0, z[f"{key}_W"]), key
+        assert np.array_equal(H0, z[f"{key}_H"]), key

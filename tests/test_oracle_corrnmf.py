@@ -122,3 +122,39 @@ def test_mm_updates(mm, solver):
         assert np.allclose(klnmf.update_W(md["X"].T, md["W"].T, md["H"].T).T, ld(f"model{n}_signatures_mat_updated").T)
     assert np.allclose(M.update_sample_embeddings(mods, auxs, U, var, solver), ld("sample_embeddings_updated").T)
     assert np.allclose(M.update_variance(mods, U), ld("variance_updated"))
+
+
+@pytest.mark.parametrize("tag", ["corrnmf_pcawg_k4_dim3_seed3", "corrnmf_pcawg_k6_dim2_seed8"])
+def test_oracle_reproduces_live_reference_corrnmf_trajectory(tag):
+    """Whole CorrNMFDet iterations of the LIVE reference (oracle/make_golden.py::corrnmf_case, run in the build container):
+    our initialisation gives the reference's starting point for the seed, and the oracle's iterations reproduce its ELBO
+    history and final parameters."""
+    import os
+
+    import pandas as pd
+    from conftest import ROOT
+
+    import salamander_b200 as sal
+    from oracle import EPSILON
+    from salamander_b200.initialization.initialize import initialize_corrnmf
+
+    z = np.load(os.path.join(ROOT, "tests", "golden", "trajectories", f"{tag}.npz"))
+    k, dim, seed, n_iter = int(z["k"]), int(z["dim"]), int(z["seed"]), int(z["n_iter"])
+    cnt = pd.read_csv(os.path.join(ROOT, "salamander_b200", "data", "pcawg_breast_sbs.csv"), index_col=0).T
+    adata = sal.AnnData(cnt)
+    adata.X = np.asarray(adata.X, dtype=float).clip(EPSILON)
+    np.random.seed(seed)
+    asig, var0 = initialize_corrnmf(adata, k, dim, "random", None, seed=seed)
+    assert np.array_equal(np.asarray(asig.X), z["W0"])
+    assert np.array_equal(np.asarray(asig.obsm["embeddings"]), z["L0"]) and np.array_equal(np.asarray(adata.obsm["embeddings"]), z["U0"])
+    assert np.array_equal(np.asarray(asig.obs["scalings"].values, dtype=float), z["a0"]) and float(var0) == float(z["var0"])
+    X = np.asarray(adata.X, dtype=float)
+    W, a, b, L, U, var = z["W0"].copy(), z["a0"].copy(), z["b0"].copy(), z["L0"].copy(), z["U0"].copy(), float(z["var0"])
+    hist = []
+    for _ in range(n_iter):
+        W, a, b, L, U, var, H = corrnmf.update_parameters(X, W, a, b, L, U, var)
+        hist.append(corrnmf.elbo(X, W, H, L, U, var))
+    assert np.allclose(hist, z["history"], rtol=1e-9, atol=0), (hist, z["history"])
+    assert np.allclose(W, z["W"], rtol=1e-7, atol=1e-14) and np.allclose(a, z["a"], rtol=1e-7) and np.allclose(b, z["b"], rtol=1e-7)
+    assert np.allclose(L, z["L"], rtol=1e-6, atol=1e-9) and np.allclose(U, z["U"], rtol=1e-6, atol=1e-9)
+    assert np.isclose(var, float(z["var"]), rtol=1e-9)
