@@ -130,6 +130,45 @@ def corrnmf_case(tag, k, dim, seed, n_iter):
     print(f"{tag}: ELBO history {model2.history['objective_function']}")
 
 
+def mmcorrnmf_case(tag, ns, dim, seed, n_iter):
+    """MultimodalCorrNMF of the live reference on the three PCAWG breast modalities (counts clipped to EPSILON first: the
+    multimodal model does not clip and some samples have no SV at all): start state and ``n_iter`` whole iterations."""
+    sal = rl.load_package()
+    eps = float(np.finfo(np.float32).eps)
+
+    def mdata():
+        mods = {}
+        for name in ("sbs", "indel", "sv"):
+            df = pd.read_csv(os.path.join(DATA, f"pcawg_breast_{name}.csv"), index_col=0).T.astype(float).clip(lower=eps)
+            mods[name] = rl.RefAnnData(df)
+        return rl.RefMuData(mods)
+
+    kw = dict(ns_signatures=ns, dim_embeddings=dim, init_method="random", min_iterations=n_iter, max_iterations=n_iter, conv_test_freq=1)
+    model = sal.models.MultimodalCorrNMF(**kw)
+    md0 = mdata()
+    model._setup_mdata(md0)
+    np.random.seed(seed)
+    model._initialize(None, {"seed": seed})
+    out = {"U0": np.array(md0.obsm["embeddings"]), "var0": float(model.variance)}
+    for name in model.mod_names:
+        a_, s_ = md0[name], model.asignatures[name]
+        out[f"{name}_W0"], out[f"{name}_L0"] = np.array(s_.X), np.array(s_.obsm["embeddings"])
+        out[f"{name}_a0"] = np.array(s_.obs["scalings"].values, dtype=float)
+        out[f"{name}_b0"] = np.array(a_.obs["scalings"].values, dtype=float)
+    model2 = sal.models.MultimodalCorrNMF(**kw)
+    md1 = mdata()
+    np.random.seed(seed)
+    model2.fit(md1, init_kwargs={"seed": seed})
+    out.update(history=np.array(model2.history["objective_function"]), U=np.array(md1.obsm["embeddings"]), var=float(model2.variance))
+    for name in model2.mod_names:
+        a_, s_ = md1[name], model2.asignatures[name]
+        out[f"{name}_W"], out[f"{name}_L"] = np.array(s_.X), np.array(s_.obsm["embeddings"])
+        out[f"{name}_a"] = np.array(s_.obs["scalings"].values, dtype=float)
+        out[f"{name}_b"] = np.array(a_.obs["scalings"].values, dtype=float)
+    np.savez_compressed(os.path.join(OUT, f"{tag}.npz"), ns=np.array(ns), dim=dim, seed=seed, n_iter=n_iter, **out)
+    print(f"{tag}: ELBO history {model2.history['objective_function']}")
+
+
 def init_cases(tag="init_pcawg"):
     """W0 / H0 of the live reference's ``initialize_mat`` for every initialisation method (bit-for-bit targets of
     salamander_b200.initialization)."""
@@ -176,6 +215,7 @@ def main():
     # CorrNMFDet (config 4's model on the PCAWG SBS counts): whole iterations incl. both Newton-CG embedding updates
     corrnmf_case("corrnmf_pcawg_k4_dim3_seed3", 4, 3, 3, 6)
     corrnmf_case("corrnmf_pcawg_k6_dim2_seed8", 6, 2, 8, 4)
+    mmcorrnmf_case("mmcorrnmf_pcawg_ns322_dim2_seed5", [3, 2, 2], 2, 5, 4)
     init_cases()
 
 

@@ -95,6 +95,34 @@ def _concat(adatas, join="outer"):
     return out
 
 
+class RefMuData:
+    """The part of ``mudata.MuData`` the reference's MultimodalCorrNMF touches: ``mod`` (name -> AnnData), ``n_mod``,
+    ``n_obs``, ``obs_names``, ``obs``, ``obsm``, ``obsp``, ``update()`` and item access by modality name."""
+
+    def __init__(self, mods):
+        import pandas as pd
+
+        self.mod = dict(mods)
+        first = next(iter(self.mod.values()))
+        self.obs_names = first.obs_names
+        self.obs = pd.DataFrame(index=self.obs_names)
+        self.obsm, self.obsp = {}, {}
+
+    @property
+    def n_mod(self):
+        return len(self.mod)
+
+    @property
+    def n_obs(self):
+        return len(self.obs_names)
+
+    def update(self):
+        return None
+
+    def __getitem__(self, name):
+        return self.mod[name]
+
+
 _loaded = {}
 
 
@@ -134,6 +162,7 @@ def load_package():
         sys.modules.setdefault(name, MagicMock())
     if _SRC not in sys.path:
         sys.path.insert(0, _SRC)
+    sys.modules["mudata"].MuData = RefMuData
     pkg = importlib.import_module("salamander")
     _loaded["pkg"] = pkg
     return pkg

@@ -200,3 +200,29 @@ def test_iterations_match_the_oracle_on_pcawg_modalities():
         assert np.allclose(model.mdata[name].obs["scalings"].values, md["b"], rtol=1e-6)
     assert np.allclose(model.mdata.obsm["embeddings"], U, rtol=1e-5, atol=1e-7)
     assert np.isclose(model.variance, var, rtol=1e-7)
+
+
+def test_fit_matches_the_live_reference_trajectory():
+    """``MultimodalCorrNMF.fit`` against whole iterations of the LIVE reference on the three PCAWG modalities
+    (tests/golden/trajectories/mmcorrnmf_pcawg_ns322_dim2_seed5.npz, oracle/make_golden.py::mmcorrnmf_case)."""
+    z = np.load(os.path.join(ROOT, "tests", "golden", "trajectories", "mmcorrnmf_pcawg_ns322_dim2_seed5.npz"))
+    ns, dim, seed, n_iter = [int(v) for v in z["ns"]], int(z["dim"]), int(z["seed"]), int(z["n_iter"])
+    data = os.path.join(ROOT, "salamander_b200", "data")
+    frames = {
+        name: pd.read_csv(os.path.join(data, f"pcawg_breast_{name}.csv"), index_col=0).T.astype(float).clip(lower=1.1920928955078125e-07)
+        for name in ("sbs", "indel", "sv")
+    }
+    mdata = MuData({name: AnnData(df) for name, df in frames.items()})
+    model = sal.models.MultimodalCorrNMF(ns_signatures=ns, dim_embeddings=dim, init_method="random", min_iterations=n_iter,
+                                         max_iterations=n_iter, conv_test_freq=1)
+    np.random.seed(seed)
+    model.fit(mdata, init_kwargs={"seed": seed})
+    hist = np.array(model.history["objective_function"])
+    assert hist.shape == z["history"].shape
+    assert np.allclose(hist, z["history"], rtol=1e-8, atol=0), (hist, z["history"])
+    for name in ("sbs", "indel", "sv"):
+        assert np.allclose(model.asignatures[name].X, z[f"{name}_W"], rtol=1e-6, atol=1e-12), name
+        assert np.allclose(model.asignatures[name].obsm["embeddings"], z[f"{name}_L"], rtol=1e-5, atol=1e-8), name
+        assert np.allclose(model.mdata[name].obs["scalings"].values, z[f"{name}_b"], rtol=1e-6), name
+    assert np.allclose(model.mdata.obsm["embeddings"], z["U"], rtol=1e-5, atol=1e-7)
+    assert np.isclose(model.variance, float(z["var"]), rtol=1e-7)

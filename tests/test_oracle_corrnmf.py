@@ -158,3 +158,57 @@ def test_oracle_reproduces_live_reference_corrnmf_trajectory(tag):
     assert np.allclose(W, z["W"], rtol=1e-7, atol=1e-14) and np.allclose(a, z["a"], rtol=1e-7) and np.allclose(b, z["b"], rtol=1e-7)
     assert np.allclose(L, z["L"], rtol=1e-6, atol=1e-9) and np.allclose(U, z["U"], rtol=1e-6, atol=1e-9)
     assert np.isclose(var, float(z["var"]), rtol=1e-9)
+
+
+def _mm_frames():
+    import os
+
+    import pandas as pd
+    from conftest import ROOT
+
+    from oracle import EPSILON
+
+    data = os.path.join(ROOT, "salamander_b200", "data")
+    return {name: pd.read_csv(os.path.join(data, f"pcawg_breast_{name}.csv"), index_col=0).T.astype(float).clip(lower=EPSILON)
+            for name in ("sbs", "indel", "sv")}
+
+
+def test_oracle_reproduces_live_reference_mmcorrnmf_trajectory():
+    """Whole MultimodalCorrNMF iterations of the LIVE reference on the three PCAWG modalities
+    (oracle/make_golden.py::mmcorrnmf_case): our initialisation gives the reference's start for the seed, the oracle's
+    iterations its ELBO history and final parameters."""
+    import os
+
+    from conftest import ROOT
+
+    import salamander_b200 as sal
+    from oracle import mmcorrnmf as mm
+
+    z = np.load(os.path.join(ROOT, "tests", "golden", "trajectories", "mmcorrnmf_pcawg_ns322_dim2_seed5.npz"))
+    ns, dim, seed, n_iter = [int(v) for v in z["ns"]], int(z["dim"]), int(z["seed"]), int(z["n_iter"])
+    frames = _mm_frames()
+    mdata = sal.MuData({name: sal.AnnData(df) for name, df in frames.items()})
+    from salamander_b200.initialization.initialize import initialize_mmcorrnmf
+
+    np.random.seed(seed)
+    asignatures, var_init = initialize_mmcorrnmf(mdata, ns, dim, "random", None, seed=seed)
+    assert np.array_equal(np.asarray(mdata.obsm["embeddings"]), z["U0"]) and float(var_init) == float(z["var0"])
+    mods = []
+    for name in ("sbs", "indel", "sv"):
+        asig = asignatures[name]
+        assert np.array_equal(np.asarray(asig.X), z[f"{name}_W0"]), name
+        assert np.array_equal(np.asarray(asig.obsm["embeddings"]), z[f"{name}_L0"]), name
+        mods.append(dict(X=np.asarray(frames[name].values, dtype=float), W=z[f"{name}_W0"].copy(), a=z[f"{name}_a0"].copy(),
+                         b=z[f"{name}_b0"].copy(), L=z[f"{name}_L0"].copy()))
+    U, var = z["U0"].copy(), float(z["var0"])
+    mm.compute_exposures(mods, U)
+    hist = []
+    for _ in range(n_iter):
+        U, var = mm.update_parameters(mods, U, var)
+        hist.append(mm.elbo(mods, U, var))
+    assert np.allclose(hist, z["history"], rtol=1e-9, atol=0), (hist, z["history"])
+    for md, name in zip(mods, ("sbs", "indel", "sv")):
+        assert np.allclose(md["W"], z[f"{name}_W"], rtol=1e-7, atol=1e-14), name
+        assert np.allclose(md["L"], z[f"{name}_L"], rtol=1e-6, atol=1e-9), name
+        assert np.allclose(md["b"], z[f"{name}_b"], rtol=1e-7), name
+    assert np.allclose(U, z["U"], rtol=1e-6, atol=1e-9) and np.isclose(var, float(z["var"]), rtol=1e-9)
