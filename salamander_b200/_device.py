@@ -302,3 +302,8 @@ class Workspace:
             ),
             "sal_mvnmf_trial",
         )
+
+
+def trim_device_scratch() -> None:
+    """Free the workspace scratch buffers that finished fits left on the library's per-device free list (sal_trim_scratch)."""
+    _lib.check(_lib.load().sal_trim_scratch(), "sal_trim_scratch")
