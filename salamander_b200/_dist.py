@@ -59,6 +59,30 @@ def broadcast_numpy(arr: np.ndarray, device: torch.device, src: int = 0) -> np.n
     return t.cpu().numpy()
 
 
+def exchange_owned_rows(t: torch.Tensor, lo: int, hi: int) -> torch.Tensor:
+    """Every rank has written rows [lo, hi) of the replicated tensor ``t`` (its share of the signatures); make all rows
+    current everywhere, in place.  Done as a sum of copies that are zero outside the owner's rows: x + 0 is exact, so the
+    replicas stay bit-identical (multi-GPU CorrNMF signature embeddings)."""
+    if world()[1] == 1:
+        return t
+    mine = torch.zeros_like(t)
+    mine[lo:hi] = t[lo:hi]
+    allreduce_sum_(mine)
+    t.copy_(mine)
+    return t
+
+
+def allreduce_sum_counting_replicated_once(t: torch.Tensor, replicated: slice) -> torch.Tensor:
+    """In-place sum over ranks of a vector whose entries in ``replicated`` are already identical on every rank (computed
+    from replicated parameters) and must therefore be counted once, while the other entries are per-shard partial sums."""
+    rank, ws = world()
+    if ws == 1:
+        return t
+    if rank != 0:
+        t[replicated] = 0
+    return allreduce_sum_(t)
+
+
 class PeerExchange:
     """Symmetric (peer-mapped) exchange buffer for the one-shot all-reduce fused into the reduction kernel
     (sal_klnmf_update_p2p): every rank allocates ``nbytes`` of zeroed symmetric memory, the ranks rendezvous and each

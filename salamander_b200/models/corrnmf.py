@@ -105,9 +105,7 @@ class CorrState:
         """[sum L^2, sum U^2 over all samples, sum lnGamma(1 + X) over all samples]"""
         self.call("sal_corrnmf_norms", self.L, self.U, self.m, self.X if with_lgamma else None, self.norms)
         if self.world > 1:
-            if self.rank != 0:
-                self.norms[0] = 0.0  # L is replicated: count it once
-            self.allreduce(self.norms)
+            _dist.allreduce_sum_counting_replicated_once(self.norms, slice(0, 1))  # L is replicated: count it once
         return self.norms.tolist()
 
     # -- plumbing ------------------------------------------------------------------------------
@@ -277,10 +275,7 @@ class CorrNMFDet(CorrNMF):
                 "sal_corrnmf_signature_embeddings_range", aux_all, st.a, b_all, st.L, U_all, st.m, float(self.variance),
                 j0, j1 - j0, ws=st.ws_full,
             )
-            L_new = torch.zeros_like(st.L)
-            L_new[j0:j1] = st.L[j0:j1]
-            st.allreduce(L_new)
-            st.L.copy_(L_new)
+            _dist.exchange_owned_rows(st.L, j0, j1)
 
     def update_sample_embeddings(self, aux=None) -> None:
         with self._resident() as st:

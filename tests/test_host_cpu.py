@@ -113,6 +113,17 @@ W = rng.dirichlet(np.ones(5), size=2); H = rng.gamma(2.0, 5.0, size=(n, 2))
 num = torch.from_numpy(H[lo:hi].T @ (X[lo:hi] / (H[lo:hi] @ W)))
 _dist.allreduce_sum_(num)
 assert np.allclose(num.numpy(), H.T @ (X / (H @ W)), rtol=1e-12)
+# multi-GPU CorrNMF: signatures are dealt to the ranks for the embedding Newton-CG, the rows are exchanged afterwards
+k = 5
+j0, j1 = _dist.shard_bounds(k, world, rank)
+L = torch.full((k, 3), -1.0, dtype=torch.float64)
+L[j0:j1] = torch.arange(j0, j1, dtype=torch.float64)[:, None] + 0.125 * torch.arange(3, dtype=torch.float64)[None, :]
+_dist.exchange_owned_rows(L, j0, j1)
+assert torch.equal(L, torch.arange(k, dtype=torch.float64)[:, None] + 0.125 * torch.arange(3, dtype=torch.float64)[None, :]), (rank, L)
+# [sum L^2 (replicated, counted once), sum U^2 over this rank's samples, sum lnGamma over this rank's samples]
+norms = torch.tensor([7.0, float(rank + 1), 10.0 * (rank + 1)], dtype=torch.float64)
+_dist.allreduce_sum_counting_replicated_once(norms, slice(0, 1))
+assert torch.equal(norms, torch.tensor([7.0, 3.0, 30.0], dtype=torch.float64)), (rank, norms)
 dist.destroy_process_group()
 print("ok", rank)
 """
