@@ -278,3 +278,12 @@ def test_initialisation_is_bit_identical_to_the_live_reference():
         W0, H0 = initialize_mat(X.copy(), int(k), method, **kw)
         assert np.array_equal(W0, z[f"{key}_W"]), key
         assert np.array_equal(H0, z[f"{key}_H"]), key
+
+
+def test_integration_doc_lists_every_abi_symbol():
+    """INTEGRATION.md maps each entry point of include/salamander_b200.h to the reference function it replaces."""
+    hdr = open(os.path.join(ROOT, "include", "salamander_b200.h")).read()
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    symbols = sorted(set(re.findall(r"\b(sal_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(symbols) >= 30
+    assert [s for s in symbols if s not in doc] == []
