@@ -144,6 +144,36 @@ int sal_klnmf_update_p2p(sal_handle_t h, const void* X, const void* W_in, void* 
 size_t sal_p2p_exchange_bytes(int k, int n_ranks);
 
 /*
+ * A whole convergence-test period in ONE persistent launch: the body of the reference's fit loop
+ * (models/signature_nmf.py:361-380) -- `n_updates` joint multiplicative updates (update_WH,
+ * models/_utils_klnmf.py:281-361, unweighted) with the KL objective (kl_divergence, :11-55) of the incoming iterate of
+ * every `objective_every`-th update (0: never) fused into that update, and, with `final_objective`, one objective-only
+ * sweep over X after the last update (the value signature_nmf.py:365-380 evaluates at max_iterations):
+ *     (W_in, H_in) -> (W_out, H_out);  objectives[i] = KL before update i * objective_every;
+ *     objectives[ceil(n_updates / objective_every)] = KL of the final iterate (if asked for).
+ * fp32 handles in SAL_MATH_TF32 mode, V = 96, k <= 32 (sal_klnmf_period_supported).  The CTAs stay resident
+ * (cooperative launch) and exchange the per-CTA numerators through sequence-tagged words in global memory: no kernel
+ * boundary, no reduction kernel and no grid barrier between two updates; every CTA applies the W epilogue
+ * (_utils_klnmf.py:338-341) itself.  H_out also serves as the working copy of the exposures after the first update
+ * (H_out == H_in: in place); W_out may alias W_in.
+ * Several GPUs (n_ranks > 1, samples sharded as in sal_klnmf_update_p2p): every CTA exchanges ITS slice of the numerator
+ * with the peers over NVLink inside the same kernel (tagged 16-byte words pushed into the peers' receive buffers, summed
+ * in rank order: bit-identical W on all ranks); peer_buffers / p2p_state as for sal_klnmf_update_p2p (the tag counter in
+ * p2p_state[0] advances by the number of sweeps).  With n_ranks == 1 both may be null.
+ * sal_klnmf_period_emulated runs 1 or 2 "virtual ranks" (one handle, shard and receive buffer each) inside ONE launch on one
+ * GPU, so that the exchange protocol is testable without a second GPU (kernels that wait on one another must not be
+ * separate launches on one device).
+ */
+int sal_klnmf_period_supported(sal_handle_t h, int n_given, int n_ranks);
+int sal_klnmf_period(sal_handle_t h, const void* X, const void* W_in, void* W_out, const void* H_in, void* H_out, int n_given,
+                     int clip_given, int n_updates, int objective_every, int final_objective, double* objectives,
+                     const void* peer_buffers, void* p2p_state, int n_ranks, int rank, void* stream);
+int sal_klnmf_period_emulated(const sal_handle_t* handles, int n_virtual, const void* const* X, const void* const* W_in,
+                              void* const* W_out, const void* const* H_in, void* const* H_out, int n_given, int clip_given,
+                              int n_updates, int objective_every, int final_objective, double* const* objectives,
+                              const void* const* peer_tables, void* const* states, void* stream);
+
+/*
  * Small problems (D_local <= 256, state fits the shared memory of one SM -- BASELINE config 0, 96 x 192): n_iterations
  * joint updates (update_WH, _utils_klnmf.py:281-361, unweighted) in ONE launch of a single persistent CTA; *objective
  * (optional) receives the KL divergence of the INCOMING iterate (kl_divergence, :11-55).  W_out / H_out may alias the

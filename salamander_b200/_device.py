@@ -204,6 +204,39 @@ class Workspace:
             "sal_klnmf_update_p2p",
         )
 
+    def period_supported(self, n_given: int = 0, n_ranks: int = 1) -> bool:
+        return bool(self.lib.sal_klnmf_period_supported(self._h, int(n_given), int(n_ranks)))
+
+    def klnmf_period(self, X, W_in, W_out, H_in, H_out, n_given: int, clip_given: bool, n_updates: int, objective_every: int,
+                     final_objective: bool, objectives=None, peers=None, state=None, n_ranks: int = 1, rank: int = 0) -> None:
+        """``n_updates`` joint updates (+ fused / trailing objectives) in ONE persistent launch (sal_klnmf_period)."""
+        V, D, k = self.V, self.D, self.k
+        n_obj = (-(-int(n_updates) // int(objective_every)) if objective_every else 0) + int(bool(final_objective))
+        if n_obj and (objectives is None or objectives.numel() < n_obj):
+            raise ValueError(f"'objectives' has to hold {n_obj} doubles.")
+        _lib.check(
+            self.lib.sal_klnmf_period(
+                self._h,
+                self._ptr(X, D * V, "X"),
+                self._ptr(W_in, k * V, "W_in"),
+                self._ptr(W_out, k * V, "W_out"),
+                self._ptr(H_in, D * k, "H_in"),
+                self._ptr(H_out, D * k, "H_out"),
+                int(n_given),
+                int(bool(clip_given)),
+                int(n_updates),
+                int(objective_every),
+                int(bool(final_objective)),
+                None if objectives is None else self._ptr(objectives, objectives.numel(), "objectives", torch.float64),
+                None if peers is None else self._ptr(peers, n_ranks, "peers", torch.int64),
+                None if state is None else self._ptr(state, 2, "state", torch.int32),
+                int(n_ranks),
+                int(rank),
+                self._stream(),
+            ),
+            "sal_klnmf_period",
+        )
+
     def small_supported(self) -> bool:
         return bool(self.lib.sal_klnmf_small_supported(self._h))
 
@@ -302,6 +335,36 @@ class Workspace:
             ),
             "sal_mvnmf_trial",
         )
+
+
+def klnmf_period_emulated(workspaces, Xs, W_ins, W_outs, H_ins, H_outs, n_given: int, clip_given: bool, n_updates: int,
+                          objective_every: int, final_objective: bool, objectives, peer_tables, states) -> None:
+    """1 or 2 emulated ranks (one Workspace, shard and receive buffer each) inside ONE cooperative launch on one GPU
+    (sal_klnmf_period_emulated): the multi-GPU exchange protocol of the period kernel without a second GPU."""
+    n = len(workspaces)
+    lib = workspaces[0].lib
+
+    def arr(ptrs):
+        return (C.c_void_p * n)(*[p.value if isinstance(p, C.c_void_p) else p for p in ptrs])
+
+    hs = arr([w._h for w in workspaces])
+    cols = []
+    for name, ts, per_el in (("X", Xs, "DV"), ("W_in", W_ins, "kV"), ("W_out", W_outs, "kV"), ("H_in", H_ins, "Dk"), ("H_out", H_outs, "Dk")):
+        ptrs = []
+        for w, t in zip(workspaces, ts):
+            numel = {"DV": w.D * w.V, "kV": w.k * w.V, "Dk": w.D * w.k}[per_el]
+            ptrs.append(w._ptr(t, numel, name))
+        cols.append(arr(ptrs))
+    objs = arr([w._ptr(o, o.numel(), "objectives", torch.float64) for w, o in zip(workspaces, objectives)])
+    tabs = arr([w._ptr(t, n, "peer_table", torch.int64) for w, t in zip(workspaces, peer_tables)])
+    sts = arr([w._ptr(t, 2, "state", torch.int32) for w, t in zip(workspaces, states)])
+    _lib.check(
+        lib.sal_klnmf_period_emulated(
+            hs, n, cols[0], cols[1], cols[2], cols[3], cols[4], int(n_given), int(bool(clip_given)), int(n_updates),
+            int(objective_every), int(bool(final_objective)), objs, tabs, sts, workspaces[0]._stream(),
+        ),
+        "sal_klnmf_period_emulated",
+    )
 
 
 def trim_device_scratch() -> None:

@@ -37,6 +37,9 @@ SYMBOLS = {
     "sal_klnmf_update": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "sal_klnmf_update_p2p": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "sal_p2p_exchange_bytes": (C.c_size_t, [_i, _i]),
+    "sal_klnmf_period_supported": (_i, [_vp, _i, _i]),
+    "sal_klnmf_period": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp]),
+    "sal_klnmf_period_emulated": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "sal_klnmf_small_supported": (_i, [_vp]),
     "sal_klnmf_small_updates": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),
     "sal_w_epilogue": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),

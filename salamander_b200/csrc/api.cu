@@ -72,6 +72,41 @@ static void scratch_give(int device, void* p) {
         if (b.ptr == p && b.device == device) b.in_use = false;
 }
 
+// Exchange buffers of the period kernel.  They hold sequence-tagged words; the tag counter is one device word per DEVICE,
+// shared by every handle and only ever increased (atomicMax by the kernels), and a buffer is zeroed when a handle takes it
+// from the free list (it may have held anything before), so a stale word can never carry a tag a later launch waits for.
+static unsigned int* g_period_seq[64] = {nullptr};
+
+int sal_period_scratch(sal_ctx* c, cudaStream_t st) {
+    if (c->period_partials) return 0;
+    const size_t nv = (size_t)SAL_KMAX * SAL_VMAX;
+    const size_t b_part = (size_t)2 * c->n_sm * nv * 8, b_sums = (size_t)2 * nv * 8 + 256, b_obj = (size_t)2 * c->n_sm * 16 + 512;
+    {
+        std::lock_guard<std::mutex> lock(g_scratch_mutex);
+        unsigned int*& seq = g_period_seq[c->device & 63];
+        if (!seq) {
+            SAL_CUDA(cudaMalloc(&seq, 64));
+            const unsigned int one = 1;
+            SAL_CUDA(cudaMemset(seq, 0, 64));
+            SAL_CUDA(cudaMemcpy(seq, &one, sizeof(one), cudaMemcpyHostToDevice));
+        }
+        c->period_seq = seq;
+    }
+    void* p = scratch_take(c->device, b_part);
+    void* s = scratch_take(c->device, b_sums);
+    void* o = scratch_take(c->device, b_obj);
+    if (!p || !s || !o) {
+        scratch_give(c->device, p), scratch_give(c->device, s), scratch_give(c->device, o);
+        sal_set_error("cudaMalloc of the period-kernel exchange buffers failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return (int)cudaErrorMemoryAllocation;
+    }
+    SAL_CUDA(cudaMemsetAsync(p, 0, b_part, st));
+    SAL_CUDA(cudaMemsetAsync(s, 0, b_sums, st));
+    SAL_CUDA(cudaMemsetAsync(o, 0, b_obj, st));
+    c->period_partials = p, c->period_sums = s, c->period_obj = o;
+    return 0;
+}
+
 bool sal_pdl_enabled() {
     static const bool on = [] {
         const char* e = getenv("SAL_B200_NO_PDL");
@@ -128,6 +163,8 @@ int sal_destroy(sal_handle_t h) {
     // everything that used them has to be complete -- the synchronisation cudaFree used to imply
     cudaDeviceSynchronize();
     scratch_give(h->device, h->partial_wnum), scratch_give(h->device, h->partial_obj), scratch_give(h->device, h->partial_hsum);
+    scratch_give(h->device, h->period_partials), scratch_give(h->device, h->period_sums), scratch_give(h->device, h->period_obj);
+    delete h->map_cache;
     if (h->norm_counter) cudaFree(h->norm_counter);
     if (h->ev) {
         for (cudaEvent_t e : *h->ev) cudaEventDestroy(e);
@@ -268,6 +305,68 @@ int sal_klnmf_update_p2p(sal_handle_t h, const void* X, const void* W_in, void* 
     cudaStream_t st = (cudaStream_t)stream;
     if (h->math != SAL_MATH_FMA && sal_pass_tf32_supported(h, a)) return sal_launch_pass_tf32(h, a, st);
     return sal_launch_pass_fma(h, a, st);
+}
+
+static int period_args(sal_handle_t h, PeriodArgs& a, const void* X, const void* W_in, void* W_out, const void* H_in, void* H_out,
+                       int n_given, int clip_given, int n_updates, int objective_every, int final_objective, double* objectives,
+                       const void* peer_buffers, void* p2p_state, int n_ranks, int rank) {
+    SAL_CHECK_ARG(h != nullptr, "handle is null");
+    SAL_CHECK_ARG(X && W_in && H_in, "X, W_in, H_in must be non-null");
+    SAL_CHECK_ARG(n_updates >= 0 && objective_every >= 0 && (n_updates > 0 || final_objective), "nothing to do");
+    SAL_CHECK_ARG(n_updates == 0 || (W_out && H_out), "updates need W_out and H_out");
+    SAL_CHECK_ARG(n_given >= 0 && n_given <= h->k, "n_given out of range");
+    SAL_CHECK_ARG((objective_every == 0 && !final_objective) || objectives, "objectives requested but the output array is null");
+    SAL_CHECK_ARG(n_ranks >= 1 && rank >= 0 && rank < n_ranks, "bad rank / n_ranks");
+    SAL_CHECK_ARG(n_ranks == 1 || (peer_buffers && p2p_state), "several ranks need the peer table and the shared tag counter");
+    a.X = X, a.W_in = W_in, a.H_in = H_in, a.W_out = W_out, a.H_out = H_out ? H_out : const_cast<void*>(H_in);
+    a.objectives = objectives, a.peers = n_ranks > 1 ? peer_buffers : nullptr, a.state = n_ranks > 1 ? p2p_state : nullptr;
+    a.n_updates = n_updates, a.obj_every = objective_every, a.final_obj = final_objective ? 1 : 0;
+    a.n_given = n_given, a.clip_given = clip_given, a.n_ranks = n_ranks, a.rank = rank;
+    if (!sal_period_supported(h, a)) {
+        sal_set_error("sal_klnmf_period: needs an fp32 handle in tf32 mode, V = 96, k <= 32, D_local >= %d (or TF32_ALWAYS), 16-byte aligned "
+                      "X / H, at least one signature to update and at most 8 ranks", (int)SAL_TF32_MIN_SAMPLES);
+        return SAL_EUNSUPPORTED;
+    }
+    return 0;
+}
+
+int sal_klnmf_period_supported(sal_handle_t h, int n_given, int n_ranks) {
+    if (!h) return 0;
+    PeriodArgs a = {};
+    a.n_given = n_given, a.n_ranks = n_ranks, a.n_updates = 1;
+    return sal_period_supported(h, a) ? 1 : 0;
+}
+
+int sal_klnmf_period(sal_handle_t h, const void* X, const void* W_in, void* W_out, const void* H_in, void* H_out, int n_given,
+                     int clip_given, int n_updates, int objective_every, int final_objective, double* objectives,
+                     const void* peer_buffers, void* p2p_state, int n_ranks, int rank, void* stream) {
+    PeriodArgs a;
+    if (int e = period_args(h, a, X, W_in, W_out, H_in, H_out, n_given, clip_given, n_updates, objective_every, final_objective,
+                            objectives, peer_buffers, p2p_state, n_ranks, rank))
+        return e;
+    SAL_CUDA(cudaSetDevice(h->device));
+    h->x_dirty = 0;
+    sal_ctx* cs[1] = {h};
+    return sal_launch_period(cs, 1, &a, (cudaStream_t)stream);
+}
+
+int sal_klnmf_period_emulated(const sal_handle_t* hs, int n_virtual, const void* const* X, const void* const* W_in, void* const* W_out,
+                              const void* const* H_in, void* const* H_out, int n_given, int clip_given, int n_updates,
+                              int objective_every, int final_objective, double* const* objectives,
+                              const void* const* peer_tables, void* const* states, void* stream) {
+    SAL_CHECK_ARG(hs && n_virtual >= 1 && n_virtual <= 2, "1 or 2 emulated ranks");
+    SAL_CHECK_ARG(X && W_in && W_out && H_in && H_out && objectives && peer_tables && states, "null argument array");
+    PeriodArgs as[2];
+    sal_ctx* cs[2];
+    for (int v = 0; v < n_virtual; ++v) {
+        if (int e = period_args(hs[v], as[v], X[v], W_in[v], W_out[v], H_in[v], H_out[v], n_given, clip_given, n_updates,
+                                objective_every, final_objective, objectives[v], peer_tables[v], states[v], n_virtual, v))
+            return e;
+        cs[v] = hs[v];
+        SAL_CHECK_ARG(hs[v]->device == hs[0]->device && hs[v]->k == hs[0]->k && hs[v]->math == hs[0]->math, "emulated ranks must share device, k and math mode");
+    }
+    SAL_CUDA(cudaSetDevice(hs[0]->device));
+    return sal_launch_period(cs, n_virtual, as, (cudaStream_t)stream);
 }
 
 size_t sal_p2p_exchange_bytes(int k, int n_ranks) { return (size_t)2 * n_ranks * (k + 1) * SAL_VMAX * 16; }

@@ -29,7 +29,24 @@ struct sal_ctx {
     int timing;                                       // sal_set_timing
     std::vector<cudaEvent_t>* ev;                     // event pairs around the UPDATE_H | WNUM pass kernels
     size_t ev_used;
+    // period kernel (klnmf_period_tf32.cu): sequence-tagged exchange buffers, taken from the scratch list at first use
+    void* period_partials;      // uint2 [2][n_sm][SAL_KMAX * SAL_VMAX]
+    void* period_sums;          // uint2 [2][SAL_KMAX * SAL_VMAX]
+    void* period_obj;           // uint4 [2][n_sm]
+    unsigned int* period_seq;   // per-DEVICE tag counter (shared by all handles of the device, only ever increases)
+    std::vector<struct sal_map_entry>* map_cache;     // tensor maps by (pointer, kind): encoding one costs ~10 us of host time
+    int x_dirty;                // X was written by a kernel of this handle (sal_clip_counts) and no pass has run since
 };
+
+struct sal_map_entry {
+    const void* ptr;
+    int kind;  // 0: X [D][96] swizzled boxes; 1: H [D][k] rows (2-D) ; 2: H as [tile][k][128] (3-D, k % 4 != 0)
+    alignas(64) unsigned char map[128];
+};
+// Tensor map of kind `kind` over `ptr` for this handle's (D, k), from the handle's cache (encoded on a miss).
+int sal_cached_map(sal_ctx* c, void* map_out, const void* ptr, int kind);
+// exchange buffers + tag counter of the period kernel, zeroed on the launch stream at first use
+int sal_period_scratch(sal_ctx* c, cudaStream_t st);
 
 // bracket a pass kernel with events when timing is on (no-ops otherwise)
 int sal_timing_begin(sal_ctx* c, int flags, cudaStream_t st);
@@ -123,6 +140,18 @@ int sal_launch_corrnmf_sample_embeddings(sal_ctx* c, const void* auxT, const voi
 int sal_launch_corrnmf_signature_embeddings(sal_ctx* c, const void* auxT, const void* a, const void* b, void* L, const void* U, int m,
                                             double variance, int sig_begin, int sig_count, cudaStream_t st);
 int sal_launch_corrnmf_norms(sal_ctx* c, const void* L, const void* U, int m, const void* X_or_null, double* out, cudaStream_t st);
+
+// ---- persistent period kernel (klnmf_period_tf32.cu) ------------------------------------------------------
+struct PeriodArgs {
+    const void *X, *W_in, *H_in;
+    void *W_out, *H_out;
+    double* objectives;   // [ceil(n_updates / obj_every) + final_obj]
+    const void* peers;    // device array [n_ranks] of receive buffers, or null (single rank)
+    void* state;          // device unsigned: tag counter shared with the peers, or null (the device's own counter)
+    int n_updates, obj_every, final_obj, n_given, clip_given, n_ranks, rank;
+};
+bool sal_period_supported(const sal_ctx* c, const PeriodArgs& a);
+int sal_launch_period(sal_ctx* const* cs, int n_virtual, const PeriodArgs* as, cudaStream_t st);
 
 // ---- small-problem persistent kernel (klnmf_small.cu) ----------------------------------------------------
 bool sal_small_supported(const sal_ctx* c);
