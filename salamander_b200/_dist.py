@@ -35,6 +35,16 @@ def allreduce_sum_(t: torch.Tensor) -> torch.Tensor:
     return t
 
 
+def all_ranks_agree(flag: bool, device: torch.device) -> bool:
+    """True iff ``flag`` is true on EVERY rank (all-reduce MIN): code paths whose kernels or collectives wait on the
+    peers must be chosen by all ranks together."""
+    if world()[1] == 1:
+        return bool(flag)
+    t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return bool(int(t.item()))
+
+
 def gather_rows(local: torch.Tensor, n_total: int) -> torch.Tensor:
     """All-gather row blocks laid out by ``shard_bounds`` into the full (n_total, ...) tensor on every rank."""
     rank, ws = world()

@@ -31,13 +31,18 @@
 
 namespace {
 
-constexpr int EPI0 = 128;           // first epilogue thread (warps 4 .. 11)
-constexpr int EPI_THREADS = 256;
-constexpr int PER_CHUNK = 64;       // values of a CTA's slice reduced per round
-constexpr int PER_MAX_RANKS = 8;    // one NVSwitch box
+// 12 warps = 3 warpgroups.  Warpgroup 0: warp 0 data movement (X loads, exposure loads and stores: one event loop), warp 1 MMA
+// issuer (+ TMEM allocation), warps 2 - 3 idle; warpgroups 1 and 2: the two epilogue warpgroups.  The register file is split
+// per SM sub-partition (3 warps each: 168 registers per thread at launch), which the epilogue's tile loop does not fit in --
+// so after the set-up warpgroup 0 gives registers back (setmaxnreg.dec) and the epilogue warpgroups take them (setmaxnreg.inc).
+constexpr int PER_THREADS = 384;
+constexpr int EW0 = 4;              // first epilogue warp
+constexpr int REGS_UTIL = 88, REGS_EPI = 208;  // 88 + 2 * 208 = 504 = 3 * 168: the pool is what the launch allocated
+constexpr int EPI0 = EW0 * 32;      // first epilogue thread
+constexpr int PER_MAX_RANKS = 8;    // one NVSwitch box (the exchange handles up to 32: one lane per peer)
 constexpr int PER_MAX_VIRTUAL = 2;
-constexpr int PER_EXTRA = 32 * 3 * 8 + 8 * 8 + 64;  // s_red [32][3], s_obj [8] (doubles) + slack, appended to the misc area
-constexpr int PER_WREG = 12;        // W elements a thread owns: 3 * KP8 / 8 warp-tasks of 32 features
+constexpr int PER_EXTRA = 2432;  // appended to the misc area: s_part [8][32] doubles (2048), s_tot [32] doubles (256), slack
+constexpr int PER_WREG = 12;        // W elements a thread owns: up to 4 signatures x 3 features
 // The owned W elements (full fp32) survive the tile loops in otherwise unused TMEM columns -- the tile loop has no
 // registers to spare (168 per thread at 384 threads): 16 columns per epilogue warpgroup, lane = the thread's own TMEM lane.
 constexpr uint32_t TM_WST = 416;
@@ -64,6 +69,17 @@ struct PeriodParams {
     int n_virtual, G, k, n_updates, obj_every, final_obj, n_given, clip_given, n_ranks;
 };
 
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {  // non-blocking
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void bar_epi() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 __device__ __forceinline__ uint2 ld_tag2(const uint2* p) {
@@ -130,14 +146,40 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
         : "memory");
 }
 
+// Batched polling: every word that does not carry the tag yet is re-requested in the SAME round, so a retry costs one memory
+// round trip for the whole batch instead of one per word (a thread that arrives early -- the usual case -- would otherwise walk
+// through its words one round trip at a time).  `pending` is a bit mask over the N slots; addr(z) gives slot z's address.
+template <int N, class Addr>
+__device__ __forceinline__ void poll_batch(uint2 (&w)[N], unsigned int pending, unsigned int tag, Addr addr) {
+    unsigned int spins = 0;
+    unsigned long long t0 = 0;
+    while (pending) {
+#pragma unroll
+        for (int z = 0; z < N; ++z)
+            if ((pending >> z) & 1u) w[z] = ld_tag2(addr(z));
+#pragma unroll
+        for (int z = 0; z < N; ++z)
+            if (((pending >> z) & 1u) && w[z].y == tag) pending &= ~(1u << z);
+        if (pending && (++spins & 255u) == 0) {
+            const unsigned long long now = global_ns();
+            if (t0 == 0) t0 = now;
+            if (now - t0 > SAL_WAIT_LIMIT_NS) __trap();
+        }
+    }
+}
+
 // timeline: slot s of update u, written by one thread of CTA 1 (or 0 when the grid has one CTA)
 constexpr int TL_SLOTS = 8;
 __device__ __forceinline__ void tl_stamp(unsigned long long* tl, bool on, int u, int s) {
     if (on) tl[u * TL_SLOTS + s] = global_ns();
 }
+// per-CTA stamps behind the timeline: [sweep][CTA][4] (0 own tiles done, 1 all MMAs retired, 2 slice published, 3 W epilogue done)
+__device__ __forceinline__ void cta_stamp(unsigned long long* tl, bool on, int U, int G, int u, int c, int s) {
+    if (on) tl[(U + 1) * TL_SLOTS + ((size_t)u * G + c) * 4 + s] = global_ns();
+}
 
 template <int KP8, bool GK>
-__global__ void __launch_bounds__(NTHREADS, 1) klnmf_period_tc_kernel(const __grid_constant__ PeriodParams P) {
+__global__ void __launch_bounds__(PER_THREADS, 1) klnmf_period_tc_kernel(const __grid_constant__ PeriodParams P) {
     extern __shared__ __align__(1024) unsigned char smem_dyn[];
     const uint32_t base = smem_u32(smem_dyn);
     if (base & 1023u) __trap();  // the swizzled TMA boxes need 1024-byte alignment
@@ -147,16 +189,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) klnmf_period_tc_kernel(const __gr
     const uint32_t sX = base, sHraw = base + q.off_hraw, sW1hi = base + q.off_w1hi, sW1lo = base + q.off_w1lo;
     const uint32_t sW2 = base + q.off_w2, sHT = base + q.off_sht, bars = base + q.off_bar;
     const int SHT_LBO = q.sht_lbo;
-    // barriers: full[3] empty[3] hready[2] whfull[2] rready[2] hnfull[2] shtfree done hfull[4] hempty[4] hout[4] hstored
+    // barriers: full[3] empty[3] hready[2] whfull[2] rready[2] hnfull[2] shtfree done hfull[4] hempty[4] hout[4] wn
     const uint32_t bar_full = bars, bar_empty = bars + 24, bar_hready = bars + 48, bar_whfull = bars + 64;
     const uint32_t bar_rready = bars + 80, bar_hnfull = bars + 96, bar_shtfree = bars + 112, bar_done = bars + 120;
-    const uint32_t bar_hfull = bars + 128, bar_hempty = bars + 160, bar_hout = bars + 192, bar_hstored = bars + 224;
+    const uint32_t bar_hfull = bars + 128, bar_hempty = bars + 160, bar_hout = bars + 192, bar_wn = bars + 224;
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_dyn + q.off_misc);
     double* s_obj = reinterpret_cast<double*>(smem_dyn + q.off_misc + 16);   // [8]
-    double* s_red = reinterpret_cast<double*>(smem_dyn + q.off_misc + 128);  // [32][3]
-    // reduction scratch: aliases the W operands of G1, which are dead between the last MMA of an update and the W epilogue
-    // that rewrites them completely (>= 6 KB: s_part / s_recv 4 KB, s_loc 512 B)
-    double* s_scr = reinterpret_cast<double*>(smem_dyn + q.off_w1hi);
+    double* s_part = reinterpret_cast<double*>(smem_dyn + q.off_misc + 128);        // [8][32] warp partials / receive staging
+    double* s_tot = reinterpret_cast<double*>(smem_dyn + q.off_misc + 128 + 2048);  // [32]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int G = P.G, vr = (int)blockIdx.x / G, c = (int)blockIdx.x - vr * G;
@@ -183,37 +223,40 @@ __global__ void __launch_bounds__(NTHREADS, 1) klnmf_period_tc_kernel(const __gr
         }
         mbar_init(bar_shtfree, 1);
         mbar_init(bar_done, 1);
-        mbar_init(bar_hstored, 1);
+        mbar_init(bar_wn, 1);
         for (int i = 0; i < NH; ++i) mbar_init(bar_hfull + 8 * i, 1), mbar_init(bar_hempty + 8 * i, 1), mbar_init(bar_hout + 8 * i, 128);
         fence_barrier_init();
     }
-    if (warp == 2) {
+    if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)),
                      "r"(TM_COLS)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    for (int i = tid; i < q.sht / 4; i += NTHREADS) sts32(sHT + 4 * i, 0.f);
-    // W of the incoming iterate: every epilogue warp owns the warp-tasks t = ew + 8 r, task t = (signature t / 3, features
-    // 32 (t % 3) .. + 31), and keeps its elements in registers for the whole period
-    const int e = tid - EPI0, ew = e >> 5;
+    for (int i = tid; i < q.sht / 4; i += PER_THREADS) sts32(sHT + 4 * i, 0.f);
+    // W of the incoming iterate: epilogue warp ew owns the signatures j = ew, ew + 8, ... (three features per lane: lane,
+    // lane + 32, lane + 64), so the row sums of the W epilogue never leave the warp.  Rows >= k of the operands are zero.
     uint32_t wst[16];  // the thread's W elements as bits (prologue only; stashed in TMEM afterwards)
-    auto store_w_operands = [&](int j, int f, float w) {  // tf32 hi + lo (round to nearest); rows >= k are zero
+    auto store_w_operands = [&](int j, int f, float w) {  // tf32 hi + lo (round to nearest)
         const float hi = tf32_rn(w), lo = tf32_rn(w - hi);
         const uint32_t o1 = (j >> 2) * SW1_LBO + (f >> 3) * SW1_SBO + (f & 7) * 16 + (j & 3) * 4;
         sts32(sW1hi + o1, hi), sts32(sW1lo + o1, lo);
         sts32(sW2 + (f >> 2) * q.sw2_lbo + (j >> 3) * SW2_SBO + (j & 7) * 16 + (f & 3) * 4, hi);
     };
-    if (warp >= 4) {
+    if (warp >= EW0) {
 #pragma unroll
-        for (int r = 0; r < PER_WREG; ++r) {
-            const int t = ew + 8 * r, j = t / 3, f = (t - 3 * j) * 32 + lane;
-            float w = 0.f;
-            if (t < 3 * KP8) {
-                if (j < k) w = __ldcg(R.W_in + (size_t)j * VT + f);
-                store_w_operands(j, f, w);
+        for (int r = 0; r < PER_WREG / 3; ++r) {
+            const int j = (warp - EW0) + 8 * r;
+#pragma unroll
+            for (int s3 = 0; s3 < 3; ++s3) {
+                const int f = s3 * 32 + lane;
+                float w = 0.f;
+                if (j < KP8) {
+                    if (j < k) w = __ldcg(R.W_in + (size_t)j * VT + f);
+                    store_w_operands(j, f, w);
+                }
+                wst[3 * r + s3] = __float_as_uint(w);
             }
-            wst[r] = __float_as_uint(w);
         }
 #pragma unroll
         for (int r = PER_WREG; r < 16; ++r) wst[r] = 0u;
@@ -223,8 +266,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) klnmf_period_tc_kernel(const __gr
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t t_wst = tmem + ((uint32_t)((warp & 3) * 32) << 16) + TM_WST + (uint32_t)(((warp - 4) >> 2) & 1) * 16u;
-    if (warp >= 4) {
+    const uint32_t t_wst = tmem + ((uint32_t)((warp & 3) * 32) << 16) + TM_WST + (uint32_t)(((warp - EW0) >> 2) & 1) * 16u;
+    if (warp >= EW0) {
         tmem_st16(t_wst, wst);
         tc_wait_st();
     }
@@ -232,54 +275,105 @@ __global__ void __launch_bounds__(NTHREADS, 1) klnmf_period_tc_kernel(const __gr
     // sweep u: update (u < L) or the trailing objective-only sweep; the KL term rides on every obj_every-th update
     auto sweep_kl = [&](int u) { return u >= L || (P.obj_every > 0 && u % P.obj_every == 0); };
 
-    if (warp == 0) {
-        // ================= X producer: free-running, S tiles ahead, across updates =================
-        if (lane == 0) {
-            int i = 0;
-            const int T = U * n_my;
-            for (int t = 0; t < T; ++t) {
-                const int st = t % S;
-                const int d0 = (c + i * G) * TILE;
-                mbar_wait(bar_empty + 8 * st, ((t / S) & 1) ^ 1);
-                mbar_arrive_expect_tx(bar_full + 8 * st, XSTAGE_BYTES);
-                for (int b = 0; b < NBOX; ++b) tma_load_2d(sX + st * XSTAGE_BYTES + b * BOX_BYTES, &R.mapX, bar_full + 8 * st, b * 32, d0);
-                if (++i == n_my) i = 0;
-            }
-        }
-    } else if (warp == 2) {
-        // ================= exposure producer =================
-        // Sweep 0 reads H_in, later sweeps read what this CTA's store warp wrote in the sweep before (it signals bar_hstored once
-        // its bulk stores have completed).  The partial last tile of a generic-k problem cannot go through the 3-D map: the whole
-        // warp copies its rows with plain loads and zero-fills the rest of the slot.
-        for (int u = 0; u < U; ++u) {
-            const CUtensorMap* map = u == 0 ? &R.mapH0 : &R.mapH1;
-            const float* Hsrc = u == 0 ? R.H_in : R.H_out;
-            if (u > 0) mbar_wait(bar_hstored, (u - 1) & 1);
-            for (int i = 0; i < n_my; ++i) {
-                const int t = u * n_my + i, hs = t % NH;
-                const int tile = c + i * G, d0 = tile * TILE;
-                const bool ragged = GK && (int64_t)d0 + TILE > R.D;  // warp-uniform
+    // (each setmaxnreg dominates exactly its own role code: the register budget of a region is what its dominating
+    // setmaxnreg says)
+    if (warp < EW0) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_UTIL));
+      if (warp == 0) {
+        // ================= data movement: one event loop =================
+        // Three queues served by one warp with NON-blocking barrier tests (warp-uniform control flow, lane 0 issues):
+        //   X tiles     : free-running, S tiles ahead, across sweeps (X never changes);
+        //   exposures in: sweep 0 reads H_in, later sweeps read back what this CTA stored in the sweep before -- a CTA always
+        //                 meets the same tiles -- so they wait until those bulk stores have completed (known locally: the same
+        //                 thread issued them);
+        //   exposures out: the epilogue leaves the updated rows in the tile's slot; one bulk store each.
+        // The partial last tile of a generic-k problem cannot go through the 3-D map: the whole warp copies its rows with
+        // plain loads / stores.
+        const int T = U * n_my;
+        int tx = 0, ix = 0, sx = 0, px = 1;           // X: running tile, tile in sweep, stage, parity to test on `empty`
+        int th = 0, ih = 0, uh = 0, sh = 0, ph = 1;   // exposure loads: running tile, tile in sweep, sweep, slot, parity on `hempty`
+        int ts = 0, is = 0, us = 0, ss = 0, ps = 0;   // exposure stores: ..., slot, parity on `hout`
+        const bool has_ragged = GK && (int64_t)(c + (n_my - 1) * G) * TILE + TILE > R.D;  // this CTA owns the partial last tile
+        while (ts < T) {  // (the last store is the last event)
+            bool idle = true;
+            if (tx < T && mbar_test(bar_empty + 8 * sx, (uint32_t)px)) {
                 if (lane == 0) {
-                    mbar_wait(bar_hempty + 8 * hs, ((t / NH) & 1) ^ 1);
-                    if (!ragged) {
-                        mbar_arrive_expect_tx(bar_hfull + 8 * hs, (uint32_t)(TILE * k * 4));
+                    const int d0 = (c + ix * G) * TILE;
+                    mbar_arrive_expect_tx(bar_full + 8 * sx, XSTAGE_BYTES);
+                    for (int b = 0; b < NBOX; ++b) tma_load_2d(sX + sx * XSTAGE_BYTES + b * BOX_BYTES, &R.mapX, bar_full + 8 * sx, b * 32, d0);
+                }
+                idle = false;
+                ++tx;
+                if (++ix == n_my) ix = 0;
+                if (++sx == S) sx = 0, px ^= 1;
+            }
+            // rows of sweep uh >= 1 were written by this CTA's store of running tile th - n_my: it must have been issued, and at
+            // most the `newer` bulk groups committed after it may still be pending (groups complete in order)
+            if (th < T && (uh == 0 || th - n_my < ts) && mbar_test(bar_hempty + 8 * sh, (uint32_t)ph)) {
+                if (uh > 0 && lane == 0) {
+                    const int newer = has_ragged ? 0 : ts - (th - n_my) - 1;
+                    if (newer >= 3)
+                        asm volatile("cp.async.bulk.wait_group 3;" ::: "memory");
+                    else if (newer == 2)
+                        asm volatile("cp.async.bulk.wait_group 2;" ::: "memory");
+                    else if (newer == 1)
+                        asm volatile("cp.async.bulk.wait_group 1;" ::: "memory");
+                    else
+                        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                    // (store and load both go through the async proxy, issued by this thread: no proxy fence needed)
+                }
+                __syncwarp();
+                const CUtensorMap* map = uh == 0 ? &R.mapH0 : &R.mapH1;
+                const int tile = c + ih * G, d0 = tile * TILE;
+                const bool ragged = GK && (int64_t)d0 + TILE > R.D;
+                if (!ragged) {
+                    if (lane == 0) {
+                        mbar_arrive_expect_tx(bar_hfull + 8 * sh, (uint32_t)(TILE * k * 4));
                         if (GK)
-                            tma_load_3d(sHraw + hs * q.hraw, map, bar_hfull + 8 * hs, 0, 0, tile);
+                            tma_load_3d(sHraw + sh * q.hraw, map, bar_hfull + 8 * sh, 0, 0, tile);
                         else
-                            tma_load_2d(sHraw + hs * q.hraw, map, bar_hfull + 8 * hs, 0, d0);
+                            tma_load_2d(sHraw + sh * q.hraw, map, bar_hfull + 8 * sh, 0, d0);
+                    }
+                } else {
+                    const float* src = (uh == 0 ? R.H_in : R.H_out) + (size_t)d0 * k;
+                    const int n = (int)(R.D - d0) * k;
+                    for (int x = lane; x < TILE * k; x += 32) sts32(sHraw + sh * q.hraw + x * 4, x < n ? __ldcg(src + x) : 0.f);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_hfull + 8 * sh);
+                }
+                idle = false;
+                ++th;
+                if (++ih == n_my) ih = 0, ++uh;
+                if (++sh == NH) sh = 0, ph ^= 1;
+            }
+            if (mbar_test(bar_hout + 8 * ss, (uint32_t)ps)) {
+                const int tile = c + is * G, d0 = tile * TILE;
+                const bool ragged = GK && (int64_t)d0 + TILE > R.D;
+                if (us < L) {
+                    if (ragged) {
+                        const int n = (int)(R.D - d0) * k;
+                        float* dst = R.H_out + (size_t)d0 * k;
+                        for (int x = lane; x < n; x += 32) dst[x] = lds32(sHraw + ss * q.hraw + x * 4);
+                        __syncwarp();
+                    } else if (lane == 0) {
+                        if (GK)
+                            tma_store_3d(&R.mapH1, sHraw + ss * q.hraw, 0, 0, tile);
+                        else
+                            tma_store_2d(&R.mapH1, sHraw + ss * q.hraw, 0, d0);
+                        tma_store_commit_and_wait_read();
                     }
                 }
-                if (ragged) {
-                    __syncwarp();
-                    const int n = (int)(R.D - d0) * k;
-                    const float* src = Hsrc + (size_t)d0 * k;
-                    for (int x = lane; x < TILE * k; x += 32) sts32(sHraw + hs * q.hraw + x * 4, x < n ? __ldcg(src + x) : 0.f);
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_hfull + 8 * hs);
-                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_hempty + 8 * ss);
+                ++ts;
+                if (++ss == NH) ss = 0, ps ^= 1;
+                if (++is == n_my) is = 0, ++us;
+                idle = false;
             }
+            if (idle) __nanosleep(64);  // leave the issue slots of this scheduler to the epilogue warps
         }
-    } else if (warp == 1) {
+        if (lane == 0) tma_store_wait_all();
+      } else if (warp == 1) {
         // ================= MMA issuer =================
         constexpr uint32_t ID1 = make_idesc(128, VT, 0, 0);
         constexpr uint32_t ID2 = make_idesc(128, N2, 0, 0);
@@ -327,6 +421,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) klnmf_period_tc_kernel(const __gr
                             mma_ss(tmem + TM_WN, dX + (uint64_t)(ks * (1024 >> 4)), dHT + (uint64_t)(ks * htstep), ID3, (i > 0 || ks > 0));
                         tc_commit(bar_empty + 8 * st);
                         tc_commit(bar_shtfree);
+                        if (i == n_my - 1) tc_commit(bar_wn);  // phase u: the numerator of sweep u is complete (G2 of this tile is not)
 #pragma unroll
                         for (int ks = 0; ks < VT / 8; ++ks) mma_ts(tHn, tR + ks * 8, dW2 + (uint64_t)(ks * w2step), ID2, ks > 0);
                         tc_commit(bar_hnfull + 8 * b);
@@ -341,49 +436,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) klnmf_period_tc_kernel(const __gr
             __syncwarp();
         }
         mbar_wait(bar_done, (U - 1) & 1);  // before the CTA tears TMEM down
-    } else if (warp == 3) {
-        // ================= exposure store =================
-        for (int u = 0; u < U; ++u) {
-            const bool do_store = u < L;
-            for (int i = 0; i < n_my; ++i) {
-                const int t = u * n_my + i, hs = t % NH;
-                const int tile = c + i * G, d0 = tile * TILE;
-                const bool ragged = GK && (int64_t)d0 + TILE > R.D;  // warp-uniform
-                if (lane == 0) mbar_wait(bar_hout + 8 * hs, (t / NH) & 1);
-                if (do_store) {
-                    if (ragged) {
-                        __syncwarp();
-                        const int n = (int)(R.D - d0) * k;
-                        float* dst = R.H_out + (size_t)d0 * k;
-                        for (int x = lane; x < n; x += 32) dst[x] = lds32(sHraw + hs * q.hraw + x * 4);
-                        __syncwarp();
-                    } else if (lane == 0) {
-                        if (GK)
-                            tma_store_3d(&R.mapH1, sHraw + hs * q.hraw, 0, 0, tile);
-                        else
-                            tma_store_2d(&R.mapH1, sHraw + hs * q.hraw, 0, d0);
-                        tma_store_commit_and_wait_read();
-                    }
-                }
-                if (lane == 0) mbar_arrive(bar_hempty + 8 * hs);
-            }
-            // the next sweep of this CTA reads these rows back: wait until the bulk stores have been performed
-            __syncwarp();
-            if (lane == 0) {
-                tma_store_wait_all();
-                asm volatile("fence.proxy.async;" ::: "memory");
-                __threadfence_block();
-                mbar_arrive(bar_hstored);
-            }
-        }
+      }
     } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_EPI));
         // ================= epilogue warpgroups (+ reduction, exchange and W epilogue between the updates) =================
         const int qw = warp & 3;
         const int s = qw * 32 + lane;  // sample row of the tile = TMEM lane
         const uint32_t lane_off = (uint32_t)(qw * 32) << 16;
         const uint32_t sw = (s >> 2) & 1;
         const float eps = (float)SAL_EPS_F32;
-        const int g = (warp - 4) >> 2;  // this warpgroup meets the tiles whose running number t is congruent g mod 2
+        const int g = (warp - EW0) >> 2;  // this warpgroup meets the tiles whose running number t is congruent g mod 2
 
         // exposures of sample s of running tile t -> registers and, as tf32 hi / lo, the TMEM A operand of G1
         auto load_h = [&](int t, int i, float (&h)[KP8]) {
@@ -391,7 +453,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) klnmf_period_tc_kernel(const __gr
             mbar_wait(bar_hfull + 8 * hs, (t / NH) & 1);
             const uint32_t hrow = sHraw + hs * q.hraw + s * (k * 4);
             const uint32_t th = tmem + lane_off + (b ? TM_H1 : TM_H0);
-            (void)i;
+            // rows past the end of X (zero-filled by TMA): exposures read as 1, so that WH > 0 and the zero counts give a zero
+            // quotient (no contribution to anything; the rows are clipped again when the tile is stored)
+            const bool row_valid = (int64_t)(c + i * G) * TILE + s < R.D;
 #pragma unroll
             for (int j = 0; j < KP8; j += 8) {
                 if (GK) {  // rows are not 16-byte aligned: scalar loads
@@ -403,6 +467,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) klnmf_period_tc_kernel(const __gr
                     if (j + 4 < k) t1 = lds128(hrow + j * 4 + 16);
                     h[j] = t0.x, h[j + 1] = t0.y, h[j + 2] = t0.z, h[j + 3] = t0.w;
                     h[j + 4] = t1.x, h[j + 5] = t1.y, h[j + 6] = t1.z, h[j + 7] = t1.w;
+                }
+                if (!row_valid) {
+#pragma unroll
+                    for (int x = 0; x < 8; ++x)
+                        if (j + x < k) h[j + x] = 1.f;
                 }
                 uint32_t hi[8], lo[8];
 #pragma unroll
@@ -419,11 +488,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) klnmf_period_tc_kernel(const __gr
         };
 
         float h[KP8], hn[KP8];
-        double obj_acc = 0.0;
 
         // the tiles of one sweep; DO_R: update (quotient written back, G2 / G3 follow); DO_KL: KL term of the incoming iterate
-        auto sweep_tiles = [&](auto do_r_c, auto do_kl_c, int u) {
+        auto sweep_tiles = [&](auto do_r_c, auto do_kl_c, int u) -> double {
             constexpr bool DO_R = decltype(do_r_c)::value, DO_KL = decltype(do_kl_c)::value;
+            double obj_acc = 0.0;
             const int t_begin = u * n_my;
             const int i0 = (g - t_begin) & 1;  // first tile of this warpgroup in the sweep
             if (i0 < n_my) load_h(t_begin + i0, i0, h);
@@ -435,36 +504,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) klnmf_period_tc_kernel(const __gr
                 mbar_wait(bar_whfull + 8 * b, (t >> 1) & 1);
                 tc_fence_after();
                 const uint32_t tWH = tmem + lane_off + (b ? TM_WH1 : TM_WH0);
-                float kl = 0.f;
-                {
-                    // software pipeline over the three boxes: the TMEM load of box c + 1 is in flight while box c is divided
-                    uint32_t v0[32], v1[32];
-                    const uint32_t rowbase = sX + st * XSTAGE_BYTES + s * 128;
-                    tmem_ld32(tWH, v0);
-                    tc_wait_ld();
-                    tmem_ld32(tWH + 32, v1);
-                    if (!valid) {  // rows past the end of X: x = 0 (TMA zero fill), make the quotient 0 * 1
-#pragma unroll
-                        for (int x = 0; x < 32; ++x) v0[x] = 0x3f800000u;
-                    }
-                    quotient_box<DO_R, DO_KL>(v0, rowbase, s, sw, kl);
-                    if (DO_R) tmem_st32(tWH, v0);
-                    tc_wait_ld();
-                    tmem_ld32(tWH + 64, v0);
-                    if (!valid) {
-#pragma unroll
-                        for (int x = 0; x < 32; ++x) v1[x] = 0x3f800000u;
-                    }
-                    quotient_box<DO_R, DO_KL>(v1, rowbase + BOX_BYTES, s, sw, kl);
-                    if (DO_R) tmem_st32(tWH + 32, v1);
-                    tc_wait_ld();
-                    if (!valid) {
-#pragma unroll
-                        for (int x = 0; x < 32; ++x) v0[x] = 0x3f800000u;
-                    }
-                    quotient_box<DO_R, DO_KL>(v0, rowbase + 2 * BOX_BYTES, s, sw, kl);
-                    if (DO_R) tmem_st32(tWH + 64, v0);
-                }
+                const float kl = quotient_row_loop<DO_R, DO_KL>(tWH, sX + st * XSTAGE_BYTES + s * 128, s, sw);
                 if (DO_KL && valid) obj_acc += (double)kl;
                 if (DO_R) {
                     if (t > 0) mbar_wait(bar_shtfree, (t - 1) & 1);  // G3 of the previous tile has read sHT
@@ -511,197 +551,208 @@ __global__ void __launch_bounds__(NTHREADS, 1) klnmf_period_tc_kernel(const __gr
 #pragma unroll
                 for (int j = 0; j < KP8; ++j) h[j] = hn[j];
             }
+            return obj_acc;
         };
 
         for (int u = 0; u < U; ++u) {
             const bool do_r = u < L, do_kl = sweep_kl(u);
+            tl_stamp(P.tl, tl_on && tid == EPI0, u, 0);
+            double obj_acc = 0.0;
+            if (do_r && do_kl)
+                obj_acc = sweep_tiles(std::true_type{}, std::true_type{}, u);
+            else if (do_r)
+                obj_acc = sweep_tiles(std::true_type{}, std::false_type{}, u);
+            else
+                obj_acc = sweep_tiles(std::false_type{}, std::true_type{}, u);
+            // (everything below is defined here, after the tile loop: the loop has no registers to spare)
+            const int ew = warp - EW0;
             const unsigned int tag = seq0 + (unsigned int)u;
             const int slot = (int)(tag & 1u);
-            const bool tl = tl_on && e == 0;
-            tl_stamp(P.tl, tl, u, 0);
-            if (do_r && do_kl)
-                sweep_tiles(std::true_type{}, std::true_type{}, u);
-            else if (do_r)
-                sweep_tiles(std::true_type{}, std::false_type{}, u);
-            else
-                sweep_tiles(std::false_type{}, std::true_type{}, u);
+            const bool tl = tl_on && tid == EPI0;
+            const bool cs = P.tl != nullptr && vr == 0 && tid == EPI0;
             tl_stamp(P.tl, tl, u, 1);
+            cta_stamp(P.tl, cs, U, G, u, c, 0);
 
-            // ---- every MMA of the sweep has retired: the numerator leaves TMEM as tagged words ----
-            mbar_wait(bar_done, u & 1);
-            tc_fence_after();
-            tl_stamp(P.tl, tl, u, 2);
-            if (do_r && g == 0 && qw < 3) {
-                uint32_t v[32];
-                tmem_ld32(tmem + lane_off + TM_WN, v);
-                tc_wait_ld();
-                uint2* dst = R.partials + ((size_t)slot * G + c) * nvals + s;  // s = feature 0 .. 95
+            // ---- the numerator leaves TMEM as tagged words as soon as the last G3 has retired (G2 / E2 / the store of the last
+            // tile go on meanwhile); the warpgroup that did NOT have the last tile does it: it is free earlier ----
+            if (do_r && g != ((u * n_my + n_my - 1) & 1)) {
+                mbar_wait(bar_wn, u & 1);
+                tc_fence_after();
+                if (qw < 3) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem + lane_off + TM_WN, v);
+                    tc_wait_ld();
+                    uint2* dst = R.partials + ((size_t)slot * G + c) * nvals + s;  // s = feature 0 .. 95
 #pragma unroll
-                for (int j = 0; j < KP8; ++j)
-                    if (j < k) st_tag2(dst + j * VT, v[j], tag);
+                    for (int j = 0; j < KP8; ++j)
+                        if (j < k) st_tag2(dst + j * VT, v[j], tag);
+                }
             }
+            tl_stamp(P.tl, tl, u, 2);
+            cta_stamp(P.tl, cs, U, G, u, c, 1);
             tc_fence_before();
-            if (do_kl) {
+            if (do_kl) {  // per-CTA objective partial: warp sums -> one tagged word
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) obj_acc += __shfl_xor_sync(0xffffffffu, obj_acc, o);
                 if (lane == 0) s_obj[ew] = obj_acc;
-                obj_acc = 0.0;
-            }
-            tl_stamp(P.tl, tl, u, 3);
-
-            if (do_r) {
-                // ---- stage A: this CTA's slice of the k * 96 values, summed over the G partials in a fixed order ----
-                const int VPC = (nvals + G - 1) / G;
-                const int v_lo = c * VPC, v_hi = v_lo + VPC < nvals ? v_lo + VPC : nvals;
-                double* s_part = s_scr;        // [parts][chunk] <= 256, later s_recv [n_ranks][chunk] <= 512
-                double* s_two = s_scr + 256;   // [4][chunk]
-                double* s_loc = s_scr + 512;   // [chunk]
-                for (int ch0 = v_lo; ch0 < v_hi; ch0 += PER_CHUNK) {
-                    const int chunk = v_hi - ch0 < PER_CHUNK ? v_hi - ch0 : PER_CHUNK;
-                    const int parts = EPI_THREADS / chunk;  // >= 4
-                    const int part = e / chunk, vi = e - part * chunk;
-                    if (part < parts) {
-                        const uint2* src = R.partials + (size_t)slot * G * nvals + ch0 + vi;
-                        double acc = 0.0;
-                        for (int b0 = part; b0 < G; b0 += 4 * parts) {
-                            // four polled loads in flight per thread
-                            float x[4];
-#pragma unroll
-                            for (int z = 0; z < 4; ++z) {
-                                const int b = b0 + z * parts;
-                                x[z] = b < G ? poll_f32(src + (size_t)b * nvals, tag) : 0.f;
-                            }
-#pragma unroll
-                            for (int z = 0; z < 4; ++z)
-                                if (b0 + z * parts < G) acc += (double)x[z];
-                        }
-                        s_part[part * chunk + vi] = acc;
-                    }
-                    bar_epi();
-                    if (e < 4 * chunk) {
-                        const int qd = e / chunk, v2 = e - qd * chunk;
-                        double t2 = 0.0;
-                        for (int pp = qd; pp < parts; pp += 4) t2 += s_part[pp * chunk + v2];
-                        s_two[qd * chunk + v2] = t2;
-                    }
-                    bar_epi();
-                    double total = 0.0;
-                    if (e < chunk) total = (s_two[e] + s_two[chunk + e]) + (s_two[2 * chunk + e] + s_two[3 * chunk + e]);
-                    if (P.n_ranks > 1) {
-                        // ---- exchange of the slice over NVLink: push to every peer, poll the own buffer, sum in rank order ----
-                        if (e < chunk) s_loc[e] = total;
-                        bar_epi();
-                        const size_t row = (size_t)slot * P.n_ranks * (size_t)(nvals + VT);  // start of recv[slot]; (k + 1) * 96 words per rank
-                        double* s_recv = s_scr;
-                        const int rr = e / chunk, rv = e - rr * chunk;
-                        for (int r0 = 0; r0 < P.n_ranks; r0 += parts) {
-                            const int rk = r0 + rr;
-                            if (rr < parts && rk < P.n_ranks) {
-                                const double mine = s_loc[rv];
-                                double val = mine;
-                                if (rk != R.rank) {
-                                    const unsigned long long bits = (unsigned long long)__double_as_longlong(mine);
-                                    uint4* dstp = reinterpret_cast<uint4*>(R.peers[rk]) + (row + (size_t)R.rank * (nvals + VT) + ch0 + rv);
-                                    st_tag4(dstp, (unsigned int)bits, (unsigned int)(bits >> 32), tag);
-                                    const uint4* srcp = reinterpret_cast<const uint4*>(R.peers[R.rank]) + (row + (size_t)rk * (nvals + VT) + ch0 + rv);
-                                    val = poll_f64(srcp, tag);
-                                }
-                                s_recv[rk * chunk + rv] = val;
-                            }
-                        }
-                        bar_epi();
-                        if (e < chunk) {
-                            total = 0.0;
-                            for (int rk = 0; rk < P.n_ranks; ++rk) total += s_recv[rk * chunk + e];
-                        }
-                    }
-                    if (e < chunk) st_tag2(R.sums + (size_t)slot * nvals + ch0 + e, __float_as_uint((float)total), tag);
-                    if (ch0 + PER_CHUNK < v_hi) bar_epi();  // the scratch is reused by the next chunk
-                }
-                tl_stamp(P.tl, tl, u, 4);
-            }
-
-            // ---- objective: per-CTA partials, summed (and exchanged) by the last CTA, which has the fewest tiles ----
-            if (do_kl) {
-                bar_epi();  // s_obj complete (and the scratch of stage A no longer read)
-                if (e == 0) {
+                bar_epi();
+                if (tid == EPI0) {
                     double t2 = 0.0;
                     for (int w8 = 0; w8 < 8; ++w8) t2 += s_obj[w8];
                     const unsigned long long bits = (unsigned long long)__double_as_longlong(t2);
                     st_tag4(R.obj_part + (size_t)slot * G + c, (unsigned int)bits, (unsigned int)(bits >> 32), tag);
                 }
-                if (c == G - 1) {
-                    double* s_o = s_scr;  // [G] <= 256
-                    if (e < G) s_o[e] = poll_f64(R.obj_part + (size_t)slot * G + e, tag);
-                    bar_epi();
-                    if (e == 0) {
-                        double tot = 0.0;
-                        for (int b = 0; b < G; ++b) tot += s_o[b];
-                        if (P.n_ranks > 1) {
-                            const size_t row = (size_t)slot * P.n_ranks * (size_t)(nvals + VT);
-                            const unsigned long long bits = (unsigned long long)__double_as_longlong(tot);
-                            for (int rk = 0; rk < P.n_ranks; ++rk)
-                                if (rk != R.rank)
-                                    st_tag4(reinterpret_cast<uint4*>(R.peers[rk]) + (row + (size_t)R.rank * (nvals + VT) + nvals),
-                                            (unsigned int)bits, (unsigned int)(bits >> 32), tag);
-                            const double mine = tot;
-                            tot = 0.0;
-                            for (int rk = 0; rk < P.n_ranks; ++rk)
-                                tot += rk == R.rank ? mine
-                                                    : poll_f64(reinterpret_cast<const uint4*>(R.peers[R.rank]) +
-                                                                   (row + (size_t)rk * (nvals + VT) + nvals),
-                                                               tag);
+            }
+            tl_stamp(P.tl, tl, u, 3);
+
+            const size_t xrow = (size_t)slot * P.n_ranks * (size_t)(nvals + VT);  // start of recv[slot]; (k + 1) * 96 words per rank
+            if (do_r) {
+                // ---- stage A: this CTA's slice of the k * 96 values, summed over the G partials in a fixed order.
+                // Partial b holds the slice as one contiguous run, so a warp instruction reads 32 / VW whole runs (VW lanes each):
+                // G requests of ~100 bytes per CTA instead of one request per word.  Thread (warp ew, run r, value vi) adds the
+                // partials b = (8 it + ew) * (32 / VW) + r, it = 0, 1, ...; a shuffle tree over r, then the eight warps in order.
+                const int VPC = (nvals + G - 1) / G;
+                const int v_lo = c * VPC, v_hi = v_lo + VPC < nvals ? v_lo + VPC : nvals;
+                const int VW = VPC <= 4 ? 4 : VPC <= 8 ? 8 : VPC <= 16 ? 16 : 32, BPW = 32 / VW;
+                const int vi = lane & (VW - 1), bsub = lane / VW, e = tid - EPI0;
+                const uint2* pbase = R.partials + (size_t)slot * G * nvals;
+                for (int ch0 = v_lo; ch0 < v_hi; ch0 += 32) {
+                    const int nv = v_hi - ch0 < 32 ? v_hi - ch0 : 32;
+                    double acc = 0.0;
+                    if (vi < nv) {
+                        for (int b0 = ew * BPW + bsub; b0 < G; b0 += 40 * BPW) {
+                            uint2 w[5];
+                            unsigned int pending = 0;
+#pragma unroll
+                            for (int z = 0; z < 5; ++z)
+                                if (b0 + z * 8 * BPW < G) pending |= 1u << z;
+                            const unsigned int have = pending;
+                            poll_batch<5>(w, pending, tag, [&](int z) { return pbase + (size_t)(b0 + z * 8 * BPW) * nvals + ch0 + vi; });
+#pragma unroll
+                            for (int z = 0; z < 5; ++z)
+                                if ((have >> z) & 1u) acc += (double)__uint_as_float(w[z].x);
                         }
-                        const int idx = u >= L ? (P.obj_every > 0 ? (L + P.obj_every - 1) / P.obj_every : 0) : u / P.obj_every;
-                        R.objective[idx] = tot;
                     }
-                    bar_epi();  // the scratch goes back to the W operands below
+                    for (int o = VW; o < 32; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                    if (lane < VW) s_part[ew * 32 + lane] = acc;
+                    bar_epi();
+                    double total = 0.0;
+                    if (e < nv) {
+#pragma unroll
+                        for (int w8 = 0; w8 < 8; ++w8) total += s_part[w8 * 32 + e];
+                    }
+                    if (P.n_ranks > 1) {
+                        // ---- exchange over NVLink: thread (rank rk, value) pushes the sum to peer rk and polls peer rk's word;
+                        // the contributions are added in rank order, so every rank obtains the same bits
+                        if (e < nv) s_tot[e] = total;
+                        bar_epi();  // (also: nobody reads s_part any more, it becomes the receive staging)
+                        const int rk = e >> 5, rv = e & 31;
+                        if (rk < P.n_ranks && rv < nv) {
+                            double val = s_tot[rv];
+                            if (rk != R.rank) {
+                                const unsigned long long bits = (unsigned long long)__double_as_longlong(val);
+                                st_tag4(reinterpret_cast<uint4*>(R.peers[rk]) + (xrow + (size_t)R.rank * (nvals + VT) + ch0 + rv), (unsigned int)bits,
+                                        (unsigned int)(bits >> 32), tag);
+                                val = poll_f64(reinterpret_cast<const uint4*>(R.peers[R.rank]) + (xrow + (size_t)rk * (nvals + VT) + ch0 + rv), tag);
+                            }
+                            s_part[rk * 32 + rv] = val;
+                        }
+                        bar_epi();
+                        if (e < nv) {
+                            total = 0.0;
+                            for (int r2 = 0; r2 < P.n_ranks; ++r2) total += s_part[r2 * 32 + e];
+                        }
+                    }
+                    if (e < nv) st_tag2(R.sums + (size_t)slot * nvals + ch0 + e, __float_as_uint((float)total), tag);
+                    if (ch0 + 32 < v_hi) bar_epi();  // the staging is reused by the next chunk
+                }
+                tl_stamp(P.tl, tl, u, 4);
+                cta_stamp(P.tl, cs, U, G, u, c, 2);
+            }
+
+            // ---- objective: the per-CTA partials are summed (and exchanged) by the last warp of the last CTA, which has the
+            // fewest tiles and the fewest values of stage A ----
+            if (do_kl && c == G - 1 && ew == 7) {
+                double acc = 0.0;
+                for (int b0 = lane; b0 < G; b0 += 32) acc += poll_f64(R.obj_part + (size_t)slot * G + b0, tag);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                if (P.n_ranks > 1) {
+                    const int rk = lane;
+                    double v0 = acc;
+                    if (rk < P.n_ranks && rk != R.rank) {
+                        const unsigned long long bits = (unsigned long long)__double_as_longlong(acc);
+                        st_tag4(reinterpret_cast<uint4*>(R.peers[rk]) + (xrow + (size_t)R.rank * (nvals + VT) + nvals), (unsigned int)bits,
+                                (unsigned int)(bits >> 32), tag);
+                        v0 = poll_f64(reinterpret_cast<const uint4*>(R.peers[R.rank]) + (xrow + (size_t)rk * (nvals + VT) + nvals), tag);
+                    }
+                    acc = 0.0;
+                    for (int r2 = 0; r2 < P.n_ranks; ++r2) acc += __shfl_sync(0xffffffffu, v0, r2);
+                }
+                if (lane == 0) {
+                    const int idx = u >= L ? (P.obj_every > 0 ? (L + P.obj_every - 1) / P.obj_every : 0) : u / P.obj_every;
+                    R.objective[idx] = acc;
                 }
             }
 
             if (do_r) {
                 // ---- stage B: every CTA polls the k * 96 totals and applies the W epilogue into its own operands ----
                 // W[j] <- clip(W[j] * N[j] / sum_v(W[j][v] N[j][v])), given signatures restored (reference _utils_klnmf.py:338-341;
-                // same arithmetic and summation order as klnmf_finish_kernel / w_epilogue_kernel)
+                // double arithmetic as in klnmf_finish_kernel / w_epilogue_kernel, one warp-wide tree per signature).  All polled loads
+                // of a thread are in flight together.
                 uint32_t wbits[16];
                 tmem_ld16(t_wst, wbits);
+                uint2 wd[PER_WREG];
+                const uint2* sbase = R.sums + (size_t)slot * nvals + lane;
+                {
+                    unsigned int pending = 0;
+#pragma unroll
+                    for (int r = 0; r < PER_WREG / 3; ++r)
+                        if (ew + 8 * r < k) pending |= 7u << (3 * r);
+                    poll_batch<PER_WREG>(wd, pending, tag, [&](int z) { return sbase + (ew + 8 * (z / 3)) * VT + (z % 3) * 32; });
+                }
+                mbar_wait(bar_done, u & 1);  // G2 of the last tile reads the W operands that are rewritten below (long retired by now)
+                tc_fence_after();
                 tc_wait_ld();
-                double val[PER_WREG];
 #pragma unroll
-                for (int r = 0; r < PER_WREG; ++r) {
-                    const int t = ew + 8 * r, j = t / 3, f = (t - 3 * j) * 32 + lane;
-                    val[r] = 0.0;
-                    if (t < 3 * k) {
-                        const float num = poll_f32(R.sums + (size_t)slot * nvals + j * VT + f, tag);
-                        val[r] = (double)__uint_as_float(wbits[r]) * (double)num;
-                        double ssum = val[r];
+                for (int r = 0; r < PER_WREG / 3; ++r) {
+                    const int j = ew + 8 * r;
+                    if (j < k) {
+                        double val[3];
 #pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
-                        if (lane == 0) s_red[t] = ssum;  // t = 3 j + (warp of the row)
+                        for (int s3 = 0; s3 < 3; ++s3)
+                            val[s3] = (double)__uint_as_float(wbits[3 * r + s3]) * (double)__uint_as_float(wd[3 * r + s3].x);
+                        double tot = (val[0] + val[1]) + val[2];
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+                        // val / tot through one reciprocal per signature (seed + two Newton steps) and a residual correction of each
+                        // quotient: within 1 ulp of the IEEE quotient, a handful of DFMAs instead of three division sequences
+                        double rcp;
+                        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rcp) : "d"(tot));
+                        double err = fma(-tot, rcp, 1.0);
+                        rcp = fma(rcp, err, rcp);
+                        err = fma(-tot, rcp, 1.0);
+                        rcp = fma(rcp, err, rcp);
+#pragma unroll
+                        for (int s3 = 0; s3 < 3; ++s3) {
+                            const double qv = val[s3] * rcp;
+                            double out = fma(fma(-tot, qv, val[s3]), rcp, qv);
+                            if (j < P.n_given) out = (double)__uint_as_float(wbits[3 * r + s3]);
+                            if (P.clip_given || j >= P.n_given) out = fmax(out, (double)SAL_EPS_F32);
+                            wbits[3 * r + s3] = __float_as_uint((float)out);
+                            store_w_operands(j, s3 * 32 + lane, (float)out);
+                        }
                     }
                 }
                 tl_stamp(P.tl, tl, u, 5);
-                bar_epi();  // row sums complete; nobody reads the reduction scratch any more
-#pragma unroll
-                for (int r = 0; r < PER_WREG; ++r) {
-                    const int t = ew + 8 * r, j = t / 3, f = (t - 3 * j) * 32 + lane;
-                    if (t < 3 * KP8) {
-                        if (t < 3 * k) {
-                            const double tot = s_red[3 * j] + s_red[3 * j + 1] + s_red[3 * j + 2];
-                            double out = val[r] / tot;
-                            if (j < P.n_given) out = (double)__uint_as_float(wbits[r]);
-                            if (P.clip_given || j >= P.n_given) out = fmax(out, (double)SAL_EPS_F32);
-                            wbits[r] = __float_as_uint((float)out);
-                        }
-                        store_w_operands(j, f, __uint_as_float(wbits[r]));
-                    }
-                }
+                cta_stamp(P.tl, cs, U, G, u, c, 3);
                 tmem_st16(t_wst, wbits);
                 tc_wait_st();
                 fence_proxy_async();
                 bar_epi();  // all W operands rewritten: the next sweep's first G1 may be issued (through hready)
                 tl_stamp(P.tl, tl, u, 6);
             }
+            tl_stamp(P.tl, tl, u, 7);
         }
         // ---- the final signatures go to global memory once ----
         if (c == 0 && L > 0) {
@@ -709,9 +760,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) klnmf_period_tc_kernel(const __gr
             tmem_ld16(t_wst, wbits);
             tc_wait_ld();
 #pragma unroll
-            for (int r = 0; r < PER_WREG; ++r) {
-                const int t = ew + 8 * r, j = t / 3, f = (t - 3 * j) * 32 + lane;
-                if (t < 3 * k) R.W_out[(size_t)j * VT + f] = __uint_as_float(wbits[r]);
+            for (int r = 0; r < PER_WREG / 3; ++r) {
+                const int j = (warp - EW0) + 8 * r;
+                if (j < k) {
+#pragma unroll
+                    for (int s3 = 0; s3 < 3; ++s3) R.W_out[(size_t)j * VT + s3 * 32 + lane] = __uint_as_float(wbits[3 * r + s3]);
+                }
             }
         }
     }
@@ -719,7 +773,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) klnmf_period_tc_kernel(const __gr
     tc_fence_before();
     __syncthreads();
     if (c == 0 && tid == 0) atomicMax(R.seq, seq0 + (unsigned int)U);  // every CTA read seq0 long ago (it took part in sweep 0)
-    if (warp == 2) {
+    if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TM_COLS) : "memory");
     }
@@ -767,7 +821,7 @@ int launch_period_v(sal_ctx* const* cs, int n_virtual, const PeriodArgs* as, cud
         R.D = c->D, R.n_tiles = (int)((c->D + TILE - 1) / TILE), R.rank = a.rank;
     }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(G * n_virtual)), cfg.blockDim = dim3(NTHREADS), cfg.dynamicSmemBytes = (size_t)q.total, cfg.stream = st;
+    cfg.gridDim = dim3((unsigned)(G * n_virtual)), cfg.blockDim = dim3(PER_THREADS), cfg.dynamicSmemBytes = (size_t)q.total, cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeCooperative;  // co-residency of all CTAs is part of the protocol: they wait on one another
     attr[0].val.cooperative = 1;

@@ -271,6 +271,161 @@ __device__ __forceinline__ void quotient_box(uint32_t (&v)[32], uint32_t rowbase
     }
 }
 
+// The same box with the special-function work batched: the eight reciprocals of a chunk are issued back to back, then the
+// eight logarithms (volatile asm keeps that order), so a warp has eight independent MUFU results in flight instead of one --
+// ptxas otherwise schedules every MUFU right in front of its consumer (to save registers), which makes the KL variant
+// latency bound with one or two epilogue warps per scheduler (profiles/r02_period_kl_ncu.md).  Two KL accumulators.
+__device__ __forceinline__ float rcp_approx_v(float x) {
+    float r;
+    asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float lg2_approx_v(float x) {
+    float r;
+    asm volatile("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+template <bool DO_R, bool DO_KL>
+__device__ __forceinline__ void quotient_box_batched(uint32_t (&v)[32], uint32_t rowbase, int s, uint32_t sw, float& kl) {
+    float4 va = lds128(rowbase + ((uint32_t)(0 ^ (s & 3)) << 5) + sw * 16);
+    float4 vb = lds128(rowbase + ((uint32_t)(0 ^ (s & 3)) << 5) + (sw ^ 1) * 16);
+    float kl0 = 0.f, kl1 = 0.f;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        const uint32_t a32 = rowbase + ((uint32_t)(m ^ (s & 3)) << 5);
+        const float4 xlo = sw ? vb : va, xhi = sw ? va : vb;
+        if (m < 3) {
+            const uint32_t n32 = rowbase + ((uint32_t)((m + 1) ^ (s & 3)) << 5);
+            va = lds128(n32 + sw * 16), vb = lds128(n32 + (sw ^ 1) * 16);
+        }
+        const float xv[8] = {xlo.x, xlo.y, xlo.z, xlo.w, xhi.x, xhi.y, xhi.z, xhi.w};
+        float rc[8], r[8], rr[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) rc[e] = rcp_approx_v(__uint_as_float(v[8 * m + e]));
+#pragma unroll
+        for (int e = 0; e < 8; ++e) r[e] = xv[e] * rc[e];
+        if (DO_KL) {
+            // KL term x ln(x/wh) - x + wh = x ln2 * lg2(r) + (wh - x), cancelling pair first.  lg2.approx (2^-22 absolute):
+            // with D >= SAL_TF32_MIN_SAMPLES the per-term noise (~1e-7 x) averages to < 3e-8 of the objective.
+            // The chunk's contribution is ONE dependent FMA chain that starts with the logarithm issued LAST, so no consumer can
+            // be scheduled before all eight logarithms are in flight.  x = 0 contributes wh: coefficient 0 (the logarithm of
+            // the clamped quotient stays finite) plus wh - x.
+            float lg[8], cf[8], dsum = 0.f;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                cf[e] = xv[e] * 0.693147180559945f;
+                dsum += __uint_as_float(v[8 * m + e]) - xv[e];
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) lg[e] = lg2_approx_v(fmaxf(r[e], 1e-37f));
+            float t = dsum;
+#pragma unroll
+            for (int e = 7; e >= 0; --e) t = fmaf(cf[e], lg[e], t);
+            if (m & 1)
+                kl1 += t;
+            else
+                kl0 += t;
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            // round-to-nearest tf32 = add half an ulp; the MMA ignores the 13 low mantissa bits, no need to mask them
+            rr[e] = __uint_as_float(__float_as_uint(r[e]) + 0x1000u);
+            v[8 * m + e] = __float_as_uint(rr[e]);
+        }
+        if (DO_R) {
+            const float4 rlo = make_float4(rr[0], rr[1], rr[2], rr[3]), rhi = make_float4(rr[4], rr[5], rr[6], rr[7]);
+            sts128(a32 + sw * 16, sw ? rhi : rlo);
+            sts128(a32 + (sw ^ 1) * 16, sw ? rlo : rhi);
+        }
+    }
+    if (DO_KL) kl += kl0 + kl1;
+}
+
+// tcgen05.ld of 8 consecutive columns
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];" : SAL_R8(v, 0) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st8_(uint32_t taddr, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%8], {%0, %1, %2, %3, %4, %5, %6, %7};" ::SAL_W8(v, 0), "r"(taddr) : "memory");
+}
+
+// The quotient of one sample row (96 features) as a LOOP over twelve chunks of eight features -- TMEM columns 8 c .. 8 c + 7,
+// the 32-byte piece (c & 3) ^ (s & 3) of box c >> 2 -- two chunks per iteration, the next chunk's TMEM / shared-memory loads in
+// flight while the current one is divided.  The unrolled form (three 32-column boxes, ~4,000 instructions per tile and variant)
+// ran at the speed of the instruction fetch, not of the pipes (ncu: stall_no_inst; profiles/r02_period_kl_ncu.md): this body is
+// ~150 instructions and stays in the instruction cache.  Rows past the end of X need no special case here: their exposures are
+// read as 1 (see load_h), so WH > 0 and the zero-filled X gives a zero quotient.  Returns the row's KL term (DO_KL).
+template <bool DO_R, bool DO_KL>
+__device__ __forceinline__ float quotient_row_loop(uint32_t tWH, uint32_t rowbase, int s, uint32_t sw) {
+    float kl0 = 0.f, kl1 = 0.f;
+    const uint32_t s3 = (uint32_t)(s & 3);
+    const uint32_t off_a = sw * 16, off_b = (sw ^ 1u) * 16;
+    auto chunk_addr = [&](int c) { return rowbase + (uint32_t)(c >> 2) * (uint32_t)BOX_BYTES + ((((uint32_t)c & 3u) ^ s3) << 5); };
+    auto process = [&](int c, const uint32_t (&w)[8], const float4& va, const float4& vb, float& kl) {
+        const float4 xlo = sw ? vb : va, xhi = sw ? va : vb;
+        const float xv[8] = {xlo.x, xlo.y, xlo.z, xlo.w, xhi.x, xhi.y, xhi.z, xhi.w};
+        float r[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) r[e] = xv[e] * rcp_approx(__uint_as_float(w[e]));
+        if (DO_KL) {
+            // KL term x ln(x/wh) - x + wh = ln2 * x lg2(r) + (wh - x), cancelling pair first.  lg2.approx (2^-22 absolute): with
+            // D >= SAL_TF32_MIN_SAMPLES the per-term noise (~1e-7 x) averages to < 3e-8 of the objective.  x = 0 contributes wh:
+            // the clamp keeps the logarithm finite and its coefficient x is 0.
+            float lg[8], dsum = 0.f;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                lg[e] = lg2_approx(fmaxf(r[e], 1e-37f));
+                dsum += __uint_as_float(w[e]) - xv[e];
+            }
+            float t = 0.f;
+#pragma unroll
+            for (int e = 7; e >= 0; --e) t = fmaf(xv[e], lg[e], t);
+            kl += fmaf(t, 0.693147180559945f, dsum);
+        }
+        if (DO_R) {
+            uint32_t rb[8];
+            // round-to-nearest tf32 = add half an ulp; the MMA ignores the 13 low mantissa bits, no need to mask them
+#pragma unroll
+            for (int e = 0; e < 8; ++e) rb[e] = __float_as_uint(r[e]) + 0x1000u;
+            const float4 rlo = make_float4(__uint_as_float(rb[0]), __uint_as_float(rb[1]), __uint_as_float(rb[2]), __uint_as_float(rb[3]));
+            const float4 rhi = make_float4(__uint_as_float(rb[4]), __uint_as_float(rb[5]), __uint_as_float(rb[6]), __uint_as_float(rb[7]));
+            const uint32_t a = chunk_addr(c);
+            sts128(a + off_a, sw ? rhi : rlo);
+            sts128(a + off_b, sw ? rlo : rhi);
+            tmem_st8_(tWH + 8 * c, rb);
+        }
+    };
+    // two chunks (16 TMEM columns, one tcgen05.ld) per step; six steps, two per loop iteration
+    uint32_t wa[16], wb[16];
+    float4 xa[4], xb[4];
+    auto fetch = [&](int c, uint32_t (&w)[16], float4 (&x)[4]) {
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : SAL_R8(w, 0), SAL_R8(w, 8)
+            : "r"(tWH + 8 * c)
+            : "memory");
+        const uint32_t a0 = chunk_addr(c), a1 = chunk_addr(c + 1);
+        x[0] = lds128(a0 + off_a), x[1] = lds128(a0 + off_b), x[2] = lds128(a1 + off_a), x[3] = lds128(a1 + off_b);
+    };
+    auto process2 = [&](int c, const uint32_t (&w)[16], const float4 (&x)[4]) {
+        const uint32_t w0[8] = {w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7]};
+        const uint32_t w1[8] = {w[8], w[9], w[10], w[11], w[12], w[13], w[14], w[15]};
+        process(c, w0, x[0], x[1], kl0);
+        process(c + 1, w1, x[2], x[3], kl1);
+    };
+    fetch(0, wa, xa);
+#pragma unroll 1
+    for (int c = 0; c < 12; c += 4) {
+        tc_wait_ld();  // chunks c, c + 1 have arrived
+        fetch(c + 2, wb, xb);
+        process2(c, wa, xa);
+        tc_wait_ld();  // chunks c + 2, c + 3 have arrived
+        if (c + 4 < 12) fetch(c + 4, wa, xa);
+        process2(c + 2, wb, xb);
+    }
+    return kl0 + kl1;
+}
+
 // shared-memory matrix descriptor (tcgen05): start >> 4 | LBO >> 4 << 16 | SBO >> 4 << 32 | version 1 << 46 | layout << 61
 constexpr uint64_t LAYOUT_NONE = 0, LAYOUT_128B_BASE32B = 1;
 __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo, uint32_t sbo, uint64_t layout) {

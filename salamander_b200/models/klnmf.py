@@ -40,6 +40,9 @@ class KLNMF(StandardNMF):
         # period is within 2 % of a replayed one while capturing ~6 graphs per fit costs more than that and occasionally
         # stalls in the driver; at 125k samples graphs are 12 % faster.
         self.use_graphs: bool | str = "auto"
+        # tf32 fits: a whole convergence-test period per persistent launch, reduction / exchange / W epilogue inside the
+        # kernel (sal_klnmf_period, see _fit_loop_period); False falls back to the two-kernel updates below
+        self.use_period_kernel = True
         self.use_small_kernel = True  # problems that fit one SM: persistent single-CTA kernel (see _fit_loop_small)
         # multi-GPU all-reduce of the numerator: "auto" / "p2p" = one-shot NVLink exchange fused into the reduction
         # kernel (sal_klnmf_update_p2p), "nccl" = library collective between separate kernels
@@ -172,21 +175,136 @@ class KLNMF(StandardNMF):
 
     def _peer_exchange(self, st):
         """The symmetric exchange buffer of the fused all-reduce, set up once per device state; ``None`` (NCCL path)
-        when ``allreduce = "nccl"`` was asked for or symmetric memory cannot be set up on this system."""
+        when ``allreduce = "nccl"`` was asked for or symmetric memory cannot be set up on EVERY rank: the choice is
+        made collectively (a rank that fell back alone would leave its peers polling for words that never arrive)."""
         if self.allreduce == "nccl":
             return None
         if "peer_exchange" not in st.weights:
+            px, err = None, None
             try:
                 nbytes = int(st.ws.lib.sal_p2p_exchange_bytes(32, st.world))  # sized for the largest k: shared by all fits
-                st.weights["peer_exchange"] = _dist.shared_peer_exchange(nbytes, st.device)
+                px = _dist.shared_peer_exchange(nbytes, st.device)
             except Exception as exc:  # pragma: no cover - depends on the system
+                err = exc
+            if not _dist.all_ranks_agree(px is not None, st.device):
                 if self.allreduce == "p2p":
-                    raise
+                    raise RuntimeError(f"peer-memory all-reduce unavailable on at least one rank ({err})")
                 import warnings
 
-                warnings.warn(f"peer-memory all-reduce unavailable ({exc}); using NCCL")
-                st.weights["peer_exchange"] = None
+                warnings.warn(f"peer-memory all-reduce unavailable on at least one rank ({err}); using NCCL")
+                px = None
+            st.weights["peer_exchange"] = px
         return st.weights["peer_exchange"]
+
+    # ---- period-kernel fit driver ------------------------------------------------------------------
+    _PERIODS_PER_LAUNCH = 16  # non-deciding periods folded into one launch
+    _QUEUE_DEPTH = 4          # launches in flight while no decision is pending
+
+    def _period_path(self, st, n_given):
+        """(use the persistent period kernel?, peer exchange).  Decided collectively on several GPUs."""
+        if not self.use_period_kernel or st.weights["kl"] is not None or st.weights["lhalf"] is not None or st.ws.timing:
+            return False, None
+        px = None
+        ok = st.ws.period_supported(n_given, st.world)
+        if st.world > 1:
+            px = self._peer_exchange(st) if ok else None
+            ok = _dist.all_ranks_agree(ok and px is not None, st.device)
+        return ok, px
+
+    def _fit_loop_period(self, st, px, n_given, verbose, verbosity_freq):
+        """Fit driver on the persistent period kernel (sal_klnmf_period).  Same iterates, history and stopping iteration as
+        the reference loop (signature_nmf.py:361-380):
+
+        * a launch runs whole periods of ``conv_test_freq`` updates, the objective of each period's incoming iterate fused
+          into its first update and -- when the launch ends at ``max_iterations`` -- the objective of the final iterate as a
+          trailing sweep; nothing else touches X;
+        * while the convergence test cannot fire (n < ``min_iterations``) there is nothing to decide: several periods go
+          into one launch and the host runs ahead of the GPU;
+        * afterwards every launch is one period and speculative: it writes into spare buffers (three W / H states rotate)
+          and up to two periods are in flight beyond the last objective the host has seen; a period whose incoming
+          iterate turns out to be the converged one is simply not adopted.
+        """
+        freq, min_it = int(self.conv_test_freq), int(self.min_iterations)
+        max_it = max(int(self.max_iterations), 1)
+        n_seg = -(-max_it // freq)                     # periods with at least one update
+        final_ckpt = max_it % freq == 0                # the reference evaluates the objective at n == max_iterations
+        fl = st.fit_loop
+        if not fl.get("period") or fl["Ws"][fl["cur"]] is not st.W or fl["Hs"][fl["cur"]] is not st.H:
+            fl.clear()
+            fl.update({"period": True, "cur": 0, "Ws": [st.W, st.W_next, torch.empty_like(st.W)],
+                       "Hs": [st.H, torch.empty_like(st.H), torch.empty_like(st.H)]})
+        Ws, Hs, cur = fl["Ws"], fl["Hs"], fl["cur"]
+        n_slots = self._PERIODS_PER_LAUNCH + 1
+        ring = 2 * self._QUEUE_DEPTH
+        if "obj_dev" not in fl:
+            fl["obj_dev"] = torch.zeros((ring, n_slots), dtype=torch.float64, device=st.device)
+            fl["obj_host"] = torch.zeros((ring, n_slots), dtype=torch.float64).pin_memory()
+            fl["events"] = [torch.cuda.Event() for _ in range(ring)]
+        obj_dev, obj_host, events = fl["obj_dev"], fl["obj_host"], fl["events"]
+
+        def deciding(p):  # can the convergence test fire at checkpoint p (iteration p * freq)?
+            return p >= 1 and p * freq >= min_it
+
+        pending = []  # (ring slot, first checkpoint, n checkpoints, state index before, state index after)
+        seg, n_launched, of_values, n_done, final_state = 0, 0, [], 0, None
+        while True:
+            # ---- launch as far ahead as the decisions allow ----
+            while seg < n_seg:
+                if deciding(seg):
+                    if sum(1 for q in pending if deciding(q[1])) >= 2:
+                        break
+                    m = 1
+                else:
+                    if len(pending) >= self._QUEUE_DEPTH:
+                        break
+                    m = 1
+                    while seg + m < n_seg and not deciding(seg + m) and m < self._PERIODS_PER_LAUNCH:
+                        m += 1
+                n0, n1 = seg * freq, min((seg + m) * freq, max_it)
+                fin = final_ckpt and seg + m == n_seg
+                slot, nxt = n_launched % ring, (cur + 1) % 3
+                st.ws.klnmf_period(
+                    st.X, Ws[cur], Ws[nxt], Hs[cur], Hs[nxt], n_given, True, n1 - n0, freq, fin, objectives=obj_dev[slot],
+                    peers=None if px is None else px.peers, state=None if px is None else px.state,
+                    n_ranks=st.world if px is not None else 1, rank=st.rank if px is not None else 0,
+                )
+                obj_host[slot].copy_(obj_dev[slot], non_blocking=True)
+                events[slot].record()
+                pending.append((slot, seg, m + (1 if fin else 0), cur, nxt))
+                cur, seg, n_launched = nxt, seg + m, n_launched + 1
+            if not pending:
+                break
+            # ---- the oldest launch's objectives ----
+            slot, p0, n_ck, s_before, s_after = pending.pop(0)
+            events[slot].synchronize()
+            stop = False
+            for i in range(n_ck):
+                p = p0 + i
+                of_values.append(float(obj_host[slot, i]))
+                if p >= 1:
+                    rel_change = np.abs(of_values[-2] - of_values[-1]) / np.abs(of_values[-2])
+                    if bool(rel_change < self.tol and p * freq >= min_it):
+                        # the fit ended at iteration p * freq.  A deciding launch holds one period, so that is the state it
+                        # started from (it and the launches behind it are not adopted) -- or, for the trailing checkpoint at
+                        # max_iterations, the state it ended with
+                        n_done, final_state, stop = p * freq, (s_before if i == 0 else s_after), True
+                        break
+                if p * freq >= max_it:
+                    n_done, final_state, stop = max_it, s_after, True
+                    break
+                n_end = min((p + 1) * freq, max_it)
+                for it in range(p * freq + 1, n_end + 1):
+                    if verbose and it % verbosity_freq == 0:
+                        print(f"iteration: {it}; objective: {of_values[-1]:.2f}")
+                n_done, final_state = n_end, s_after
+            if stop or (seg >= n_seg and not pending):
+                break
+        torch.cuda.current_stream(st.device).synchronize()  # dropped speculative launches still write the spare buffers
+        st.W, st.H = Ws[final_state], Hs[final_state]
+        st.W_next = Ws[(final_state + 1) % 3]
+        fl["cur"] = final_state
+        self.launch_stats = {"graphs": 0, "launches": n_launched, "driver": "persistent period kernel"}
+        return of_values, n_done
 
     # "auto": graphs while an update takes less than ~80 us of GPU time.  An eager update costs the host ~50-60 us (ctypes
     # marshalling, tensor-map encodes, two launches): hidden behind the GPU at 1M samples per shard, not at 500k (measured
@@ -216,6 +334,9 @@ class KLNMF(StandardNMF):
             and st.ws.small_supported()
         ):
             return self._fit_loop_small(n_given, verbose, verbosity_freq)
+        use_period, px = self._period_path(st, n_given)
+        if use_period:
+            return self._fit_loop_period(st, px, n_given, verbose, verbosity_freq)
         if freq < 3:
             return super()._fit_loop(given_parameters, verbose, verbosity_freq)
         # spare buffers, pinned read-back slot and captured graphs live with the device state, so that a second

@@ -49,11 +49,10 @@ class StandardState:
         if model._clip_on_device:
             changed = torch.zeros(1, dtype=torch.int64, device=dev)
             self.ws.clip_counts(self.X, changed)
+            if model.shard_input:
+                self.allreduce(changed)  # every rank must take the same branch: the gather below is a collective
             if int(changed.item()) > 0:  # reference signature_nmf.py:281 rebinds adata.X to the clipped matrix
-                clipped = self.download(self.X)
-                if model.shard_input and self.world > 1:
-                    clipped = _dist.gather_rows(self.X, self.D_total).to(torch.float64).cpu().numpy()
-                model.adata.X = clipped
+                model.adata.X = self.rows_to_host(self.X)
             model._clip_on_device = False
         self.W = self.upload(W_host)
         self.H = self.upload(H_host[self.lo : self.hi])

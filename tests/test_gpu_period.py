@@ -84,7 +84,7 @@ def test_period_equals_two_kernel_updates(D, k, L, n_given):
     assert _relerr(W_out, W_ref) < 2e-6, _relerr(W_out, W_ref)
     assert _relerr(H_out, H_ref) < 2e-5, _relerr(H_out, H_ref)
     got = objs.cpu().numpy()
-    assert np.isclose(got[0], obj_ref[0], rtol=1e-12, atol=0), (got, obj_ref)  # same inputs, same per-sample terms
+    assert np.isclose(got[0], obj_ref[0], rtol=1e-7, atol=0), (got, obj_ref)  # same inputs; the fp32 per-row sums associate differently
     assert np.allclose(got[:-1], obj_ref, rtol=1e-6, atol=0), (got, obj_ref)
     assert np.isclose(got[-1], float(final.item()), rtol=1e-6), (got[-1], float(final.item()))
     if n_given:
@@ -192,4 +192,6 @@ def test_two_emulated_ranks_one_update_is_exact():
     assert torch.equal(Ws[0], Ws[1])
     assert _relerr(Ws[0], W1) < 1e-6
     assert torch.equal(Hcat, H1)  # the exposure update only depends on the (identical) incoming W
-    assert np.allclose(objs[0].cpu().numpy(), o1.cpu().numpy(), rtol=1e-12)
+    got, ref = objs[0].cpu().numpy(), o1.cpu().numpy()
+    assert np.isclose(got[0], ref[0], rtol=1e-12)  # incoming iterate: same per-sample terms, another association
+    assert np.isclose(got[1], ref[1], rtol=1e-6)   # after the update: W differs in the last bits

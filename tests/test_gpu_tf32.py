@@ -177,11 +177,10 @@ def test_fit_meets_fp32_criteria(tag):
     print(f"{tag}: final KL {hist[-1]:.6f} vs reference {ref[-1]:.6f} (rel {abs(hist[-1] - ref[-1]) / ref[-1]:.2e}), "
           f"{len(hist)} vs {len(ref)} checkpoints, min cosine {cos.min():.7f}")
     assert abs(hist[-1] - ref[-1]) / abs(ref[-1]) < 1e-4
-    # k = 8 on 192 samples has a nearly flat direction: the reference needs 8,740 iterations with objective steps of
-    # ~1e-6 relative per test, which single precision (any fp32 arithmetic, tensor cores or not -- at this size the
-    # exact FMA kernels run) cannot resolve against tol = 1e-7, so it stops earlier on the same plateau.  The
-    # well-conditioned fits (k = 4 here, the 20,000-sample fit below) meet the 0.9999 criterion.
-    assert cos.min() >= (0.9999 if tag != "klnmf_pcawg_k8_seed5" else 0.999)
+    # k = 8 on 192 samples has a nearly flat direction (8,740 reference iterations, objective steps of ~1e-6 relative per test):
+    # fp32 iterates stop a little earlier on the same plateau and still meet 0.9999 -- provided the objective is not evaluated
+    # in single precision (tests/test_fp32_plateau.py shows both for the reference arithmetic; csrc/klnmf_small.cu)
+    assert cos.min() >= 0.9999
 
 
 def test_large_fit_tf32_matches_float64_fit():
