@@ -107,8 +107,10 @@ int64_t sal_launch_count(sal_handle_t h);
  *   Stream ordering: the tensor-core pass is launched as a programmatic dependent launch and requests its first tiles
  *   of X before it waits for the previous kernel of the stream (X is constant during a fit).  W, H, weights and every
  *   output are only touched after that wait.  Hence X must not be written by the KERNEL that directly precedes a pass on
- *   the same stream (a memcpy, an event or a host synchronisation in between restores full ordering; the models
- *   synchronise after sal_clip_counts, the only kernel of this library that writes X).
+ *   the same stream.  The library enforces this for its own writer: after sal_clip_counts (the only kernel of this library
+ *   that writes X) the handle's next pass is launched in plain stream order.  A caller whose own kernel writes X right before
+ *   a pass either synchronises / puts a memcpy or event in between, or calls sal_mark_counts_written(h) first.
+ *   (sal_klnmf_period is an ordinary stream-ordered launch and has no such requirement.)
  */
 int sal_klnmf_pass(sal_handle_t h, const void* X, const void* W, const void* H_in, void* H_out,
                    const void* w_kl, const void* w_lhalf, const void* h_scale, int flags,
@@ -198,6 +200,8 @@ int sal_w_epilogue(sal_handle_t h, const void* W_in, const void* Wnum, int n_giv
  * *n_changed (device int64, must be zeroed by the caller) receives how many entries were raised.
  */
 int sal_clip_counts(sal_handle_t h, void* X, int64_t n, long long* n_changed, void* stream);
+/* X was (or is being) written by a kernel outside this library: the handle's next pass must not read it ahead of stream order. */
+int sal_mark_counts_written(sal_handle_t h);
 
 /* H[d][j] <- max(H[d][j] * scale[j], EPSILON) in place: the exposure half of the normalise-and-clip that ends every
  * initialisation (initialize_mat, initialization/initialize.py:116-118; normalize_WH, utils.py:155-158). */

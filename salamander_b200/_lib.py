@@ -44,6 +44,7 @@ SYMBOLS = {
     "sal_klnmf_small_updates": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),
     "sal_w_epilogue": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),
     "sal_clip_counts": (_i, [_vp, _vp, _i64, _vp, _vp]),
+    "sal_mark_counts_written": (_i, [_vp]),
     "sal_scale_clip_rows": (_i, [_vp, _vp, _vp, _vp]),
     "sal_mvnmf_logdet": (_i, [_vp, _vp, _d, _vp, _vp]),
     "sal_mvnmf_w_unconstrained": (_i, [_vp, _vp, _vp, _vp, _d, _d, _i, _vp, _vp]),

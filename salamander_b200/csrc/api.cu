@@ -396,11 +396,18 @@ int sal_w_epilogue(sal_handle_t h, const void* W_in, const void* Wnum, int n_giv
     return sal_launch_w_epilogue(h, W_in, Wnum, n_given, clip_given, W_out, (cudaStream_t)stream);
 }
 
+int sal_mark_counts_written(sal_handle_t h) {
+    SAL_CHECK_ARG(h != nullptr, "handle is null");
+    h->x_dirty = 1;
+    return 0;
+}
+
 int sal_clip_counts(sal_handle_t h, void* X, int64_t n, long long* n_changed, void* stream) {
     SAL_CHECK_ARG(h != nullptr, "handle is null");
     SAL_CHECK_ARG(n >= 0 && (n == 0 || (X && n_changed)), "X / n_changed must be non-null");
     if (n == 0) return 0;
     SAL_CUDA(cudaSetDevice(h->device));
+    h->x_dirty = 1;  // the next tensor-core pass of this handle is launched in plain stream order (it reads X early otherwise)
     return sal_launch_clip_counts(h, X, n, n_changed, (cudaStream_t)stream);
 }
 

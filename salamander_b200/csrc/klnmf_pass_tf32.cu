@@ -600,7 +600,13 @@ int launch_tc_v(sal_ctx* c, const PassArgs& a, cudaStream_t st) {
     p.n_tiles = (int)((c->D + TILE - 1) / TILE);
     const int grid = p.n_tiles < c->n_sm ? p.n_tiles : c->n_sm;
     if (int e = sal_timing_begin(c, a.flags, st)) return e;
-    SAL_CUDA(sal_launch_pdl(klnmf_pass_tc_kernel<KP8, DO_R, DO_KL, GK, HS, WT>, grid, NTHREADS, q.total, st, mapX, mapH, mapHout, p));
+    // The kernel requests its first X tiles BEFORE the dependency wait (X never changes during a fit).  If a kernel of this
+    // handle has just written X (sal_clip_counts) that early read would race with it: this one launch is then made without the
+    // programmatic-overlap attribute, i.e. in plain stream order.  (X written by anybody else right before a pass remains the
+    // caller's business: synchronise the stream or call sal_mark_counts_written.)
+    const bool overlap = !c->x_dirty;
+    c->x_dirty = 0;
+    SAL_CUDA(sal_launch_pdl_if(overlap, klnmf_pass_tc_kernel<KP8, DO_R, DO_KL, GK, HS, WT>, grid, NTHREADS, q.total, st, mapX, mapH, mapHout, p));
     if (int e = sal_timing_end(c, a.flags, st)) return e;
     c->launches++;
     if (a.flags & SAL_PASS_HSUM) {  // column sums of H_in: per-block partials in the layout the reduction kernel expects

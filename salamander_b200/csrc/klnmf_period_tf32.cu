@@ -448,8 +448,14 @@ __global__ void __launch_bounds__(PER_THREADS, 1) klnmf_period_tc_kernel(const _
         const int g = (warp - EW0) >> 2;  // this warpgroup meets the tiles whose running number t is congruent g mod 2
 
         // exposures of sample s of running tile t -> registers and, as tf32 hi / lo, the TMEM A operand of G1
-        auto load_h = [&](int t, int i, float (&h)[KP8]) {
+        // (stage / arrive: the first tile of a sweep is staged while the reduction of the previous sweep is still in flight --
+        // the exposures do not depend on W -- and announced to the MMA warp once the W operands have been rewritten)
+        auto load_h = [&](int t, int i, float (&h)[KP8], bool stage = true, bool arrive = true) {
             const int hs = t % NH, b = t & 1;
+            if (!stage) {
+                mbar_arrive(bar_hready + 8 * b);
+                return;
+            }
             mbar_wait(bar_hfull + 8 * hs, (t / NH) & 1);
             const uint32_t hrow = sHraw + hs * q.hraw + s * (k * 4);
             const uint32_t th = tmem + lane_off + (b ? TM_H1 : TM_H0);
@@ -484,10 +490,11 @@ __global__ void __launch_bounds__(PER_THREADS, 1) klnmf_period_tc_kernel(const _
             }
             tc_wait_st();
             tc_fence_before();
-            mbar_arrive(bar_hready + 8 * b);
+            if (arrive) mbar_arrive(bar_hready + 8 * b);
         };
 
         float h[KP8], hn[KP8];
+        bool staged = false;  // the first tile of the coming sweep is already in TMEM
 
         // the tiles of one sweep; DO_R: update (quotient written back, G2 / G3 follow); DO_KL: KL term of the incoming iterate
         auto sweep_tiles = [&](auto do_r_c, auto do_kl_c, int u) -> double {
@@ -495,7 +502,8 @@ __global__ void __launch_bounds__(PER_THREADS, 1) klnmf_period_tc_kernel(const _
             double obj_acc = 0.0;
             const int t_begin = u * n_my;
             const int i0 = (g - t_begin) & 1;  // first tile of this warpgroup in the sweep
-            if (i0 < n_my) load_h(t_begin + i0, i0, h);
+            if (i0 < n_my) load_h(t_begin + i0, i0, h, !staged, true);
+            staged = false;
             for (int i = i0; i < n_my; i += 2) {
                 const int t = t_begin + i, st = t % S, b = t & 1;
                 const int64_t d0 = (int64_t)(c + i * G) * TILE;
@@ -695,6 +703,15 @@ __global__ void __launch_bounds__(PER_THREADS, 1) klnmf_period_tc_kernel(const _
                 }
             }
 
+            if (do_r && u + 1 < U) {
+                // the coming sweep's first tile of this warpgroup: exposures to TMEM now, if they have arrived (never wait here)
+                const int tb = (u + 1) * n_my, i0n = (g - tb) & 1, tn = tb + i0n;
+                // (warp-uniform decision: the TMEM stores inside are .sync.aligned)
+                if (i0n < n_my && __all_sync(0xffffffffu, mbar_test(bar_hfull + 8 * (tn % NH), (uint32_t)((tn / NH) & 1)))) {
+                    load_h(tn, i0n, h, true, false);
+                    staged = true;
+                }
+            }
             if (do_r) {
                 // ---- stage B: every CTA polls the k * 96 totals and applies the W epilogue into its own operands ----
                 // W[j] <- clip(W[j] * N[j] / sum_v(W[j][v] N[j][v])), given signatures restored (reference _utils_klnmf.py:338-341;

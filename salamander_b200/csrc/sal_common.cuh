@@ -87,14 +87,19 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 bool sal_pdl_enabled();
 
 template <typename... KArgs, typename... Args>
-inline cudaError_t sal_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+inline cudaError_t sal_launch_pdl_if(bool overlap, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args&&... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr, cfg.numAttrs = sal_pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr, cfg.numAttrs = (overlap && sal_pdl_enabled()) ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t sal_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    return sal_launch_pdl_if(true, kernel, grid, block, smem, st, std::forward<Args>(args)...);
 }
 #endif
 

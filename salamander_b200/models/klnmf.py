@@ -43,6 +43,7 @@ class KLNMF(StandardNMF):
         # tf32 fits: a whole convergence-test period per persistent launch, reduction / exchange / W epilogue inside the
         # kernel (sal_klnmf_period, see _fit_loop_period); False falls back to the two-kernel updates below
         self.use_period_kernel = True
+        self.loop_start_event = None  # optional torch.cuda.Event the period driver records right before its first launch
         self.use_small_kernel = True  # problems that fit one SM: persistent single-CTA kernel (see _fit_loop_small)
         # multi-GPU all-reduce of the numerator: "auto" / "p2p" = one-shot NVLink exchange fused into the reduction
         # kernel (sal_klnmf_update_p2p), "nccl" = library collective between separate kernels
@@ -201,15 +202,19 @@ class KLNMF(StandardNMF):
     _QUEUE_DEPTH = 4          # launches in flight while no decision is pending
 
     def _period_path(self, st, n_given):
-        """(use the persistent period kernel?, peer exchange).  Decided collectively on several GPUs."""
+        """(use the persistent period kernel?, peer exchange).  Decided collectively on several GPUs, once per device state
+        (the agreement is a collective plus a host synchronisation: not something to repeat per fit loop)."""
         if not self.use_period_kernel or st.weights["kl"] is not None or st.weights["lhalf"] is not None or st.ws.timing:
             return False, None
-        px = None
-        ok = st.ws.period_supported(n_given, st.world)
-        if st.world > 1:
-            px = self._peer_exchange(st) if ok else None
-            ok = _dist.all_ranks_agree(ok and px is not None, st.device)
-        return ok, px
+        key = ("period_path", n_given)
+        if key not in st.weights:
+            px = None
+            ok = st.ws.period_supported(n_given, st.world)
+            if st.world > 1:
+                px = self._peer_exchange(st) if ok else None
+                ok = _dist.all_ranks_agree(ok and px is not None, st.device)
+            st.weights[key] = (ok, px)
+        return st.weights[key]
 
     def _fit_loop_period(self, st, px, n_given, verbose, verbosity_freq):
         """Fit driver on the persistent period kernel (sal_klnmf_period).  Same iterates, history and stopping iteration as
@@ -263,6 +268,8 @@ class KLNMF(StandardNMF):
                 n0, n1 = seg * freq, min((seg + m) * freq, max_it)
                 fin = final_ckpt and seg + m == n_seg
                 slot, nxt = n_launched % ring, (cur + 1) % 3
+                if n_launched == 0 and self.loop_start_event is not None:
+                    self.loop_start_event.record()  # measurement aid: device time from the driver's first launch on
                 st.ws.klnmf_period(
                     st.X, Ws[cur], Ws[nxt], Hs[cur], Hs[nxt], n_given, True, n1 - n0, freq, fin, objectives=obj_dev[slot],
                     peers=None if px is None else px.peers, state=None if px is None else px.state,

@@ -195,3 +195,35 @@ def test_two_emulated_ranks_one_update_is_exact():
     got, ref = objs[0].cpu().numpy(), o1.cpu().numpy()
     assert np.isclose(got[0], ref[0], rtol=1e-12)  # incoming iterate: same per-sample terms, another association
     assert np.isclose(got[1], ref[1], rtol=1e-6)   # after the update: W differs in the last bits
+
+
+def test_headline_config_against_the_oracle():
+    """BASELINE config 3 at full size: 96 x 1,000,000, k = 20, dtype float32 / math tf32, 20 iterations of KLNMF.fit from
+    bench.init_rows against oracle.klnmf_mt.HostKLNMF (float64, same arithmetic as oracle.klnmf.update_WH / kl_divergence,
+    reference _utils_klnmf.py:11-55, 281-361) on the FULL matrix.  North-star fp32 criteria: final KL within 1e-4 relative,
+    per-signature cosine >= 0.9999."""
+    import bench
+    import salamander_b200 as sal
+    from oracle.klnmf_mt import HostKLNMF
+    from salamander_b200 import AnnData
+
+    D, k, n_iter = 1_000_000, 20, 20
+    X32 = bench.synth_rows(0, D, k)
+    W0, H0 = bench.init_rows(X32, 0, k)
+    model = sal.models.KLNMF(n_signatures=k, init_method="custom", min_iterations=n_iter, max_iterations=n_iter, dtype="float32", math="tf32")
+    model.fit(AnnData(X32), init_kwargs={"signatures_mat": W0.copy(), "exposures_mat": H0.copy()})
+    assert model.launch_stats["driver"] == "persistent period kernel"
+    kl_gpu = model.history["objective_function"][-1]
+    host = HostKLNMF(X32.astype(np.float64))
+    W, H = W0.copy(), H0.copy()
+    for _ in range(n_iter):
+        W, H = host.update_WH(W, H)
+    kl_cpu = host.kl_divergence(W, H)
+    host.close()
+    A = np.asarray(model.asignatures.X)
+    cos = (A * W).sum(1) / (np.linalg.norm(A, axis=1) * np.linalg.norm(W, axis=1))
+    print(f"96 x 1M, k = 20, {n_iter} iterations: KL gpu {kl_gpu:.3f} cpu {kl_cpu:.3f} (rel {abs(kl_gpu - kl_cpu) / kl_cpu:.2e}), min cosine {cos.min():.9f}")
+    assert abs(kl_gpu - kl_cpu) / abs(kl_cpu) < 1e-4
+    assert cos.min() >= 0.9999
+    Hg = np.asarray(model.adata.obsm["exposures"])
+    assert np.abs(Hg - H).sum() / np.abs(H).sum() < 1e-3
