@@ -227,3 +227,40 @@ def test_headline_config_against_the_oracle():
     assert cos.min() >= 0.9999
     Hg = np.asarray(model.adata.obsm["exposures"])
     assert np.abs(Hg - H).sum() / np.abs(H).sum() < 1e-3
+
+
+@pytest.mark.parametrize("D,k,n_given", [(4099, 5, 0), (12345, 20, 1), (300, 12, 0)])
+def test_no_writes_outside_the_outputs(D, k, n_given):
+    """Guard bands (compute-sanitizer is not available on the GPU pool): every output buffer of the period kernel and of the
+    two-kernel update lies between sentinel regions that must come back untouched; inputs must not change."""
+    dev = torch.device("cuda", 0)
+    X, W, H = _problem(D, k, 21 + D, dev)
+    ws = Workspace(96, D, k, torch.float32, dev, math="tf32_always")
+    pad = 4096  # floats on either side (16-byte alignment of the views is kept)
+    SENT = -12345.0
+
+    def banded(n):
+        buf = torch.full((n + 2 * pad,), SENT, dtype=torch.float32, device=dev)
+        return buf, buf[pad : pad + n]
+
+    Wb, W_out = banded(k * 96)
+    Hb, H_out = banded(D * k)
+    ob = torch.full((4 + 2 * 8,), SENT, dtype=torch.float64, device=dev)
+    objs = ob[8:12]
+    X0, W0, H0 = X.clone(), W.clone(), H.clone()
+    ws.klnmf_period(X, W, W_out.view(k, 96), H, H_out.view(D, k), n_given, True, 6, 2, True, objectives=objs)
+    torch.cuda.synchronize()
+    for buf, n in ((Wb, k * 96), (Hb, D * k)):
+        assert bool((buf[:pad] == SENT).all()) and bool((buf[pad + n :] == SENT).all())
+    assert bool((ob[:8] == SENT).all()) and bool((ob[12:] == SENT).all())
+    assert bool((objs > 0).all()) and bool(torch.isfinite(W_out).all()) and bool(torch.isfinite(H_out).all())
+    assert torch.equal(X, X0) and torch.equal(W, W0) and torch.equal(H, H0)
+    # the two-kernel update through the same bands
+    Wb.fill_(SENT), Hb.fill_(SENT)
+    Wnum = torch.empty_like(W)
+    ws.klnmf_update(X, W, W_out.view(k, 96), H, H_out.view(D, k), n_given, True, Wnum)
+    torch.cuda.synchronize()
+    for buf, n in ((Wb, k * 96), (Hb, D * k)):
+        assert bool((buf[:pad] == SENT).all()) and bool((buf[pad + n :] == SENT).all())
+    assert torch.equal(X, X0) and torch.equal(W, W0) and torch.equal(H, H0)
+    ws.close()
