@@ -228,6 +228,19 @@ int sal_mvnmf_w_unconstrained(sal_handle_t h, const void* W, const void* N, cons
 int sal_mvnmf_trial(sal_handle_t h, const void* W, const void* W_unc, double gamma_blend, double delta,
                     void* W_trial, void* h_scale, double* logdet_out, void* stream);
 
+/*
+ * Small MvNMF problems (D_local <= 256, state fits the shared memory of one SM -- BASELINE config 1, MvNMF on 96 x 192):
+ * n_iterations whole iterations of MvNMF._update_parameters (models/mvnmf.py:190-210: update_H, update_W_unconstrained
+ * :37-66, line_search :69-92 with normalize_WH utils.py:155-158) in ONE launch of a single persistent CTA, back-tracking
+ * included; *objective (optional) receives the penalised objective (kl_divergence_penalized, :27-34) of the INCOMING
+ * iterate.  gamma (the step size that persists across iterations, mvnmf.py:177-188) is read from *gamma_in and left in
+ * *gamma_out (device doubles; may alias).  W_out / H_out may alias the inputs.
+ */
+int sal_mvnmf_small_supported(sal_handle_t h);
+int sal_mvnmf_small_updates(sal_handle_t h, const void* X, const void* W_in, void* W_out, const void* H_in, void* H_out, double lam,
+                            double delta, int n_given, int n_iterations, const double* gamma_in, double* gamma_out,
+                            double* objective, void* stream);
+
 /* ---- correlated NMF (models/_utils_corrnmf.py, models/corrnmf_det.py) -------------------------------------
  * a [k] signature scalings, b [D] sample scalings, L [k][m] signature embeddings, U [D][m] sample embeddings,
  * auxT [D][k] (= sal_klnmf_pass UPDATE_H | NOCLIP on the exposures), m = dim_embeddings <= sal_corrnmf_max_dim().

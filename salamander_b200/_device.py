@@ -259,6 +259,33 @@ class Workspace:
             "sal_klnmf_small_updates",
         )
 
+    def mvnmf_small_supported(self) -> bool:
+        return bool(self.lib.sal_mvnmf_small_supported(self._h))
+
+    def mvnmf_small_updates(self, X, W_in, W_out, H_in, H_out, lam: float, delta: float, n_given: int, n_iterations: int,
+                            gamma_in, gamma_out, objective=None) -> None:
+        """``n_iterations`` whole MvNMF iterations (line search included) in one launch of a single persistent CTA."""
+        V, D, k = self.V, self.D, self.k
+        _lib.check(
+            self.lib.sal_mvnmf_small_updates(
+                self._h,
+                self._ptr(X, D * V, "X"),
+                self._ptr(W_in, k * V, "W_in"),
+                self._ptr(W_out, k * V, "W_out"),
+                self._ptr(H_in, D * k, "H_in"),
+                self._ptr(H_out, D * k, "H_out"),
+                float(lam),
+                float(delta),
+                int(n_given),
+                int(n_iterations),
+                self._ptr(gamma_in, 1, "gamma_in", torch.float64),
+                self._ptr(gamma_out, 1, "gamma_out", torch.float64),
+                self._ptr(objective, 1, "objective", torch.float64),
+                self._stream(),
+            ),
+            "sal_mvnmf_small_updates",
+        )
+
     def w_epilogue(self, W_in, Wnum, n_given: int, clip_given: bool, W_out) -> None:
         kv = self.k * self.V
         _lib.check(

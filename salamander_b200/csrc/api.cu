@@ -386,6 +386,24 @@ int sal_klnmf_small_updates(sal_handle_t h, const void* X, const void* W_in, voi
     return sal_launch_klnmf_small(h, X, W_in, W_out, H_in, H_out, n_given, n_iterations, objective, (cudaStream_t)stream);
 }
 
+int sal_mvnmf_small_supported(sal_handle_t h) { return h && sal_mvnmf_small_ok(h) ? 1 : 0; }
+
+int sal_mvnmf_small_updates(sal_handle_t h, const void* X, const void* W_in, void* W_out, const void* H_in, void* H_out, double lam,
+                            double delta, int n_given, int n_iterations, const double* gamma_in, double* gamma_out,
+                            double* objective, void* stream) {
+    SAL_CHECK_ARG(h != nullptr, "handle is null");
+    SAL_CHECK_ARG(X && W_in && W_out && H_in && H_out && gamma_in && gamma_out, "null argument");
+    SAL_CHECK_ARG(n_given >= 0 && n_given <= h->k && n_iterations >= 0, "n_given / n_iterations out of range");
+    SAL_CHECK_ARG(lam > 0.0, "lam must be positive");
+    if (!sal_mvnmf_small_ok(h)) {
+        sal_set_error("sal_mvnmf_small_updates: problem does not fit one CTA (D <= 256 and ~220 KB of shared memory)");
+        return SAL_EUNSUPPORTED;
+    }
+    SAL_CUDA(cudaSetDevice(h->device));
+    return sal_launch_mvnmf_small(h, X, W_in, W_out, H_in, H_out, lam, delta, n_given, n_iterations, gamma_in, gamma_out, objective,
+                                  (cudaStream_t)stream);
+}
+
 int sal_w_epilogue(sal_handle_t h, const void* W_in, const void* Wnum, int n_given, int clip_given,
                    void* W_out, void* stream) {
     SAL_CHECK_ARG(h != nullptr, "handle is null");

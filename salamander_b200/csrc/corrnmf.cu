@@ -20,6 +20,8 @@
 
 #include "sal_common.cuh"
 
+#include <string.h>
+
 namespace cg = cooperative_groups;
 
 namespace {
@@ -599,14 +601,23 @@ int sal_launch_corrnmf_signature_embeddings(sal_ctx* c, const void* auxT, const 
     attr.val.clusterDim.y = 1, attr.val.clusterDim.z = 1;
     cfg.attrs = &attr, cfg.numAttrs = 1;
     if (sig_count <= 8 && c->D >= 16 * 8 * SIG_THREADS) {
-        const void* fn = c->dtype == SAL_F32 ? (const void*)signature_embeddings_kernel<float> : (const void*)signature_embeddings_kernel<double>;
-        int n_active = 0;
-        attr.val.clusterDim.x = 16;
-        cfg.gridDim = dim3(sig_count * 16);
-        if (cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
-            cudaOccupancyMaxActiveClusters(&n_active, fn, &cfg) == cudaSuccess && n_active >= sig_count)
-            csize = 16;
-        (void)cudaGetLastError();  // a refused query is not an error of this call: fall back to the portable size
+        // (the occupancy query can take tens of milliseconds: asked once per device, dtype and signature count)
+        static signed char cached[64][2][9];
+        static bool cached_init = false;
+        if (!cached_init) memset(cached, -1, sizeof(cached)), cached_init = true;
+        signed char& ok16 = cached[c->device & 63][c->dtype == SAL_F32 ? 0 : 1][sig_count];
+        if (ok16 < 0) {
+            const void* fn = c->dtype == SAL_F32 ? (const void*)signature_embeddings_kernel<float> : (const void*)signature_embeddings_kernel<double>;
+            int n_active = 0;
+            attr.val.clusterDim.x = 16;
+            cfg.gridDim = dim3(sig_count * 16);
+            ok16 = (cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+                    cudaOccupancyMaxActiveClusters(&n_active, fn, &cfg) == cudaSuccess && n_active >= sig_count)
+                       ? 1
+                       : 0;
+            (void)cudaGetLastError();  // a refused query is not an error of this call: fall back to the portable size
+        }
+        if (ok16 == 1) csize = 16;
     }
     if (const char* e = getenv("SAL_B200_SIG_CLUSTER")) {  // diagnostics: force the cluster size (1, 8 or 16)
         const int forced = atoi(e);

@@ -315,8 +315,8 @@ klnmf_pass_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
             mbar_wait(bar_hfull + 8 * hs, (i / NH) & 1);
             const uint32_t hrow = sHraw + hs * q.hraw + s * (k * 4);
             const uint32_t th = tmem + lane_off + (b ? TM_H1 : TM_H0);
-            bool row_valid = true;
-            if (HS) row_valid = (int64_t)((int)blockIdx.x + i * (int)gridDim.x) * TILE + s < p.D;
+            // rows past the end of X (zero-filled by TMA) are read as 1: WH > 0, the zero counts give a zero quotient
+            const bool row_valid = (int64_t)((int)blockIdx.x + i * (int)gridDim.x) * TILE + s < p.D;
 #pragma unroll
             for (int j = 0; j < KP8; j += 8) {
                 if (GK) {  // rows are not 16-byte aligned: scalar loads
@@ -332,7 +332,12 @@ klnmf_pass_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
                 if (HS) {  // normalize_WH folded into the read (reference utils.py:155-158 as used by mvnmf.py:80-88)
 #pragma unroll
                     for (int e = 0; e < 8; ++e)
-                        if (j + e < k) h[j + e] = row_valid ? fmaxf(h[j + e] * __ldg(p.h_scale + j + e), eps) : 0.f;
+                        if (j + e < k) h[j + e] = fmaxf(h[j + e] * __ldg(p.h_scale + j + e), eps);
+                }
+                if (!row_valid) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e)
+                        if (j + e < k) h[j + e] = 1.f;
                 }
                 uint32_t hi[8], lo[8];
 #pragma unroll
@@ -361,48 +366,10 @@ klnmf_pass_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
             stamp(p.dbg, tlw, g, i, 3);
             tc_fence_after();
             const uint32_t tWH = tmem + lane_off + (b ? TM_WH1 : TM_WH0);
-            float kl = 0.f;
-            {
-                // software pipeline over the three boxes: the TMEM load of box c + 1 is in flight while box c is divided
-                uint32_t v0[32], v1[32];
-                const uint32_t rowbase = sX + st * XSTAGE_BYTES + s * 128;
-                tmem_ld32(tWH, v0);
-                tc_wait_ld();
-                tmem_ld32(tWH + 32, v1);
-                if (!valid) {  // rows past the end of X: x = 0 (TMA zero fill), make the quotient 0 * 1
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) v0[e] = 0x3f800000u;
-                }
-                quotient_box<DO_R, DO_KL>(v0, rowbase, s, sw, kl);
-                if (DO_R) tmem_st32(tWH, v0);
-                if (p.dbg && blockIdx.x == 0 && i == 0) {
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) p.dbg[(size_t)s * VT + e] = __uint_as_float(v0[e]);
-                }
-                tc_wait_ld();
-                tmem_ld32(tWH + 64, v0);
-                if (!valid) {
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) v1[e] = 0x3f800000u;
-                }
-                quotient_box<DO_R, DO_KL>(v1, rowbase + BOX_BYTES, s, sw, kl);
-                if (DO_R) tmem_st32(tWH + 32, v1);
-                if (p.dbg && blockIdx.x == 0 && i == 0) {
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) p.dbg[(size_t)s * VT + 32 + e] = __uint_as_float(v1[e]);
-                }
-                tc_wait_ld();
-                if (!valid) {
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) v0[e] = 0x3f800000u;
-                }
-                quotient_box<DO_R, DO_KL>(v0, rowbase + 2 * BOX_BYTES, s, sw, kl);
-                if (DO_R) tmem_st32(tWH + 64, v0);
-                if (p.dbg && blockIdx.x == 0 && i == 0) {
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) p.dbg[(size_t)s * VT + 64 + e] = __uint_as_float(v0[e]);
-                }
-            }
+            // the quotient as a six-step loop (instruction-cache resident; see quotient_row_loop).  Rows past the end of X need
+            // no special case: their exposures were read as 1 (load_h), so WH > 0 and the zero-filled X gives a zero quotient
+            const float kl = quotient_row_loop<DO_R, DO_KL>(tWH, sX + st * XSTAGE_BYTES + s * 128, s, sw,
+                                                            (p.dbg && blockIdx.x == 0 && i == 0) ? p.dbg + (size_t)s * VT : nullptr);
             float wk = 1.f, lam = 0.f;
             if (WT && valid) {
                 if (p.w_kl) wk = __ldg(p.w_kl + d0 + s);

@@ -1,0 +1,438 @@
+// Small-problem MvNMF: the whole fit state lives in ONE CTA and a launch runs many iterations, line search included.
+//
+// BASELINE config 1 (MvNMF n_signatures = 10 on 96 x 192 PCAWG counts) is launch-latency bound when every step is its own
+// kernel (3 passes + 4 single-CTA kernels + a host decision per line-search trial: ~190 us per iteration).  Here one
+// 1024-thread CTA keeps X in registers (thread (d, q) owns 24 features of sample d), W / H / the quotient in shared memory and
+// performs `n_iter` iterations of reference MvNMF._update_parameters (models/mvnmf.py:190-210) back to back:
+//
+//   H step                  update_H                  _utils_klnmf.py:220-264
+//   previous objective      kl_divergence_penalized   mvnmf.py:27-34 (KL of (W, H') + lam * volume_logdet(W), :19-24)
+//   unconstrained W step    update_W_unconstrained    mvnmf.py:37-66  (numerator N = (X / (W H')) H'^T, row sums of H')
+//   line search             line_search               mvnmf.py:69-92  (first trial without gamma, then gamma <- 0.8 gamma while
+//                                                     the penalised objective went up; normalize_WH utils.py:155-158 + clip;
+//                                                     gamma <- min(1, 1.2 gamma) persists across iterations, mvnmf.py:177-188)
+//
+// The penalised objective of the INCOMING iterate is produced on the way (what the period-wise fit driver needs).
+// Arithmetic in the handle's dtype with fixed summation orders (deterministic); the k x k algebra, the logarithms and every
+// objective sum are float64.  gamma lives in device memory (gamma_in -> gamma_out).
+#include "sal_common.cuh"
+
+namespace {
+
+constexpr int NT = 1024;          // 4 threads per sample
+constexpr int VQ = SAL_VMAX / 4;  // 24 features per thread
+constexpr int RP = SAL_VMAX + 1;  // pitch of the quotient tile
+constexpr int WP = SAL_VMAX;      // pitch of the [k][V] matrices
+
+__device__ __forceinline__ float tdiv(float x, float y) { return x / y; }
+__device__ __forceinline__ double tdiv(double x, double y) {  // reciprocal seed + two Newton steps + residual correction (<= 1 ulp)
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(y));
+    double e = fma(-y, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-y, r, 1.0);
+    r = fma(r, e, r);
+    const double q = x * r;
+    return fma(fma(-y, q, x), r, q);
+}
+
+struct Shared {  // block-wide scalars and the k x k scratch (float64)
+    double red[NT / 32];
+    double colsum[SAL_KMAX];
+    double col[SAL_KMAX];
+    double hsum[SAL_KMAX];
+    double bcast[4];
+    int piv;
+};
+
+__device__ double block_sum(double v, Shared& sh) {  // fixed order; result on every thread
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();  // (sh.red may still be read from the previous call)
+    if ((threadIdx.x & 31) == 0) sh.red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int w = 0; w < NT / 32; ++w) t += sh.red[w];
+    return t;
+}
+
+// G = M M^T + delta I for M [k][WP] in shared memory
+template <typename T>
+__device__ void gram(const T* M, double* G, int GP, int V, int k, double delta) {
+    for (int i = threadIdx.x; i < k * k; i += NT) {
+        const int a = i / k, b = i - a * k;
+        double t = 0.0;
+        for (int v = 0; v < V; ++v) t += (double)M[a * WP + v] * (double)M[b * WP + v];
+        G[a * GP + b] = t + (a == b ? delta : 0.0);
+    }
+    __syncthreads();
+}
+
+// The k x k factorisations run on WARP 0 alone (k <= 32: a lane per row, __syncwarp between the steps): with 1024 threads every
+// block-wide barrier of a column step costs more than the step itself.  Same pivoting rule as mvnmf.cu (first row of maximal
+// magnitude: numpy.linalg.det / inv go through LAPACK getrf).
+
+// pivot row of column c among rows c .. k - 1 (lowest index among equals); result on every lane
+__device__ __forceinline__ int pivot_row(const double* G, int GP, int k, int c) {
+    const int lane = threadIdx.x & 31;
+    double a = (lane >= c && lane < k) ? fabs(G[lane * GP + c]) : -1.0;
+    int p = lane;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double oa = __shfl_xor_sync(0xffffffffu, a, o);
+        const int op = __shfl_xor_sync(0xffffffffu, p, o);
+        if (oa > a || (oa == a && op < p)) a = oa, p = op;
+    }
+    return p;
+}
+
+// In-place LU with partial pivoting; returns det on every lane of warp 0 (call from warp 0 only)
+__device__ double lu_det_warp(double* G, int GP, int k) {
+    const int lane = threadIdx.x & 31;
+    double sign = 1.0;
+    for (int c = 0; c < k; ++c) {
+        const int p = pivot_row(G, GP, k, c);
+        if (p != c) {
+            sign = -sign;
+            if (lane < k) {
+                const double t = G[c * GP + lane];
+                G[c * GP + lane] = G[p * GP + lane];
+                G[p * GP + lane] = t;
+            }
+            __syncwarp();
+        }
+        const double d = G[c * GP + c];
+        const int nr = k - c - 1;
+        if (lane < nr) G[(c + 1 + lane) * GP + c] /= d;
+        __syncwarp();
+        for (int i = lane; i < nr * nr; i += 32) {
+            const int r = c + 1 + i / nr, j = c + 1 + i % nr;
+            G[r * GP + j] -= G[r * GP + c] * G[c * GP + j];
+        }
+        __syncwarp();
+    }
+    double det = sign;
+    for (int c = 0; c < k; ++c) det *= G[c * GP + c];
+    return det;
+}
+
+// Y = G^-1 by Gauss-Jordan with partial pivoting (G destroyed); warp 0 only
+__device__ void invert_warp(double* G, double* Y, double* col, int GP, int k) {
+    const int lane = threadIdx.x & 31;
+    for (int i = lane; i < k * k; i += 32) Y[(i / k) * GP + i % k] = (i / k == i % k) ? 1.0 : 0.0;
+    __syncwarp();
+    for (int c = 0; c < k; ++c) {
+        const int p = pivot_row(G, GP, k, c);
+        if (p != c) {
+            for (int j = lane; j < 2 * k; j += 32) {
+                double* M = j < k ? G : Y;
+                const int jj = j < k ? j : j - k;
+                const double t = M[c * GP + jj];
+                M[c * GP + jj] = M[p * GP + jj];
+                M[p * GP + jj] = t;
+            }
+            __syncwarp();
+        }
+        const double inv_d = 1.0 / G[c * GP + c];
+        __syncwarp();
+        for (int j = lane; j < 2 * k; j += 32) {
+            double* M = j < k ? G : Y;
+            M[c * GP + (j < k ? j : j - k)] *= inv_d;
+        }
+        __syncwarp();
+        if (lane < k) col[lane] = G[lane * GP + c];  // column c before the elimination
+        __syncwarp();
+        for (int i = lane; i < k * 2 * k; i += 32) {
+            const int r = i / (2 * k), j = i - r * 2 * k;
+            if (r == c) continue;
+            double* M = j < k ? G : Y;
+            const int jj = j < k ? j : j - k;
+            M[r * GP + jj] -= col[r] * M[c * GP + jj];
+        }
+        __syncwarp();
+    }
+}
+
+template <typename T, int KT>
+__global__ void __launch_bounds__(NT, 1)
+mvnmf_small_kernel(const T* X, const T* W_in, T* W_out, const T* H_in, T* H_out, int D, int V, int k, double lam, double delta,
+                   int n_given, int n_iter, const double* gamma_in, double* gamma_out, double* objective) {
+    extern __shared__ __align__(16) unsigned char raw[];
+    T* sR = reinterpret_cast<T*>(raw);     // [D][RP]  quotient X / (W H')
+    T* sH = sR + (size_t)D * RP;           // [D][k]
+    T* sW = sH + (size_t)D * k;            // [k][WP]
+    T* sWu = sW + (size_t)k * WP;          // [k][WP]  numerator N, then W_unconstrained
+    T* sWt = sWu + (size_t)k * WP;         // [k][WP]  line-search candidate
+    const int GP = k + 1;
+    const size_t t_bytes = sizeof(T) * ((size_t)D * RP + (size_t)D * k + 3 * (size_t)k * WP);
+    double* G = reinterpret_cast<double*>(raw + ((t_bytes + 7) & ~(size_t)7));  // [k][GP] Gram / LU scratch
+    double* Y = G + k * GP;                                                     // [k][GP] inverse
+    __shared__ Shared sh;
+    const int tid = threadIdx.x, d = tid >> 2, q = tid & 3, v0 = q * VQ;
+    const T eps = (T)SAL_EPS_F32;
+    const bool row = d < D;
+
+    T x[VQ];
+#pragma unroll
+    for (int i = 0; i < VQ; ++i) x[i] = (row && v0 + i < V) ? X[(size_t)d * V + v0 + i] : (T)0;
+    for (int i = tid; i < k * V; i += NT) sW[(i / V) * WP + i % V] = W_in[i];
+    for (int i = tid; i < k * WP; i += NT) sWt[i] = (T)0, sWu[i] = (T)0;
+    for (int i = tid; i < D * k; i += NT) sH[i] = H_in[i];
+    double gamma = *gamma_in;
+    __syncthreads();
+
+    // KL(X || M h) over this thread's 24 features with float64 terms (x = 0 contributes m h)
+    auto kl_row = [&](const T* M, const T (&hv)[KT]) {
+        double kl = 0.0;
+        if (row) {
+#pragma unroll 2
+            for (int i = 0; i < VQ; ++i) {
+                const int v = v0 + i;
+                if (v < V) {
+                    double wh = 0.0;
+#pragma unroll
+                    for (int j = 0; j < KT; ++j)
+                        if (j < k) wh += (double)M[j * WP + v] * (double)hv[j];
+                    const double xd = (double)x[i];
+                    kl += xd != 0.0 ? xd * log(xd / wh) - xd + wh : wh;
+                }
+            }
+        }
+        return kl;
+    };
+    auto logdet = [&](const T* M) {  // block-uniform result
+        gram(M, G, GP, V, k, delta);
+        if (tid < 32) {
+            const double det = lu_det_warp(G, GP, k);
+            if (tid == 0) sh.bcast[0] = log(det);
+        }
+        __syncthreads();
+        const double r = sh.bcast[0];
+        __syncthreads();
+        return r;
+    };
+
+    double ld_W = 0.0;  // lam-free volume of the current W; carried from the accepted candidate of the previous iteration
+    bool have_ld = false;
+    const int n_pass = n_iter > 0 ? n_iter : (objective ? 1 : 0);
+    for (int it = 0; it < n_pass; ++it) {
+        T hd[KT];
+#pragma unroll
+        for (int j = 0; j < KT; ++j) hd[j] = (row && j < k) ? sH[d * k + j] : (T)0;
+        if (it == 0 && objective) {  // penalised objective of the incoming iterate
+            const double kl = block_sum(kl_row(sW, hd), sh);
+            ld_W = logdet(sW), have_ld = true;
+            if (tid == 0) *objective = kl + lam * ld_W;
+        }
+        if (it >= n_iter) break;  // objective-only call
+        // ---- H step: hn = W^T (X / (W h)), h' = clip(h * hn) ----
+        T hn[KT];
+#pragma unroll
+        for (int j = 0; j < KT; ++j) hn[j] = (T)0;
+        if (row) {
+#pragma unroll(KT <= 8 ? VQ : 2)
+            for (int i = 0; i < VQ; ++i) {
+                const int v = v0 + i;
+                if (v < V) {
+                    T wv[KT];
+                    T wh = (T)0;
+#pragma unroll
+                    for (int j = 0; j < KT; ++j) wv[j] = j < k ? sW[j * WP + v] : (T)0, wh += wv[j] * hd[j];
+                    const T r = tdiv(x[i], wh);
+#pragma unroll
+                    for (int j = 0; j < KT; ++j) hn[j] += wv[j] * r;
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < KT; ++j) {
+            T t = hn[j];
+            t += __shfl_xor_sync(0xffffffffu, t, 1);
+            t += __shfl_xor_sync(0xffffffffu, t, 2);
+            hd[j] = (row && j < k) ? max(hd[j] * t, eps) : (T)0;  // h' (identical on the four threads of a sample)
+        }
+        if (n_given >= k) {  // all signatures given: the iteration is the H step (reference mvnmf.py:190-196)
+            __syncthreads();
+            if (row && q == 0) {
+#pragma unroll
+                for (int j = 0; j < KT; ++j)
+                    if (j < k) sH[d * k + j] = hd[j];
+            }
+            __syncthreads();
+            continue;
+        }
+        // ---- quotient with the new exposures, previous KL, numerator N = (X / (W H')) H'^T, row sums of H' ----
+        double kl_prev = 0.0;
+        if (row) {
+#pragma unroll(KT <= 8 ? VQ : 2)
+            for (int i = 0; i < VQ; ++i) {
+                const int v = v0 + i;
+                if (v < V) {
+                    T wh = (T)0;
+                    double whd = 0.0;
+#pragma unroll
+                    for (int j = 0; j < KT; ++j)
+                        if (j < k) {
+                            const T w = sW[j * WP + v];
+                            wh += w * hd[j];
+                            if (sizeof(T) == 4) whd += (double)w * (double)hd[j];
+                        }
+                    sR[d * RP + v] = tdiv(x[i], wh);
+                    const double xd = (double)x[i], wd = sizeof(T) == 4 ? whd : (double)wh;
+                    kl_prev += xd != 0.0 ? xd * log(xd / wd) - xd + wd : wd;
+                }
+            }
+        }
+        __syncthreads();  // every read of the old sH is done
+        if (row && q == 0) {
+#pragma unroll
+            for (int j = 0; j < KT; ++j)
+                if (j < k) sH[d * k + j] = hd[j];
+        }
+        kl_prev = block_sum(kl_prev, sh);  // (its barriers also publish sR and the new sH)
+        for (int i = tid; i < k * V; i += NT) {
+            const int j = i / V, v = i - j * V;
+            T a0 = (T)0, a1 = (T)0, a2 = (T)0, a3 = (T)0;
+            int dd = 0;
+            for (; dd + 3 < D; dd += 4) {
+                a0 += sR[dd * RP + v] * sH[dd * k + j];
+                a1 += sR[(dd + 1) * RP + v] * sH[(dd + 1) * k + j];
+                a2 += sR[(dd + 2) * RP + v] * sH[(dd + 2) * k + j];
+                a3 += sR[(dd + 3) * RP + v] * sH[(dd + 3) * k + j];
+            }
+            for (; dd < D; ++dd) a0 += sR[dd * RP + v] * sH[dd * k + j];
+            sWu[j * WP + v] = (a0 + a1) + (a2 + a3);
+        }
+        {
+            const int w = tid >> 5, lane = tid & 31;
+            if (w < k) {
+                double t = 0.0;
+                for (int dd = lane; dd < D; dd += 32) t += (double)sH[dd * k + w];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+                if (lane == 0) sh.hsum[w] = (double)(T)t;
+            }
+        }
+        __syncthreads();
+        if (!have_ld) ld_W = logdet(sW), have_ld = true;
+        const double prev = kl_prev + lam * ld_W;
+        // ---- unconstrained W step (mvnmf.py:37-66) ----
+        gram(sW, G, GP, V, k, delta);
+        if (tid < 32) invert_warp(G, Y, sh.col, GP, k);
+        __syncthreads();
+        for (int i = tid; i < k * V; i += NT) {
+            const int j = i / V, v = i - j * V;
+            const double w = (double)sW[j * WP + v];
+            double out;
+            if (j < n_given) {
+                out = w;
+            } else {
+                double wym = 0.0, wya = 0.0;
+                for (int a = 0; a < k; ++a) {
+                    const double y = Y[a * GP + j];
+                    const double wa = (double)sW[a * WP + v];
+                    wym += wa * fmax(0.0, -y);
+                    wya += wa * fabs(y);
+                }
+                const double r = sh.hsum[j];
+                const double a1 = r - 4.0 * lam * wym;
+                const double s2 = 8.0 * lam * wya * (double)sWu[j * WP + v];
+                const double num = sqrt(a1 * a1 + s2) + (-r + 4.0 * lam * wym);
+                out = fmax(w * num / (4.0 * lam * wya), (double)SAL_EPS_F32);
+            }
+            sWu[j * WP + v] = (T)out;
+        }
+        __syncthreads();
+        // ---- line search (mvnmf.py:69-92): candidate = normalise + clip of W_u (first) or of the blend with W ----
+        double g_blend = -1.0, ld_t = 0.0;
+        while (true) {
+            for (int i = tid; i < k * V; i += NT) {
+                const int j = i / V, v = i - j * V;
+                const double wu = (double)sWu[j * WP + v];
+                sWt[j * WP + v] = (T)(g_blend < 0.0 ? wu : (1.0 - g_blend) * (double)sW[j * WP + v] + g_blend * wu);
+            }
+            __syncthreads();
+            {  // column sums of the candidate: a warp per signature
+                const int w = tid >> 5, lane = tid & 31;
+                if (w < k) {
+                    double t = 0.0;
+                    for (int v = lane; v < V; v += 32) t += (double)sWt[w * WP + v];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+                    if (lane == 0) sh.colsum[w] = (double)(T)t;
+                }
+            }
+            __syncthreads();
+            for (int i = tid; i < k * V; i += NT) {
+                const int j = i / V, v = i - j * V;
+                sWt[j * WP + v] = (T)fmax((double)sWt[j * WP + v] / sh.colsum[j], (double)SAL_EPS_F32);
+            }
+            __syncthreads();
+            ld_t = logdet(sWt);
+            T ht[KT];
+#pragma unroll
+            for (int j = 0; j < KT; ++j) ht[j] = (row && j < k) ? max(hd[j] * (T)sh.colsum[j], eps) : (T)0;
+            const double val = block_sum(kl_row(sWt, ht), sh) + lam * ld_t;
+            if (!(val > prev && gamma > 1e-16)) break;
+            gamma *= 0.8;
+            g_blend = gamma;
+            __syncthreads();  // sh.colsum is rewritten by the next candidate
+        }
+        gamma = fmin(1.0, 1.2 * gamma);
+        ld_W = ld_t;
+        // ---- accept: W <- candidate, H <- clip(H' * colsum) ----
+        for (int i = tid; i < k * V; i += NT) sW[(i / V) * WP + i % V] = sWt[(i / V) * WP + i % V];
+        if (row && q == 0) {
+#pragma unroll
+            for (int j = 0; j < KT; ++j)
+                if (j < k) sH[d * k + j] = max(hd[j] * (T)sh.colsum[j], eps);
+        }
+        __syncthreads();
+    }
+    for (int i = tid; i < k * V; i += NT) W_out[i] = sW[(i / V) * WP + i % V];
+    for (int i = tid; i < D * k; i += NT) H_out[i] = sH[i];
+    if (tid == 0) *gamma_out = gamma;
+}
+
+template <typename T>
+size_t small_smem(int D, int k) {
+    return sizeof(T) * ((size_t)D * RP + (size_t)D * k + 3 * (size_t)k * WP) + 8 + sizeof(double) * 2 * (size_t)k * (k + 1);
+}
+
+template <typename T, int KT>
+int launch_t(sal_ctx* c, const void* X, const void* W_in, void* W_out, const void* H_in, void* H_out, double lam, double delta,
+             int n_given, int n_iter, const double* gamma_in, double* gamma_out, double* objective, cudaStream_t st) {
+    const size_t smem = small_smem<T>((int)c->D, c->k);
+    SAL_CUDA(cudaFuncSetAttribute(mvnmf_small_kernel<T, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mvnmf_small_kernel<T, KT><<<1, NT, smem, st>>>((const T*)X, (const T*)W_in, (T*)W_out, (const T*)H_in, (T*)H_out, (int)c->D, c->V,
+                                                   c->k, lam, delta, n_given, n_iter, gamma_in, gamma_out, objective);
+    SAL_CUDA(cudaGetLastError());
+    c->launches++;
+    return 0;
+}
+
+template <typename T>
+int launch_k(sal_ctx* c, const void* X, const void* W_in, void* W_out, const void* H_in, void* H_out, double lam, double delta,
+             int n_given, int n_iter, const double* gamma_in, double* gamma_out, double* objective, cudaStream_t st) {
+    if (c->k <= 4) return launch_t<T, 4>(c, X, W_in, W_out, H_in, H_out, lam, delta, n_given, n_iter, gamma_in, gamma_out, objective, st);
+    if (c->k <= 8) return launch_t<T, 8>(c, X, W_in, W_out, H_in, H_out, lam, delta, n_given, n_iter, gamma_in, gamma_out, objective, st);
+    if (c->k <= 12) return launch_t<T, 12>(c, X, W_in, W_out, H_in, H_out, lam, delta, n_given, n_iter, gamma_in, gamma_out, objective, st);
+    if (c->k <= 16) return launch_t<T, 16>(c, X, W_in, W_out, H_in, H_out, lam, delta, n_given, n_iter, gamma_in, gamma_out, objective, st);
+    return launch_t<T, 32>(c, X, W_in, W_out, H_in, H_out, lam, delta, n_given, n_iter, gamma_in, gamma_out, objective, st);
+}
+
+}  // namespace
+
+bool sal_mvnmf_small_ok(const sal_ctx* c) {
+    if (c->D < 1 || c->D > NT / 4) return false;
+    const size_t smem = c->dtype == SAL_F32 ? small_smem<float>((int)c->D, c->k) : small_smem<double>((int)c->D, c->k);
+    return smem <= 220 * 1024;
+}
+
+int sal_launch_mvnmf_small(sal_ctx* c, const void* X, const void* W_in, void* W_out, const void* H_in, void* H_out, double lam,
+                           double delta, int n_given, int n_iter, const double* gamma_in, double* gamma_out, double* objective,
+                           cudaStream_t st) {
+    return c->dtype == SAL_F32
+               ? launch_k<float>(c, X, W_in, W_out, H_in, H_out, lam, delta, n_given, n_iter, gamma_in, gamma_out, objective, st)
+               : launch_k<double>(c, X, W_in, W_out, H_in, H_out, lam, delta, n_given, n_iter, gamma_in, gamma_out, objective, st);
+}

@@ -158,6 +158,12 @@ struct PeriodArgs {
 bool sal_period_supported(const sal_ctx* c, const PeriodArgs& a);
 int sal_launch_period(sal_ctx* const* cs, int n_virtual, const PeriodArgs* as, cudaStream_t st);
 
+// ---- small-problem MvNMF (mvnmf_small.cu) ------------------------------------------------------------------
+bool sal_mvnmf_small_ok(const sal_ctx* c);
+int sal_launch_mvnmf_small(sal_ctx* c, const void* X, const void* W_in, void* W_out, const void* H_in, void* H_out, double lam,
+                           double delta, int n_given, int n_iter, const double* gamma_in, double* gamma_out, double* objective,
+                           cudaStream_t st);
+
 // ---- small-problem persistent kernel (klnmf_small.cu) ----------------------------------------------------
 bool sal_small_supported(const sal_ctx* c);
 int sal_launch_klnmf_small(sal_ctx* c, const void* X, const void* W_in, void* W_out, const void* H_in, void* H_out, int n_given,

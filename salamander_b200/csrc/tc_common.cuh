@@ -356,7 +356,7 @@ __device__ __forceinline__ void tmem_st8_(uint32_t taddr, const uint32_t (&v)[8]
 // ~150 instructions and stays in the instruction cache.  Rows past the end of X need no special case here: their exposures are
 // read as 1 (see load_h), so WH > 0 and the zero-filled X gives a zero quotient.  Returns the row's KL term (DO_KL).
 template <bool DO_R, bool DO_KL>
-__device__ __forceinline__ float quotient_row_loop(uint32_t tWH, uint32_t rowbase, int s, uint32_t sw) {
+__device__ __forceinline__ float quotient_row_loop(uint32_t tWH, uint32_t rowbase, int s, uint32_t sw, float* dbg_row = nullptr) {
     float kl0 = 0.f, kl1 = 0.f;
     const uint32_t s3 = (uint32_t)(s & 3);
     const uint32_t off_a = sw * 16, off_b = (sw ^ 1u) * 16;
@@ -387,6 +387,10 @@ __device__ __forceinline__ float quotient_row_loop(uint32_t tWH, uint32_t rowbas
             // round-to-nearest tf32 = add half an ulp; the MMA ignores the 13 low mantissa bits, no need to mask them
 #pragma unroll
             for (int e = 0; e < 8; ++e) rb[e] = __float_as_uint(r[e]) + 0x1000u;
+            if (dbg_row) {  // diagnostics: the quotient as the MMAs will read it
+#pragma unroll
+                for (int e = 0; e < 8; ++e) dbg_row[8 * c + e] = __uint_as_float(rb[e]);
+            }
             const float4 rlo = make_float4(__uint_as_float(rb[0]), __uint_as_float(rb[1]), __uint_as_float(rb[2]), __uint_as_float(rb[3]));
             const float4 rhi = make_float4(__uint_as_float(rb[4]), __uint_as_float(rb[5]), __uint_as_float(rb[6]), __uint_as_float(rb[7]));
             const uint32_t a = chunk_addr(c);

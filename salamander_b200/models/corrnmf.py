@@ -43,7 +43,10 @@ class CorrState:
         dt = model.dtype
         self.rank, self.world = (0, 1) if getattr(model, "replica", False) else _dist.world()
         if self.world > 1 and not allow_shard:
-            raise NotImplementedError("MultimodalCorrNMF on several GPUs is not built yet (CorrNMFDet is).")
+            # MultimodalCorrNMF under torchrun: REPLICAS ONLY -- every rank fits the whole (PCAWG-sized) problem on its own GPU
+            # and, started from the same seed, arrives at the same bits; the joint sample embeddings couple all modalities of
+            # a sample, and at a few hundred samples there is nothing for a second GPU to do (multi-GPU)
+            self.rank, self.world = 0, 1
         model.transfer_bytes = {"h2d": 0, "d2h": 0}
         self.model, self.device, self.dtype = model, dev, dt
         X = np.asarray(model.adata.X)

@@ -16,6 +16,7 @@ from __future__ import annotations
 
 from typing import Any, Literal
 
+import numpy as np
 import torch
 
 from .. import _dist
@@ -40,6 +41,7 @@ class MvNMF(StandardNMF):
         self.lam = lam
         self.delta = delta
         self._gamma = 1.0
+        self.use_small_kernel = True  # problems that fit one SM: whole iterations in a persistent single-CTA kernel
 
     @property
     def objective(self) -> Literal["minimize", "maximize"]:
@@ -125,6 +127,72 @@ class MvNMF(StandardNMF):
         with self._resident():
             self._update_H()
             self._update_W(self._n_given(given_parameters))
+
+    # ---- device-side fit driver for problems that fit one SM (BASELINE config 1) ---------------------
+    def _fit_loop(self, given_parameters, verbose, verbosity_freq):
+        st = self._dev
+        if self.use_small_kernel and st.world == 1 and not st.ws.timing and st.ws.mvnmf_small_supported():
+            return self._fit_loop_small(self._n_given(given_parameters), verbose, verbosity_freq)
+        return super()._fit_loop(given_parameters, verbose, verbosity_freq)
+
+    def _fit_loop_small(self, n_given: int, verbose, verbosity_freq):
+        """One launch of the persistent single-CTA kernel (sal_mvnmf_small_updates) per convergence-test period: the penalised
+        objective of the period's incoming iterate plus its ``conv_test_freq`` iterations, line search and gamma included.
+        The next period is launched before the host looks at that objective; states (W, H, gamma) rotate through three
+        buffers, so the one the convergence test may fall back to is never overwritten.  Same iterates, history and
+        stopping iteration as the reference loop (signature_nmf.py:361-380)."""
+        st = self._dev
+        freq, max_it, min_it = int(self.conv_test_freq), int(self.max_iterations), int(self.min_iterations)
+        Wb = [st.W, torch.empty_like(st.W), torch.empty_like(st.W)]
+        Hb = [st.H, torch.empty_like(st.H), torch.empty_like(st.H)]
+        gam = torch.full((3,), float(self._gamma), dtype=torch.float64, device=st.device)
+        obj_dev = torch.zeros(2, dtype=torch.float64, device=st.device)
+        obj_host = torch.zeros(2, dtype=torch.float64).pin_memory()
+        events = [torch.cuda.Event(), torch.cuda.Event()]
+
+        def n_of(i: int) -> int:
+            return min(i * freq, max_it)
+
+        def launch(i: int) -> None:  # state i -> state i + 1, objective of state i
+            n_i, s = n_of(i), i % 2
+            a, b = i % 3, (i + 1) % 3
+            st.ws.mvnmf_small_updates(
+                st.X, Wb[a], Wb[b], Hb[a], Hb[b], self.lam, self.delta, n_given, min(freq, max_it - n_i),
+                gam[a : a + 1], gam[b : b + 1], objective=obj_dev[s : s + 1],
+            )
+            obj_host[s : s + 1].copy_(obj_dev[s : s + 1], non_blocking=True)
+            events[s].record()
+
+        of_values: list[float] = []
+        i = 0
+        launch(0)
+        while True:
+            n_i, n_next = n_of(i), n_of(i + 1)
+            speculative = n_i < max_it and n_next % freq == 0
+            if speculative:
+                launch(i + 1)
+            events[i % 2].synchronize()
+            of_values.append(float(obj_host[i % 2]))
+            final = i
+            if i > 0:
+                rel_change = np.abs(of_values[-2] - of_values[-1]) / np.abs(of_values[-2])
+                if bool(rel_change < self.tol and n_i >= min_it):
+                    break  # the fit ended at iteration n_i; later periods are dropped
+            if n_i >= max_it:
+                break
+            for it in range(n_i + 1, n_next + 1):
+                if verbose and it % verbosity_freq == 0:
+                    print(f"iteration: {it}; objective: {of_values[-1]:.2f}")
+            final = i + 1
+            if not speculative:  # the last, shorter period ends at max_iterations without an objective
+                break
+            i += 1
+        torch.cuda.current_stream(st.device).synchronize()
+        st.W, st.H = Wb[final % 3], Hb[final % 3]
+        st.W_next = Wb[(final + 1) % 3]
+        self._gamma = float(gam[final % 3].item())
+        self.launch_stats = {"graphs": 0, "periods": i + 1, "driver": "single-CTA persistent kernel"}
+        return of_values, n_of(final)
 
     def _setup_fitting_parameters(self, fitting_kwargs: dict[str, Any] | None = None) -> None:
         self._gamma = 1.0
