@@ -105,7 +105,7 @@ def init_nndsvd_device(data_mat: np.ndarray, n_signatures: int, method: str = "n
     return sigs, expo.cpu().numpy()
 
 
-def init_random_device(data_mat: np.ndarray, n_signatures: int, seed: int | None = None, device=None):
+def init_random_device(data_mat: np.ndarray, n_signatures: int, seed: int | None = None, device=None, _row_totals=None):
     """``init_random`` (reference initialization/methods.py:89-109) with the D x k exposure draws on the device.
 
     Signatures: the reference's own draw, ``np.random.dirichlet(1_V, size=k)`` from the global numpy RNG (so W0 is the
@@ -122,8 +122,9 @@ def init_random_device(data_mat: np.ndarray, n_signatures: int, seed: int | None
     sigs = np.random.dirichlet(np.ones(V), size=k)
     gen = torch.Generator(device=device)
     gen.manual_seed(int(np.random.randint(0, 2**31 - 1)))
-    totals = torch.from_numpy(np.asarray(data_mat).sum(axis=1, dtype=np.float64)).to(device)
+    resident = _row_totals is not None  # (a sweep's resident counts: totals already on the device, exposures stay there)
+    totals = _row_totals if resident else torch.from_numpy(np.asarray(data_mat).sum(axis=1, dtype=np.float64)).to(device)
     e = torch.empty((D, k), dtype=torch.float64, device=device)
     e.exponential_(1.0, generator=gen)
     e.mul_((totals / e.sum(dim=1))[:, None])
-    return sigs, e.cpu().numpy()
+    return sigs, (e if resident else e.cpu().numpy())

@@ -127,7 +127,8 @@ def initialize_standard_nmf(adata, n_signatures, method="nndsvd", given_paramete
     given_parameters = {} if given_parameters is None else given_parameters.copy()
     check_given_parameters_standard_nmf(adata, n_signatures, given_parameters)
     asignatures, expo = initialize_base(adata, n_signatures, method, given_parameters.get("asignatures"), _defer=_defer, **kwargs)
-    adata.obsm["exposures"] = np.ascontiguousarray(expo)
+    # (device-drawn exposures of a resident sweep are a device tensor and stay one until the state is built)
+    adata.obsm["exposures"] = np.ascontiguousarray(expo) if isinstance(expo, np.ndarray) else expo
     return asignatures
 
 

@@ -21,6 +21,29 @@ _FITTING_KWARGS = ["weights_kl", "weights_lhalf"]
 _DEFAULT_FITTING_KWARGS = {kwarg: None for kwarg in _FITTING_KWARGS}
 
 
+def period_launch_plan(min_iterations: int, max_iterations: int, freq: int, per_launch: int) -> list[tuple[int, int, bool]]:
+    """The launches of the period driver if the convergence test never fires: ``(first period, number of periods, trailing
+    objective)``.  Periods whose incoming checkpoint cannot end the fit (p = 0 or p * freq < min_iterations) are folded, up to
+    ``per_launch`` of them, into one launch; every later period is its own (speculative) launch; the launch that ends at
+    ``max_iterations`` carries the objective of the final iterate if that is a checkpoint (reference signature_nmf.py:365-380).
+    A pure function of its arguments: every rank of a sharded fit issues the same sequence."""
+    freq, max_it = int(freq), max(int(max_iterations), 1)
+    n_seg, final_ckpt = -(-max_it // freq), max_it % freq == 0
+
+    def deciding(p):
+        return p >= 1 and p * freq >= int(min_iterations)
+
+    plan, seg = [], 0
+    while seg < n_seg:
+        m = 1
+        if not deciding(seg):
+            while seg + m < n_seg and not deciding(seg + m) and m < per_launch:
+                m += 1
+        plan.append((seg, m, bool(final_ckpt and seg + m == n_seg)))
+        seg += m
+    return plan
+
+
 class KLNMF(StandardNMF):
     def __init__(
         self,
@@ -231,8 +254,6 @@ class KLNMF(StandardNMF):
         """
         freq, min_it = int(self.conv_test_freq), int(self.min_iterations)
         max_it = max(int(self.max_iterations), 1)
-        n_seg = -(-max_it // freq)                     # periods with at least one update
-        final_ckpt = max_it % freq == 0                # the reference evaluates the objective at n == max_iterations
         fl = st.fit_loop
         if not fl.get("period") or fl["Ws"][fl["cur"]] is not st.W or fl["Hs"][fl["cur"]] is not st.H:
             fl.clear()
@@ -251,22 +272,18 @@ class KLNMF(StandardNMF):
             return p >= 1 and p * freq >= min_it
 
         pending = []  # (ring slot, first checkpoint, n checkpoints, state index before, state index after)
-        seg, n_launched, of_values, n_done, final_state = 0, 0, [], 0, None
+        plan = period_launch_plan(min_it, max_it, freq, self._PERIODS_PER_LAUNCH)
+        nxt_launch, n_launched, of_values, n_done, final_state = 0, 0, [], 0, None
         while True:
             # ---- launch as far ahead as the decisions allow ----
-            while seg < n_seg:
+            while nxt_launch < len(plan):
+                seg, m, fin = plan[nxt_launch]
                 if deciding(seg):
                     if sum(1 for q in pending if deciding(q[1])) >= 2:
                         break
-                    m = 1
-                else:
-                    if len(pending) >= self._QUEUE_DEPTH:
-                        break
-                    m = 1
-                    while seg + m < n_seg and not deciding(seg + m) and m < self._PERIODS_PER_LAUNCH:
-                        m += 1
+                elif len(pending) >= self._QUEUE_DEPTH:
+                    break
                 n0, n1 = seg * freq, min((seg + m) * freq, max_it)
-                fin = final_ckpt and seg + m == n_seg
                 slot, nxt = n_launched % ring, (cur + 1) % 3
                 if n_launched == 0 and self.loop_start_event is not None:
                     self.loop_start_event.record()  # measurement aid: device time from the driver's first launch on
@@ -278,7 +295,7 @@ class KLNMF(StandardNMF):
                 obj_host[slot].copy_(obj_dev[slot], non_blocking=True)
                 events[slot].record()
                 pending.append((slot, seg, m + (1 if fin else 0), cur, nxt))
-                cur, seg, n_launched = nxt, seg + m, n_launched + 1
+                cur, nxt_launch, n_launched = nxt, nxt_launch + 1, n_launched + 1
             if not pending:
                 break
             # ---- the oldest launch's objectives ----
@@ -304,7 +321,7 @@ class KLNMF(StandardNMF):
                     if verbose and it % verbosity_freq == 0:
                         print(f"iteration: {it}; objective: {of_values[-1]:.2f}")
                 n_done, final_state = n_end, s_after
-            if stop or (seg >= n_seg and not pending):
+            if stop or (nxt_launch >= len(plan) and not pending):
                 break
         torch.cuda.current_stream(st.device).synchronize()  # dropped speculative launches still write the spare buffers
         st.W, st.H = Ws[final_state], Hs[final_state]

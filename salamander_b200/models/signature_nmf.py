@@ -149,6 +149,11 @@ class SignatureNMF(ABC):
         """Type check, then clip the counts to EPSILON *on the caller's object* (reference :269-281)."""
         type_checker("adata", adata, AnnData)
         self.adata = adata
+        rc = getattr(self, "_resident_counts", None)
+        if rc is not None and rc.matches(adata, self._resolved_device(), self.dtype):
+            self._clip_on_device = False  # a sweep's shared, already clipped device copy (sweep.ResidentCounts)
+            return
+        self._resident_counts = None
         X = np.asarray(self.adata.X)
         if X.dtype in (np.float32, np.float64) and X.size >= self._DEVICE_CLIP_MIN_SIZE:
             # large floating matrices are clipped on the device right after the upload (sal_clip_counts) and
@@ -200,7 +205,11 @@ class SignatureNMF(ABC):
             return {}  # device-drawn exposures are not numpy's draws: only on explicit request
         if self.init_device == "auto" and np.asarray(self.adata.X).size < self._DEVICE_CLIP_MIN_SIZE:
             return {}
-        return {"_init_device": self._resolved_device()}
+        out = {"_init_device": self._resolved_device()}
+        rc = getattr(self, "_resident_counts", None)
+        if rc is not None and self.init_method == "random":
+            out["_row_totals"] = rc.totals  # the exposures are drawn from the resident totals and never leave the device
+        return out
 
     class _Resident:
         """``with self._resident():`` -- run a block with state in HBM; outside ``fit`` this uploads before

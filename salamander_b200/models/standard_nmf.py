@@ -28,7 +28,9 @@ class StandardState:
         self.device, self.dtype = dev, dt
         X_host = np.asarray(model.adata.X)
         W_host = np.asarray(model.asignatures.X, dtype=np.float64)
-        H_host = np.asarray(model.adata.obsm["exposures"])
+        H_dev = model.adata.obsm["exposures"] if isinstance(model.adata.obsm["exposures"], torch.Tensor) else None
+        H_host = None if H_dev is not None else np.asarray(model.adata.obsm["exposures"])
+        rc = getattr(model, "_resident_counts", None)
         self.k = W_host.shape[0]
         self.rank, self.world = (0, 1) if model.replica else _dist.world()
         if model.shard_input:
@@ -36,7 +38,8 @@ class StandardState:
             self.lo, self.hi = _dist.shard_bounds(self.D_total, self.world, self.rank)
             if self.world > 1:  # replicas must start bit-identical whatever the host RNG did
                 W_host = _dist.broadcast_numpy(W_host, dev)
-                H_host = _dist.broadcast_numpy(H_host, dev)
+                if H_host is not None:
+                    H_host = _dist.broadcast_numpy(H_host, dev)
         else:  # adata already holds this rank's rows only
             self.V = X_host.shape[1]
             self.lo, self.hi = 0, X_host.shape[0]
@@ -45,7 +48,7 @@ class StandardState:
                 W_host = _dist.broadcast_numpy(W_host, dev)
         D = self.hi - self.lo
         self.ws = Workspace(self.V, D, self.k, dt, dev, math=model.math)
-        self.X = self.upload(X_host[self.lo : self.hi])
+        self.X = rc.X if rc is not None else self.upload(X_host[self.lo : self.hi])  # (resident: shared by the fits of a sweep)
         if model._clip_on_device:
             changed = torch.zeros(1, dtype=torch.int64, device=dev)
             self.ws.clip_counts(self.X, changed)
@@ -55,7 +58,7 @@ class StandardState:
                 model.adata.X = self.rows_to_host(self.X)
             model._clip_on_device = False
         self.W = self.upload(W_host)
-        self.H = self.upload(H_host[self.lo : self.hi])
+        self.H = H_dev[self.lo : self.hi].to(dt).contiguous() if H_dev is not None else self.upload(H_host[self.lo : self.hi])
         scale = getattr(model, "_exposure_scale", None)
         if scale is not None:
             self.ws.scale_clip_rows(self.H, self.upload(np.asarray(scale, dtype=np.float64)))
@@ -152,6 +155,10 @@ class StandardNMF(SignatureNMF):
 
     def _to_host(self) -> None:
         st = self._dev
+        keep = getattr(self, "_download_if", None)
+        if keep is not None and not keep(self):  # a sweep's fit that is not the best of its k: only the error is kept
+            self.adata.obsm["exposures"] = None
+            return
         self.asignatures.X = st.download(st.W)
         self.adata.obsm["exposures"] = st.rows_to_host(st.H)
 

@@ -23,12 +23,50 @@ from .models.klnmf import KLNMF
 
 def _shallow_copy(adata):
     """A fresh container around the SAME count matrix: a fit only ever rebinds ``adata.X`` (when clipping changes an
-    entry), it does not write into the array, so the fits of a sweep can share it instead of copying it every time."""
-    from ._anndata import AnnData
+    entry), it does not write into the array, so the fits of a sweep can share it instead of copying it every time.
+    The names are shared as well: building 100,000 default string names per fit costs more than the fit's 200 updates."""
+    import pandas as pd
 
-    new = AnnData(np.asarray(adata.X))
-    new.obs_names, new.var_names = adata.obs_names, adata.var_names
+    from ._anndata import HAVE_ANNDATA, AnnData
+
+    if HAVE_ANNDATA:  # pragma: no cover - the real container validates its own fields
+        new = AnnData(np.asarray(adata.X))
+        new.obs_names, new.var_names = adata.obs_names, adata.var_names
+        return new
+    new = AnnData(None)
+    new.X = np.asarray(adata.X)
+    new._obs_names, new.var_names = adata.obs_names, adata.var_names
+    new.obs = pd.DataFrame(index=adata.obs_names)
     return new
+
+
+class ResidentCounts:
+    """The count matrix of a sweep, uploaded and clipped ONCE and shared by all of its fits on this rank (every fit used to
+    upload and clip its own copy: 38 MB and a host pass per fit at 96 x 100k, more than the fit's 200 updates take), plus the
+    per-sample totals the random initialisation needs.  ``adata.X`` is rebound to the clipped host matrix once, if clipping
+    changed anything (reference signature_nmf.py:281 does that in every fit)."""
+
+    def __init__(self, adata, device, dtype):
+        import torch
+
+        from ._device import Workspace, resolve_device, resolve_dtype
+        from .models.signature_nmf import EPSILON
+
+        self.device, self.dtype = resolve_device(device), resolve_dtype(dtype)
+        X = np.asarray(adata.X)
+        self.shape = X.shape
+        self.X = torch.from_numpy(np.ascontiguousarray(X)).to(self.device).to(self.dtype).contiguous()
+        ws = Workspace(X.shape[1], X.shape[0], 1, self.dtype, self.device)
+        changed = torch.zeros(1, dtype=torch.int64, device=self.device)
+        ws.clip_counts(self.X, changed)
+        if int(changed.item()) > 0:
+            adata.X = X.clip(EPSILON)
+        ws.close()
+        self.host = np.asarray(adata.X)
+        self.totals = self.X.sum(dim=1, dtype=torch.float64)
+
+    def matches(self, adata, device, dtype) -> bool:
+        return np.asarray(adata.X) is self.host and device == self.device and dtype == self.dtype
 
 
 def sweep_klnmf(
@@ -49,11 +87,18 @@ def sweep_klnmf(
     rank, world = _dist.world()
     jobs = [(int(k), int(seed0 + r)) for k in ns_signatures for r in range(n_restarts)]
     rows, best = [], {}
+    resident = None
     for idx, (k, seed) in enumerate(jobs):
         if idx % world != rank:
             continue
         model = KLNMF(n_signatures=k, init_method="random", replica=True, **model_kwargs)
         model.errors_in_fit = True
+        if resident is None:  # X goes to the device once per sweep and rank
+            resident = ResidentCounts(adata, model._resolved_device(), model.dtype)
+        model._resident_counts = resident
+        model.pinned_results = False  # kept results pile up over a sweep: pageable arrays through the cached staging buffer
+        # results come to the host only for a fit that is the best of its k so far (the table needs the error alone)
+        model._download_if = (lambda m, k=k: keep_best and (k not in best or m.reconstruction_error < best[k].reconstruction_error))
         model.fit(_shallow_copy(adata), init_kwargs={"seed": seed})
         err = model.reconstruction_error
         rows.append((k, seed, model.n_iterations, float(model.history["objective_function"][-1]), float(err), rank))

@@ -244,3 +244,29 @@ def test_sweep_over_k_and_restarts():
     curve = error_curve(table)
     assert curve.loc[3] < curve.loc[2]
     assert set(best) == {2, 3} and np.isclose(best[3].reconstruction_error, curve.loc[3])
+
+
+def test_resident_sweep_equals_standalone_fits():
+    """A sweep keeps ONE clipped device copy of the counts for all of its fits, draws the random exposures on the device from
+    the resident totals and downloads only the fits that are the best of their k: every row of the table must equal the
+    stand-alone fit with the same (k, seed), and best[k] must carry that fit's results."""
+    import bench
+    from salamander_b200.sweep import sweep_klnmf
+
+    X = bench.synth_rows(0, 6000, 6)
+    X[0, :5] = 0.0  # an entry below EPSILON: the sweep rebinds adata.X to the clipped matrix once
+    adata = AnnData(X.copy())
+    kw = dict(min_iterations=30, max_iterations=30, dtype="float32", math="tf32", init_device=True)
+    table, best = sweep_klnmf(adata, [3, 4], n_restarts=2, seed0=1, **kw)
+    assert float(np.asarray(adata.X).min()) > 0
+    assert len(table) == 4 and set(best) == {3, 4}
+    for _, row in table.iterrows():
+        m = sal.models.KLNMF(n_signatures=int(row.n_signatures), init_method="random", replica=True, **kw)
+        m.errors_in_fit = True
+        m.fit(AnnData(X.copy()), init_kwargs={"seed": int(row.seed)})
+        assert np.isclose(m.history["objective_function"][-1], row.objective, rtol=1e-6)
+        assert np.isclose(m.reconstruction_error, row.reconstruction_error, rtol=1e-6)
+        b = best[int(row.n_signatures)]
+        if np.isclose(b.reconstruction_error, row.reconstruction_error, rtol=1e-12):
+            assert np.allclose(b.asignatures.X, m.asignatures.X, rtol=1e-4, atol=1e-9)
+            assert np.allclose(b.adata.obsm["exposures"], m.adata.obsm["exposures"], rtol=1e-3, atol=1e-5)

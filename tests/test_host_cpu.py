@@ -124,6 +124,17 @@ assert torch.equal(L, torch.arange(k, dtype=torch.float64)[:, None] + 0.125 * to
 norms = torch.tensor([7.0, float(rank + 1), 10.0 * (rank + 1)], dtype=torch.float64)
 _dist.allreduce_sum_counting_replicated_once(norms, slice(0, 1))
 assert torch.equal(norms, torch.tensor([7.0, 3.0, 30.0], dtype=torch.float64)), (rank, norms)
+# path decisions whose kernels wait on the peers are taken collectively: true only if true on EVERY rank
+assert _dist.all_ranks_agree(True, torch.device("cpu")) is True
+assert _dist.all_ranks_agree(rank == 0, torch.device("cpu")) is False
+assert _dist.all_ranks_agree(False, torch.device("cpu")) is False
+# the period driver's launch plan is a pure function of (min, max, freq): both ranks issue the same launches
+from salamander_b200.models.klnmf import period_launch_plan
+plan = period_launch_plan(min_iterations=35, max_iterations=100, freq=10, per_launch=16)
+assert plan == [(0, 4, False), (4, 1, False), (5, 1, False), (6, 1, False), (7, 1, False), (8, 1, False), (9, 1, True)], plan
+assert period_launch_plan(20, 20, 10, 16) == [(0, 2, True)]
+assert period_launch_plan(500, 10000, 10, 16)[:4] == [(0, 16, False), (16, 16, False), (32, 16, False), (48, 2, False)]
+assert period_launch_plan(0, 25, 10, 16) == [(0, 1, False), (1, 1, False), (2, 1, False)]
 dist.destroy_process_group()
 print("ok", rank)
 """
