@@ -18,7 +18,7 @@
 
 #include <stdlib.h>
 
-#include "sal_common.cuh"
+#include "corrnmf_newton.cuh"
 
 #include <string.h>
 
@@ -26,226 +26,10 @@ namespace cg = cooperative_groups;
 
 namespace {
 
-constexpr int MAXM = 16;  // embedding dimensions handled (SAL_EUNSUPPORTED above)
-
-// ---------------------------------------------------------------------------------------------------------
-// DCSRCH / dcstep (MINPACK-2, as shipped in scipy/optimize/_dcsrch.py): scalar state machine
-// ---------------------------------------------------------------------------------------------------------
-struct StepState {
-    double stx, fx, dx, sty, fy, dy, stp;
-    bool brackt;
-};
-
-__device__ inline double sgn(double v) { return (v > 0.0) - (v < 0.0); }
-
-__device__ void dcstep(StepState& s, double fp, double dp, double stpmin, double stpmax) {
-    const double sgnd = sgn(dp) * sgn(s.dx);
-    double stpf, stpc, stpq;
-    if (fp > s.fx) {
-        const double theta = 3.0 * (s.fx - fp) / (s.stp - s.stx) + s.dx + dp;
-        const double sc = fmax(fabs(theta), fmax(fabs(s.dx), fabs(dp)));
-        double gamma = sc * sqrt((theta / sc) * (theta / sc) - (s.dx / sc) * (dp / sc));
-        if (s.stp < s.stx) gamma = -gamma;
-        const double p = (gamma - s.dx) + theta, q = ((gamma - s.dx) + gamma) + dp, r = p / q;
-        stpc = s.stx + r * (s.stp - s.stx);
-        stpq = s.stx + ((s.dx / ((s.fx - fp) / (s.stp - s.stx) + s.dx)) / 2.0) * (s.stp - s.stx);
-        stpf = fabs(stpc - s.stx) <= fabs(stpq - s.stx) ? stpc : stpc + (stpq - stpc) / 2.0;
-        s.brackt = true;
-    } else if (sgnd < 0.0) {
-        const double theta = 3.0 * (s.fx - fp) / (s.stp - s.stx) + s.dx + dp;
-        const double sc = fmax(fabs(theta), fmax(fabs(s.dx), fabs(dp)));
-        double gamma = sc * sqrt((theta / sc) * (theta / sc) - (s.dx / sc) * (dp / sc));
-        if (s.stp > s.stx) gamma = -gamma;
-        const double p = (gamma - dp) + theta, q = ((gamma - dp) + gamma) + s.dx, r = p / q;
-        stpc = s.stp + r * (s.stx - s.stp);
-        stpq = s.stp + (dp / (dp - s.dx)) * (s.stx - s.stp);
-        stpf = fabs(stpc - s.stp) > fabs(stpq - s.stp) ? stpc : stpq;
-        s.brackt = true;
-    } else if (fabs(dp) < fabs(s.dx)) {
-        const double theta = 3.0 * (s.fx - fp) / (s.stp - s.stx) + s.dx + dp;
-        const double sc = fmax(fabs(theta), fmax(fabs(s.dx), fabs(dp)));
-        double gamma = sc * sqrt(fmax(0.0, (theta / sc) * (theta / sc) - (s.dx / sc) * (dp / sc)));
-        if (s.stp > s.stx) gamma = -gamma;
-        const double p = (gamma - dp) + theta, q = (gamma + (s.dx - dp)) + gamma, r = p / q;
-        if (r < 0.0 && gamma != 0.0)
-            stpc = s.stp + r * (s.stx - s.stp);
-        else
-            stpc = s.stp > s.stx ? stpmax : stpmin;
-        stpq = s.stp + (dp / (dp - s.dx)) * (s.stx - s.stp);
-        if (s.brackt) {
-            stpf = fabs(stpc - s.stp) < fabs(stpq - s.stp) ? stpc : stpq;
-            stpf = s.stp > s.stx ? fmin(s.stp + 0.66 * (s.sty - s.stp), stpf) : fmax(s.stp + 0.66 * (s.sty - s.stp), stpf);
-        } else {
-            stpf = fabs(stpc - s.stp) > fabs(stpq - s.stp) ? stpc : stpq;
-            stpf = fmin(fmax(stpf, stpmin), stpmax);
-        }
-    } else {
-        if (s.brackt) {
-            const double theta = 3.0 * (fp - s.fy) / (s.sty - s.stp) + s.dy + dp;
-            const double sc = fmax(fabs(theta), fmax(fabs(s.dy), fabs(dp)));
-            double gamma = sc * sqrt((theta / sc) * (theta / sc) - (s.dy / sc) * (dp / sc));
-            if (s.stp > s.sty) gamma = -gamma;
-            const double p = (gamma - dp) + theta, q = ((gamma - dp) + gamma) + s.dy, r = p / q;
-            stpf = s.stp + r * (s.sty - s.stp);
-        } else {
-            stpf = s.stp > s.stx ? stpmax : stpmin;
-        }
-    }
-    if (fp > s.fx) {
-        s.sty = s.stp, s.fy = fp, s.dy = dp;
-    } else {
-        if (sgnd < 0.0) s.sty = s.stx, s.fy = s.fx, s.dy = s.dx;
-        s.stx = s.stp, s.fx = fp, s.dx = dp;
-    }
-    s.stp = stpf;
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// Newton-CG.  Problem P provides (collectively for the calling threads; every thread gets the same values):
-//   double f_grad_hess(const double* x, double* g, double* A)   -- all three at the same point in ONE sweep over the
-//                                                                  terms (one exp per term, one collective reduction)
-// SciPy evaluates fprime(xk) and fhess(xk) again at the top of every Newton iteration; xk is the line-search point that
-// was just accepted, where DCSRCH has already asked for f and f'.  Every trial therefore evaluates f, f' and the Hessian
-// together and the accepted trial's values are kept: one sweep per trial, none at the top of the iteration (same
-// functions at the same points, so the iterates are SciPy's).
-// ---------------------------------------------------------------------------------------------------------
-template <class P>
-__device__ void newton_cg(P& prob, double* x, int m, int maxiter) {
-    const double ftol = 1e-4, gtol = 0.9, ls_xtol = 1e-14, stpmin = 1e-8, stpmax = 50.0, eps64 = 2.220446049250313e-16;
-    const double xtol = m * 1e-5;
-    const int cg_maxiter = 20 * m;
-    double b[MAXM], xs[MAXM], ri[MAXM], ps[MAXM], Ap[MAXM], xt[MAXM], gt[MAXM], gl[MAXM];
-    double Abuf0[MAXM * MAXM], Abuf1[MAXM * MAXM];
-    double *A = Abuf0, *Al = Abuf1;  // Hessian at the current point / at the trial point (swapped on acceptance)
-    double old_fval = prob.f_grad_hess(x, gt, A), old_old_fval = 0.0;
-    bool have_old_old = false;
-    double update_l1 = 1.7976931348623157e308;
-    int k = 0;
-    while (update_l1 > xtol) {
-        if (k >= maxiter) break;
-        double maggrad = 0.0;
-        for (int i = 0; i < m; ++i) b[i] = -gt[i], maggrad += fabs(b[i]);
-        const double termcond = fmin(0.5, sqrt(maggrad)) * maggrad;
-        double dri0 = 0.0;
-        for (int i = 0; i < m; ++i) xs[i] = 0.0, ri[i] = -b[i], ps[i] = b[i], dri0 += ri[i] * ri[i];
-        int it = 0;
-        bool failed = true;
-        for (int k2 = 0; k2 < cg_maxiter; ++k2) {
-            double rn = 0.0;
-            for (int i = 0; i < m; ++i) rn += fabs(ri[i]);
-            if (rn <= termcond) {
-                failed = false;
-                break;
-            }
-            double curv = 0.0;
-            for (int i = 0; i < m; ++i) {
-                double t = 0.0;
-                for (int j = 0; j < m; ++j) t += A[i * m + j] * ps[j];
-                Ap[i] = t;
-            }
-            for (int i = 0; i < m; ++i) curv += ps[i] * Ap[i];
-            if (curv >= 0.0 && curv <= 3.0 * eps64) {
-                failed = false;
-                break;
-            } else if (curv < 0.0) {
-                if (it == 0)
-                    for (int i = 0; i < m; ++i) xs[i] = dri0 / (-curv) * b[i];
-                failed = false;
-                break;
-            }
-            const double alphai = dri0 / curv;
-            double dri1 = 0.0;
-            for (int i = 0; i < m; ++i) xs[i] += alphai * ps[i], ri[i] += alphai * Ap[i], dri1 += ri[i] * ri[i];
-            const double betai = dri1 / dri0;
-            for (int i = 0; i < m; ++i) ps[i] = -ri[i] + betai * ps[i];
-            ++it;
-            dri0 = dri1;
-        }
-        if (failed) break;  // "CG iterations didn't converge"
-        // ---- line search along pk = xs (DCSRCH)
-        double derphi0 = 0.0;
-        for (int i = 0; i < m; ++i) derphi0 += gt[i] * xs[i];
-        double alpha1 = 1.0;
-        if (have_old_old && derphi0 != 0.0) {
-            alpha1 = fmin(1.0, 1.01 * 2.0 * (old_fval - old_old_fval) / derphi0);
-            if (alpha1 < 0.0) alpha1 = 1.0;
-        }
-        bool ok = false;
-        double fnew = old_fval, stp_ok = 0.0;
-        if (!(alpha1 < stpmin || alpha1 > stpmax || derphi0 >= 0.0)) {
-            StepState s;
-            s.brackt = false;
-            int stage = 1;
-            const double finit = old_fval, ginit = derphi0, gtest = ftol * ginit;
-            double width = stpmax - stpmin, width1 = width / 0.5;
-            s.stx = s.sty = 0.0, s.fx = s.fy = finit, s.dx = s.dy = ginit, s.stp = alpha1;
-            double stmin = 0.0, stmax = alpha1 + 4.0 * alpha1;
-            for (int ls = 0; ls < 99; ++ls) {
-                for (int i = 0; i < m; ++i) xt[i] = x[i] + s.stp * xs[i];
-                const double f = prob.f_grad_hess(xt, gl, Al);
-                double g = 0.0;
-                for (int i = 0; i < m; ++i) g += gl[i] * xs[i];
-                const double ftest = finit + s.stp * gtest;
-                if (stage == 1 && f <= ftest && g >= 0.0) stage = 2;
-                bool warn = false;
-                if (s.brackt && (s.stp <= stmin || s.stp >= stmax)) warn = true;
-                if (s.brackt && stmax - stmin <= ls_xtol * stmax) warn = true;
-                if (s.stp == stpmax && f <= ftest && g <= gtest) warn = true;
-                if (s.stp == stpmin && (f > ftest || g >= gtest)) warn = true;
-                if (f <= ftest && fabs(g) <= gtol * -ginit) {
-                    ok = true, fnew = f, stp_ok = s.stp;
-                    break;
-                }
-                if (warn) break;
-                if (stage == 1 && f <= s.fx && f > ftest) {
-                    StepState t = s;
-                    t.fx = s.fx - s.stx * gtest, t.fy = s.fy - s.sty * gtest, t.dx = s.dx - gtest, t.dy = s.dy - gtest;
-                    dcstep(t, f - s.stp * gtest, g - gtest, stmin, stmax);
-                    s = t;
-                    s.fx = t.fx + t.stx * gtest, s.fy = t.fy + t.sty * gtest, s.dx = t.dx + gtest, s.dy = t.dy + gtest;
-                } else {
-                    dcstep(s, f, g, stmin, stmax);
-                }
-                if (s.brackt) {
-                    if (fabs(s.sty - s.stx) >= 0.66 * width1) s.stp = s.stx + 0.5 * (s.sty - s.stx);
-                    width1 = width;
-                    width = fabs(s.sty - s.stx);
-                    stmin = fmin(s.stx, s.sty), stmax = fmax(s.stx, s.sty);
-                } else {
-                    stmin = s.stp + 1.1 * (s.stp - s.stx), stmax = s.stp + 4.0 * (s.stp - s.stx);
-                }
-                s.stp = fmin(fmax(s.stp, stpmin), stpmax);
-                if ((s.brackt && (s.stp <= stmin || s.stp >= stmax)) || (s.brackt && stmax - stmin <= ls_xtol * stmax)) s.stp = s.stx;
-                if (!isfinite(s.stp)) break;
-            }
-        }
-        if (!ok) break;  // line search failed: keep the current point
-        old_old_fval = old_fval, have_old_old = true, old_fval = fnew;
-        update_l1 = 0.0;
-        for (int i = 0; i < m; ++i) {
-            const double xn = x[i] + stp_ok * xs[i];  // the very expression the trial point was formed with
-            update_l1 += fabs(stp_ok * xs[i]);
-            x[i] = xn;
-            gt[i] = gl[i];
-        }
-        {
-            double* t = A;
-            A = Al, Al = t;
-        }
-        ++k;
-    }
-}
-
-__device__ inline double snap_eps(double e) {
-    const double eps = SAL_EPS_F32;
-    if (e > 0.0 && e < eps) return eps;
-    if (e < 0.0 && e > -eps) return -eps;
-    return e;
-}
-
 // ---------------------------------------------------------------------------------------------------------
 // sample embeddings: one thread per sample, the k signature embeddings / scalings in shared memory
 // ---------------------------------------------------------------------------------------------------------
+template <int M>
 struct SampleProblem {
     const double* others;    // [k][m] shared
     const double* s_others;  // [k]    shared
@@ -253,29 +37,32 @@ struct SampleProblem {
     const double* s_vec;     // [k]    local: the sample's scaling for every "other" (one value repeated for a single
                              //        modality; per-modality values in multimodal CorrNMF, mmcorrnmf.py:413-419)
     double inv_var;
-    int k, m;
+    int k, m_rt;
     __device__ double f_grad_hess(const double* x, double* g, double* A) const {
+        const int m = M > 0 ? M : m_rt;
         double acc = 0.0, nrm = 0.0;
-        for (int j = 0; j < m * m; ++j) A[j] = 0.0;
-        for (int j = 0; j < m; ++j) g[j] = x[j] * inv_var, nrm += x[j] * x[j], A[j * m + j] = inv_var;
+        _Pragma("unroll") for (int j = 0; j < m * m; ++j) A[j] = 0.0;
+        _Pragma("unroll") for (int j = 0; j < m; ++j) g[j] = x[j] * inv_var, nrm += x[j] * x[j], A[j * m + j] = inv_var;
         for (int i = 0; i < k; ++i) {
             double sp = 0.0;
-            for (int j = 0; j < m; ++j) sp += others[i * m + j] * x[j];
+            _Pragma("unroll") for (int j = 0; j < m; ++j) sp += others[i * m + j] * x[j];
             const double e = exp(s_vec[i] + s_others[i] + sp);
             acc += sp * aux[i] - e;
             const double w = e - aux[i];
-            for (int j = 0; j < m; ++j) g[j] += w * others[i * m + j];
-            for (int p = 0; p < m; ++p)
-                for (int q = 0; q < m; ++q) A[p * m + q] += e * others[i * m + p] * others[i * m + q];
+            _Pragma("unroll") for (int j = 0; j < m; ++j) g[j] += w * others[i * m + j];
+            _Pragma("unroll") for (int p = 0; p < m; ++p)
+                _Pragma("unroll") for (int q = 0; q < m; ++q) A[p * m + q] += e * others[i * m + p] * others[i * m + q];
         }
         return -(acc - 0.5 * nrm * inv_var);
     }
 };
 
 // b: [D] (b_is_matrix = 0, one scaling per sample) or [D][k] (b_is_matrix = 1, one per sample and signature)
-template <typename T>
+template <typename T, int M>
 __global__ void __launch_bounds__(128) sample_embeddings_kernel(const T* auxT, const T* a, const T* b, int b_is_matrix, const T* L, T* U,
-                                                               int64_t D, int k, int m, double variance, int maxiter) {
+                                                               int64_t D, int k, int m_rt, double variance, int maxiter) {
+    constexpr int MM = M > 0 ? M : MAXM;
+    const int m = M > 0 ? M : m_rt;
     __shared__ double sL[SAL_KMAX * MAXM];
     __shared__ double sa[SAL_KMAX];
     for (int i = threadIdx.x; i < k * m; i += blockDim.x) sL[i] = (double)L[i];
@@ -283,96 +70,16 @@ __global__ void __launch_bounds__(128) sample_embeddings_kernel(const T* auxT, c
     __syncthreads();
     const int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= D) return;
-    double aux[SAL_KMAX], sv[SAL_KMAX], x[MAXM];
+    double aux[SAL_KMAX], sv[SAL_KMAX], x[MM];
     for (int i = 0; i < k; ++i) aux[i] = (double)auxT[d * k + i], sv[i] = (double)(b_is_matrix ? b[d * k + i] : b[d]);
-    for (int j = 0; j < m; ++j) x[j] = (double)U[d * m + j];
-    SampleProblem p{sL, sa, aux, sv, 1.0 / variance, k, m};
-    newton_cg(p, x, m, maxiter);
-    for (int j = 0; j < m; ++j) U[d * m + j] = (T)snap_eps(x[j]);
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// signature embeddings: one CTA per signature; evaluations are block reductions over the samples
-// ---------------------------------------------------------------------------------------------------------
-constexpr int SIG_THREADS = 256;
-
-template <typename T>
-struct SignatureProblem {
-    const T *U, *b, *auxT;  // U [D][m], b [D], auxT [D][k]
-    double* red;            // shared [SIG_THREADS / 32][1 + MAXM + MAXM * MAXM]
-    double* cl;             // shared [1 + MAXM + MAXM * MAXM]: this CTA's totals, read by the other CTAs of the cluster
-    double s, inv_var;
-    int64_t D;
-    int k, m, j;
-    int rank, nrank;        // position in the thread-block cluster that shares signature j (samples are interleaved)
-
-    // fixed-order block reduction of n values per thread; result broadcast to all threads through shared memory
-    __device__ void reduce(double* v, int n) const {
-        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, stride = 1 + MAXM + MAXM * MAXM;
-        for (int i = 0; i < n; ++i) {
-            double t = v[i];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-            if (lane == 0) red[w * stride + i] = t;
-        }
-        __syncthreads();
-        for (int i = 0; i < n; ++i) {
-            double t = 0.0;
-            for (int ww = 0; ww < SIG_THREADS / 32; ++ww) t += red[ww * stride + i];
-            v[i] = t;
-        }
-        __syncthreads();
-        if (nrank > 1) {  // sum the CTAs' totals in rank order through distributed shared memory
-            cg::cluster_group cluster = cg::this_cluster();
-            if (threadIdx.x == 0)
-                for (int i = 0; i < n; ++i) cl[i] = v[i];
-            cluster.sync();
-            for (int i = 0; i < n; ++i) {
-                double t = 0.0;
-                for (int r = 0; r < nrank; ++r) t += cluster.map_shared_rank(cl, r)[i];
-                v[i] = t;
-            }
-            cluster.sync();
-        }
-    }
-    __device__ double f_grad_hess(const double* x, double* g, double* A) const {
-        double v[1 + MAXM + MAXM * MAXM];  // [f | gradient | Hessian]: one collective reduction for all of it
-        const int n = 1 + m + m * m;
-        for (int q = 0; q < n; ++q) v[q] = 0.0;
-        for (int64_t d = (int64_t)rank * SIG_THREADS + threadIdx.x; d < D; d += (int64_t)nrank * SIG_THREADS) {
-            double u[MAXM], sp = 0.0;
-            for (int q = 0; q < m; ++q) u[q] = (double)U[d * m + q], sp += u[q] * x[q];
-            const double e = exp(s + (double)b[d] + sp), ax = (double)auxT[d * k + j];
-            v[0] += sp * ax - e;
-            const double w = e - ax;
-            for (int q = 0; q < m; ++q) v[1 + q] += w * u[q];
-            for (int p = 0; p < m; ++p)
-                for (int q = 0; q < m; ++q) v[1 + m + p * m + q] += e * u[p] * u[q];
-        }
-        reduce(v, n);
-        double nrm = 0.0;
-        for (int q = 0; q < m; ++q) nrm += x[q] * x[q], g[q] = v[1 + q] + x[q] * inv_var;
-        for (int q = 0; q < m * m; ++q) A[q] = v[1 + m + q];
-        for (int q = 0; q < m; ++q) A[q * m + q] += inv_var;
-        return -(v[0] - 0.5 * nrm * inv_var);
-    }
-};
-
-template <typename T>
-__global__ void __launch_bounds__(SIG_THREADS) signature_embeddings_kernel(const T* auxT, const T* a, const T* b, T* L, const T* U,
-                                                                          int64_t D, int k, int m, double variance, int sig_begin) {
-    __shared__ double red[(SIG_THREADS / 32) * (1 + MAXM + MAXM * MAXM)];
-    __shared__ double cl[1 + MAXM + MAXM * MAXM];
-    cg::cluster_group cluster = cg::this_cluster();
-    const int nrank = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
-    const int j = sig_begin + blockIdx.x / nrank;  // one cluster per signature; every CTA of it runs the same Newton-CG on the same numbers
-    double x[MAXM];
-    for (int q = 0; q < m; ++q) x[q] = (double)L[j * m + q];
-    SignatureProblem<T> p{U, b, auxT, red, cl, (double)a[j], 1.0 / variance, D, k, m, j, rank, nrank};
-    if (nrank > 1) cluster.sync();  // nobody writes L[j] before everybody has read it
-    newton_cg(p, x, m, 200 * m);
-    if (rank == 0 && threadIdx.x == 0)
-        for (int q = 0; q < m; ++q) L[j * m + q] = (T)snap_eps(x[q]);
+    for (int j = 0; j < MM; ++j)
+        if (j < m) x[j] = (double)U[d * m + j];
+    SampleProblem<M> p{sL, sa, aux, sv, 1.0 / variance, k, m};
+    newton_cg<M>(p, x, m, maxiter);
+#pragma unroll
+    for (int j = 0; j < MM; ++j)
+        if (j < m) U[d * m + j] = (T)snap_eps(x[j]);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -581,58 +288,22 @@ int sal_launch_corrnmf_sample_embeddings(sal_ctx* c, const void* auxT, const voi
                                          void* U, int m, double variance, int maxiter, cudaStream_t st) {
     if (c->D == 0) return 0;
     const int grid = (int)((c->D + 127) / 128);
-    SAL_DISPATCH_T(c, (sample_embeddings_kernel<float><<<grid, 128, 0, st>>>((const float*)auxT, (const float*)a, (const float*)b, b_is_matrix, (const float*)L, (float*)U, c->D, c->k, m, variance, maxiter)),
-                   (sample_embeddings_kernel<double><<<grid, 128, 0, st>>>((const double*)auxT, (const double*)a, (const double*)b, b_is_matrix, (const double*)L, (double*)U, c->D, c->k, m, variance, maxiter)));
-    SAL_CUDA(cudaGetLastError());
-    c->launches++;
-    return 0;
-}
-
-int sal_launch_corrnmf_signature_embeddings(sal_ctx* c, const void* auxT, const void* a, const void* b, void* L, const void* U, int m,
-                                            double variance, int sig_begin, int sig_count, cudaStream_t st) {
-    if (sig_count <= 0) return 0;
-    // one thread-block cluster per signature: 8 CTAs share the sums over samples once there is enough work for them, 16
-    // (non-portable size: one cluster per GPC, 8 GPCs) when there are few signatures and a lot of samples
-    int csize = c->D >= 8 * 4 * SIG_THREADS ? 8 : 1;
-    cudaLaunchConfig_t cfg = {};
-    cfg.blockDim = dim3(SIG_THREADS), cfg.dynamicSmemBytes = 0, cfg.stream = st;
-    cudaLaunchAttribute attr;
-    attr.id = cudaLaunchAttributeClusterDimension;
-    attr.val.clusterDim.y = 1, attr.val.clusterDim.z = 1;
-    cfg.attrs = &attr, cfg.numAttrs = 1;
-    if (sig_count <= 8 && c->D >= 16 * 8 * SIG_THREADS) {
-        // (the occupancy query can take tens of milliseconds: asked once per device, dtype and signature count)
-        static signed char cached[64][2][9];
-        static bool cached_init = false;
-        if (!cached_init) memset(cached, -1, sizeof(cached)), cached_init = true;
-        signed char& ok16 = cached[c->device & 63][c->dtype == SAL_F32 ? 0 : 1][sig_count];
-        if (ok16 < 0) {
-            const void* fn = c->dtype == SAL_F32 ? (const void*)signature_embeddings_kernel<float> : (const void*)signature_embeddings_kernel<double>;
-            int n_active = 0;
-            attr.val.clusterDim.x = 16;
-            cfg.gridDim = dim3(sig_count * 16);
-            ok16 = (cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
-                    cudaOccupancyMaxActiveClusters(&n_active, fn, &cfg) == cudaSuccess && n_active >= sig_count)
-                       ? 1
-                       : 0;
-            (void)cudaGetLastError();  // a refused query is not an error of this call: fall back to the portable size
+    // the embedding dimension as a template constant (2 .. 5: registers instead of local-memory arrays), 0 = run-time dimension
+#define SAL_SAMPLE_EMB(TT_, M_)                                                                                                          \
+    sample_embeddings_kernel<TT_, M_><<<grid, 128, 0, st>>>((const TT_*)auxT, (const TT_*)a, (const TT_*)b, b_is_matrix, (const TT_*)L, \
+                                                            (TT_*)U, c->D, c->k, m, variance, maxiter)
+    if (c->dtype == SAL_F32) {  // (float storage is the rare case for the correlated models: run-time dimension only)
+        SAL_SAMPLE_EMB(float, 0);
+    } else {
+        switch (m) {
+            case 2: SAL_SAMPLE_EMB(double, 2); break;
+            case 3: SAL_SAMPLE_EMB(double, 3); break;
+            case 4: SAL_SAMPLE_EMB(double, 4); break;
+            case 5: SAL_SAMPLE_EMB(double, 5); break;
+            default: SAL_SAMPLE_EMB(double, 0); break;
         }
-        if (ok16 == 1) csize = 16;
     }
-    if (const char* e = getenv("SAL_B200_SIG_CLUSTER")) {  // diagnostics: force the cluster size (1, 8 or 16)
-        const int forced = atoi(e);
-        if (forced == 1 || forced == 8 || (forced == 16 && csize == 16)) csize = forced;
-    }
-    attr.val.clusterDim.x = csize;
-    cfg.gridDim = dim3(sig_count * csize);
-    const int64_t D = c->D;
-    const int k = c->k;
-    if (c->dtype == SAL_F32)
-        SAL_CUDA(cudaLaunchKernelEx(&cfg, signature_embeddings_kernel<float>, (const float*)auxT, (const float*)a, (const float*)b, (float*)L,
-                                    (const float*)U, D, k, m, variance, sig_begin));
-    else
-        SAL_CUDA(cudaLaunchKernelEx(&cfg, signature_embeddings_kernel<double>, (const double*)auxT, (const double*)a, (const double*)b,
-                                    (double*)L, (const double*)U, D, k, m, variance, sig_begin));
+#undef SAL_SAMPLE_EMB
     SAL_CUDA(cudaGetLastError());
     c->launches++;
     return 0;

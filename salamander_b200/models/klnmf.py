@@ -210,7 +210,8 @@ class KLNMF(StandardNMF):
                 px = _dist.shared_peer_exchange(nbytes, st.device)
             except Exception as exc:  # pragma: no cover - depends on the system
                 err = exc
-            if not _dist.all_ranks_agree(px is not None, st.device):
+            # (a rank with an empty shard cannot take part in the exchange kernel either: it has no partials to publish)
+            if not _dist.all_ranks_agree(px is not None and (st.hi - st.lo) > 0, st.device):
                 if self.allreduce == "p2p":
                     raise RuntimeError(f"peer-memory all-reduce unavailable on at least one rank ({err})")
                 import warnings

@@ -155,7 +155,9 @@ class SignatureNMF(ABC):
             return
         self._resident_counts = None
         X = np.asarray(self.adata.X)
-        if X.dtype in (np.float32, np.float64) and X.size >= self._DEVICE_CLIP_MIN_SIZE:
+        # float64 is the parity mode: there the counts are clipped on the host BEFORE the initialisation looks at them, exactly
+        # as the reference does (signature_nmf.py:280-281); in float32 mode large matrices are clipped on the device
+        if str(self.dtype).endswith("float32") and X.dtype in (np.float32, np.float64) and X.size >= self._DEVICE_CLIP_MIN_SIZE:
             # large floating matrices are clipped on the device right after the upload (sal_clip_counts) and
             # the host copy is only rewritten if an entry actually changed -- same observable result
             self._clip_on_device = True
