@@ -400,11 +400,14 @@ def secondary(X_host, dev, peak_gbs):
         with model._resident():
             model._in_fit = True
             got = []
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            for _ in range(n_it):
+            for _ in range(n_it):  # parity leg (also loads every kernel variant)
                 model._update_parameters(None)
                 got.append(model.objective_function())
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(n_it):  # timed leg
+                model._update_parameters(None)
+                model.objective_function()
             torch.cuda.synchronize()
             t_gpu = (time.perf_counter() - t0) / n_it
             model._in_fit = False
