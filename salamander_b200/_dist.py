@@ -115,6 +115,13 @@ class PeerExchange:
 _PEER_EXCHANGES: dict[tuple[int, int], PeerExchange] = {}
 
 
+def drop_peer_exchanges() -> None:
+    """Forget the cached exchange buffers.  Called when a fit that used one ends with an exception: the ranks' tag counters may no
+    longer agree, and words of the aborted update may still arrive.  The next fit allocates and zeroes a fresh buffer behind a
+    barrier (every rank has to get there, which is what a collective abort means anyway)."""
+    _PEER_EXCHANGES.clear()
+
+
 def shared_peer_exchange(nbytes: int, device: torch.device) -> PeerExchange:
     """One exchange buffer per process and device, created collectively at first use and kept: allocating symmetric
     memory and the rendezvous cost ~100 ms, a fit at 8 GPUs lasts about as long.  Safe to share between consecutive fits:

@@ -361,7 +361,13 @@ class KLNMF(StandardNMF):
             return self._fit_loop_small(n_given, verbose, verbosity_freq)
         use_period, px = self._period_path(st, n_given)
         if use_period:
-            return self._fit_loop_period(st, px, n_given, verbose, verbosity_freq)
+            try:
+                return self._fit_loop_period(st, px, n_given, verbose, verbosity_freq)
+            except BaseException:
+                if px is not None:  # the exchange protocol may be out of step now: never reuse this buffer
+                    _dist.drop_peer_exchanges()
+                    st.weights.pop("peer_exchange", None)
+                raise
         if freq < 3:
             return super()._fit_loop(given_parameters, verbose, verbosity_freq)
         # spare buffers, pinned read-back slot and captured graphs live with the device state, so that a second

@@ -120,5 +120,27 @@ if rank == 0:
     cos = np.sum(A * B, axis=1) / (np.linalg.norm(A, axis=1) * np.linalg.norm(B, axis=1))
     assert cos.min() >= 0.9999, cos
     print(f"multi-GPU ok: world {world}, fp64 trajectories match, CorrNMFDet matches the oracle, tf32 60-iteration KL {kl_multi:.3f} vs oracle {kl_ref:.3f}")
+# the tf32 fit above ran on the persistent period kernel with the numerator exchange over NVLink INSIDE the kernel
+# (sal_klnmf_period, n_ranks = world): replicas must hold bit-identical signatures
+assert m3.launch_stats["driver"] == "persistent period kernel", m3.launch_stats
+Wp = torch.as_tensor(np.asarray(m3.asignatures.X), device=f"cuda:{local}")
+gathered = [torch.empty_like(Wp) for _ in range(world)]
+dist.all_gather(gathered, Wp)
+assert all(torch.equal(g, gathered[0]) for g in gathered), "replicas must hold bit-identical signatures"
+# the same fit on ONE rank holding everything (replica=True ignores the process group): equal to fp32 rounding
+if rank == 0:
+    solo = sal.models.KLNMF(n_signatures=k, init_method="custom", min_iterations=60, max_iterations=60, dtype="float32", math="tf32",
+                            device=f"cuda:{local}", replica=True)
+    solo.fit(AnnData(Xf), init_kwargs={"signatures_mat": W0f, "exposures_mat": H0f})
+    assert np.allclose(np.asarray(solo.asignatures.X), np.asarray(m3.asignatures.X), rtol=1e-3, atol=1e-9)
+    assert abs(solo.history["objective_function"][-1] - kl_multi) / kl_multi < 1e-6
+# a convergence-driven fit (speculative periods past min_iterations) stops at the same iteration on every rank
+W04, H04 = bench.init_rows(Xl, lo, 4)
+mc2 = sal.models.KLNMF(n_signatures=4, init_method="custom", min_iterations=50, max_iterations=400, tol=1e-4, dtype="float32", math="tf32",
+                       device=f"cuda:{local}", shard_input=False)
+mc2.fit(AnnData(Xl), init_kwargs={"signatures_mat": W04, "exposures_mat": H04})
+n_all = [None] * world
+dist.all_gather_object(n_all, (mc2.n_iterations, len(mc2.history["objective_function"]), mc2.history["objective_function"][-1]))
+assert len(set(n_all)) == 1 and 50 <= mc2.n_iterations < 400, n_all
 dist.barrier()
 dist.destroy_process_group()
