@@ -141,7 +141,7 @@ int sal_create(sal_handle_t* out, int V, int64_t D_local, int k, int dtype, int 
     c->V = V, c->k = k, c->KP = sal_kpad(k), c->dtype = dtype, c->device = device, c->D = D_local;
     c->math = SAL_MATH_FMA;
     c->n_sm = n_sm;
-    c->grid_pass = c->n_sm * (dtype == SAL_F32 ? 2 : 1);
+    c->grid_pass = c->n_sm * 2;  // the largest persistent grid of any pass flavour (sizes the per-CTA partial buffers)
     const size_t es = dtype == SAL_F32 ? 4 : 8;
     c->partial_wnum = scratch_take(device, (size_t)c->grid_pass * SAL_KMAX * SAL_VMAX * es);
     c->partial_obj = (double*)scratch_take(device, (size_t)c->grid_pass * sizeof(double));

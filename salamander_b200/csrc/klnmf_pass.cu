@@ -34,6 +34,13 @@ struct Cfg<double> {
     static constexpr int TS = 96, XP = 98, HPAD = 2, VEC = 2, OCC = 1;
 };
 
+// CTAs per SM: float64 used to run ONE 192-thread CTA per SM of which only 96 threads work in the sample phase -- three warps
+// cannot keep the FP64 pipe busy.  Up to 16 signatures two CTAs fit the shared memory (2 x 101 KB).
+template <typename T, int KP>
+__host__ __device__ constexpr int pass_occ() {
+    return sizeof(T) == 4 ? Cfg<T>::OCC : (KP <= 16 ? 2 : 1);
+}
+
 template <typename T, int N>
 struct alignas(16) Vec {
     T v[N];
@@ -49,7 +56,19 @@ struct PassParams {
 };
 
 __device__ __forceinline__ float sal_div(float a, float b) { return __fdividef(a, b); }
-__device__ __forceinline__ double sal_div(double a, double b) { return a / b; }
+// x / y in float64 through a reciprocal seed (>= 20 bits), two Newton steps and one residual correction of the quotient: a few
+// DFMAs instead of the ~40-instruction IEEE division sequence, within 1 ulp of the correctly rounded quotient (far inside the
+// 1e-9 trajectory tolerance; the single-CTA kernels do the same).  y > 0 and normal here (WH >= k * eps^2).
+__device__ __forceinline__ double sal_div(double a, double b) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+    double e = fma(-b, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-b, r, 1.0);
+    r = fma(r, e, r);
+    const double q = a * r;
+    return fma(fma(-b, q, a), r, q);
+}
 __device__ __forceinline__ float sal_log(float a) { return logf(a); }
 __device__ __forceinline__ double sal_log(double a) { return log(a); }
 __device__ __forceinline__ float sal_sqrt(float a) { return sqrtf(a); }
@@ -70,7 +89,7 @@ __device__ __forceinline__ double block_sum_192(double x, double* s_red) {
 }
 
 template <typename T, int KP>
-__global__ void __launch_bounds__(NT, Cfg<T>::OCC) klnmf_pass_kernel(PassParams<T> p) {
+__global__ void __launch_bounds__(NT, pass_occ<T, KP>()) klnmf_pass_kernel(PassParams<T> p) {
     using C = Cfg<T>;
     constexpr int TS = C::TS, XP = C::XP, HP = KP + C::HPAD, VEC = C::VEC, KH = KP / 2;
     using V16 = Vec<T, VEC>;
@@ -144,10 +163,13 @@ __global__ void __launch_bounds__(NT, Cfg<T>::OCC) klnmf_pass_kernel(PassParams<
         }
         __syncthreads();
 
-        // ---- phase 1: one sample per thread
+        // ---- phase 1: one sample per thread (float) / per PAIR of adjacent threads (double: the tile has 96 samples for 192
+        // threads; each thread of a pair takes half of the features and the pair adds its partial H numerators and KL terms
+        // with one shuffle -- otherwise half of the CTA idles through the most expensive phase)
+        constexpr int SPLIT = sizeof(T) == 8 ? 2 : 1;
         T hn[KP];
-        if (tid < TS) {
-            const int s = tid;
+        if (tid < TS * SPLIT) {
+            const int s = tid / SPLIT, half = tid % SPLIT;
             const int64_t d = d0 + s;
             T* xrow = sX + s * XP;
             if (s < n_valid) {
@@ -163,7 +185,9 @@ __global__ void __launch_bounds__(NT, Cfg<T>::OCC) klnmf_pass_kernel(PassParams<
                 // (exact within a factor of two), so the term keeps ~1e-7 relative accuracy instead of 1e-7 * x; terms are
                 // summed in double.  The fit's convergence test (tol 1e-7, signature_nmf.py:376) sees this number.
                 double kl = 0.0;
-                for (int v0 = 0; v0 < V; v0 += VEC) {
+                const int v_half = (((V + VEC - 1) / VEC + SPLIT - 1) / SPLIT) * VEC;
+                const int v_begin = half * v_half, v_end = v_begin + v_half < V ? v_begin + v_half : V;
+                for (int v0 = v_begin; v0 < v_end; v0 += VEC) {
                     const V16 x = *reinterpret_cast<const V16*>(xrow + v0);
                     V16 r;
 #pragma unroll
@@ -194,8 +218,14 @@ __global__ void __launch_bounds__(NT, Cfg<T>::OCC) klnmf_pass_kernel(PassParams<
                     }
                     *reinterpret_cast<V16*>(xrow + v0) = r;
                 }
-                if (p.flags & SAL_PASS_SAMPLEWISE) p.per_sample[d] = (T)kl;
-                if (p.flags & (SAL_PASS_OBJECTIVE | SAL_PASS_POISSON)) {
+                if (SPLIT == 2) {  // the pair's halves (both lanes of a pair are always active together)
+                    const unsigned int pm = __activemask();
+#pragma unroll
+                    for (int j = 0; j < KP; ++j) hn[j] += __shfl_xor_sync(pm, hn[j], 1);
+                    kl += __shfl_xor_sync(pm, kl, 1);
+                }
+                if ((p.flags & SAL_PASS_SAMPLEWISE) && half == 0) p.per_sample[d] = (T)kl;
+                if ((p.flags & (SAL_PASS_OBJECTIVE | SAL_PASS_POISSON)) && half == 0) {
                     double o = kl * (double)wk;
                     if (p.w_lhalf && !do_pois) {
                         T sq = (T)0;
@@ -205,7 +235,7 @@ __global__ void __launch_bounds__(NT, Cfg<T>::OCC) klnmf_pass_kernel(PassParams<
                     }
                     obj_acc += o;
                 }
-                if (do_h) {
+                if (do_h && half == 0) {
                     if (p.h_scale) {
 #pragma unroll
                         for (int j = 0; j < KP; ++j) hn[j] = h[j];
@@ -245,7 +275,7 @@ __global__ void __launch_bounds__(NT, Cfg<T>::OCC) klnmf_pass_kernel(PassParams<
                             if (j < k) og[j] = hn[j];
                     }
                 }
-            } else {
+            } else if (half == 0) {
                 const int vr = (V + VEC - 1) / VEC * VEC;
                 for (int v0 = 0; v0 < vr; ++v0) xrow[v0] = (T)0;
             }
@@ -587,7 +617,8 @@ int launch_pass_t(sal_ctx* c, const PassArgs& a, cudaStream_t st) {
     p.vec_x = (c->V % C::VEC == 0) && (((uintptr_t)a.X) % 16 == 0);
     p.vec_h = (c->k % C::VEC == 0) && (((uintptr_t)a.H_out) % 16 == 0);
     const int64_t n_tiles = (c->D + C::TS - 1) / C::TS;
-    const int grid = (int)(n_tiles < c->grid_pass ? n_tiles : c->grid_pass);
+    const int64_t resident = (int64_t)c->n_sm * pass_occ<T, KP>();
+    const int grid = (int)(n_tiles < resident ? n_tiles : resident);
     if (int e = sal_timing_begin(c, a.flags, st)) return e;
     klnmf_pass_kernel<T, KP><<<grid, NT, smem, st>>>(p);
     SAL_CUDA(cudaGetLastError());
