@@ -259,8 +259,9 @@ def workload_config(args):
         "l2": "per-iteration inputs are 544 MB per GPU at N = 1 and 272 MB at N = 2 (> 126 MB L2, no flush needed); at N >= 4 the "
               "strong-scaling shard (<= 136 MB) is L2-resident by construction and is not flushed",
         "timing": "CUDA events on the launch stream around exactly --steps iterations of the fit driver (updates + the objective every "
-                  "conv_test_freq iterations and its device-to-host copy; start event right before the driver's first launch), barrier + "
-                  "synchronize on both sides, max over ranks; repeated, median reported",
+                  "conv_test_freq iterations and its device-to-host copy; start event right before the driver's first launch, end event right "
+                  "behind its last launch + copy; N > 1: a one-element all-reduce enqueued in front of the start event aligns the streams), "
+                  "barrier + synchronize on both sides, max over ranks; repeated, median reported",
     }
 
 
@@ -539,25 +540,36 @@ def run_ours(args):
     run_loop(args.steps)
     reps_ms = []
     period_driver = model.launch_stats.get("driver") == "persistent period kernel"
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0, ev1, ev_host = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     launches_timed = 0
+    host_return_ms = []
+    align = torch.zeros(1, device=dev)
     with clocks:
         for rep in range(args.reps):
             barrier()  # immediately before the timed region: the ranks enter it together
             launches0 = st.ws.launches
-            # the start event is recorded by the fit driver itself right before its first launch (KLNMF.loop_start_event): the timed
-            # region is the device time of exactly --steps iterations incl. objectives and their device-to-host copies, not the
-            # Python prologue of the call (the two-kernel driver has no such hook: its event is recorded here)
+            # The timed region is DEVICE time of exactly --steps iterations incl. the objectives and their device-to-host copies: the fit
+            # driver records the start event right before its first launch and the end event right behind the last launch + copy
+            # (KLNMF.loop_start_event / loop_end_event).  On several GPUs the ranks leave the host-side barrier tens of microseconds apart
+            # -- as much as a dozen updates at the 8-GPU shard size, and the early ranks would be charged the wait for the late ones in
+            # their first exchange -- so a one-element all-reduce is enqueued right in front of the start event: the streams leave it
+            # together and the driver's launches queue up behind it.  (The two-kernel driver has no hooks: events recorded here.)
+            if world > 1:
+                dist.all_reduce(align)
             model.loop_start_event = ev0 if period_driver else None
+            model.loop_end_event = ev1 if period_driver else None
             if not period_driver:
                 ev0.record()
             of_values, n_done = run_loop(args.steps)
-            ev1.record()
-            model.loop_start_event = None
+            if not period_driver:
+                ev1.record()
+            ev_host.record()  # the host has the objectives and the loop has returned
+            model.loop_start_event = model.loop_end_event = None
             barrier()
             assert n_done == args.steps
             launches_timed = st.ws.launches - launches0
             reps_ms.append(max_over_ranks(ev0.elapsed_time(ev1)))
+            host_return_ms.append(max_over_ranks(ev0.elapsed_time(ev_host)))
     elapsed_ms = float(np.median(reps_ms))
     its = args.steps / (elapsed_ms * 1e-3)
     launch_stats = dict(model.launch_stats)
@@ -584,6 +596,8 @@ def run_ours(args):
         chain_period(2)
         barrier()
         ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if world > 1:
+            dist.all_reduce(align)  # the streams start together (see above)
         ev2.record()
         chain_period(n_chain)
         ev3.record()
@@ -674,6 +688,7 @@ def run_ours(args):
             "detail": {
                 "math": args.math,
                 "timed_repetitions_ms": reps_ms,
+                "until_the_loop_returned_on_the_host_ms": host_return_ms,
                 "value_is": f"--steps / median of {args.reps} timed repetitions of exactly --steps iterations each",
                 "warmup_iterations_run": n_warm + args.steps,
                 "fit_driver": launch_stats,

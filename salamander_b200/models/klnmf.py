@@ -67,6 +67,7 @@ class KLNMF(StandardNMF):
         # kernel (sal_klnmf_period, see _fit_loop_period); False falls back to the two-kernel updates below
         self.use_period_kernel = True
         self.loop_start_event = None  # optional torch.cuda.Event the period driver records right before its first launch
+        self.loop_end_event = None    # ... and right behind the last planned launch and the copy of its objectives to the host
         self.use_small_kernel = True  # problems that fit one SM: persistent single-CTA kernel (see _fit_loop_small)
         # multi-GPU all-reduce of the numerator: "auto" / "p2p" = one-shot NVLink exchange fused into the reduction
         # kernel (sal_klnmf_update_p2p), "nccl" = library collective between separate kernels
@@ -295,6 +296,8 @@ class KLNMF(StandardNMF):
                 )
                 obj_host[slot].copy_(obj_dev[slot], non_blocking=True)
                 events[slot].record()
+                if nxt_launch + 1 == len(plan) and self.loop_end_event is not None:
+                    self.loop_end_event.record()  # measurement aid: everything the loop asked of the device has been enqueued
                 pending.append((slot, seg, m + (1 if fin else 0), cur, nxt))
                 cur, nxt_launch, n_launched = nxt, nxt_launch + 1, n_launched + 1
             if not pending:
