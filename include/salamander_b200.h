@@ -277,6 +277,23 @@ int sal_corrnmf_signature_embeddings(sal_handle_t h, const void* auxT, const voi
 int sal_corrnmf_signature_embeddings_range(sal_handle_t h, const void* auxT, const void* a, const void* b, void* L,
                                            const void* U, int m, double variance, int sig_begin, int sig_count,
                                            void* stream);
+/* Several GPUs, samples sharded: every rank runs the Newton-CG of ALL signatures on ITS samples and the
+ * totals of each objective / gradient / Hessian evaluation (the sums over samples of _utils_corrnmf.py:182-351) are
+ * exchanged INSIDE the kernel: sequence-tagged 16-byte words pushed over NVLink into every peer's receive buffer
+ * (peers = device array [n_ranks] of buffers of sal_corrnmf_sig_exchange_bytes(k, n_ranks) bytes, zeroed once, as mapped
+ * into this rank's address space) and summed in rank order -- every rank obtains the same bits, so the solvers stay in lock
+ * step and L stays bit-identical.  launch_id: 1, 2, ... < 32768, the same on every rank and larger for every later launch on
+ * the same buffers (it prefixes the tags; zero the buffers behind a barrier before starting over). */
+size_t sal_corrnmf_sig_exchange_bytes(int k, int n_ranks);
+int sal_corrnmf_signature_embeddings_p2p(sal_handle_t h, const void* auxT, const void* a, const void* b, void* L,
+                                         const void* U, int m, double variance, const void* peers, int n_ranks, int rank,
+                                         unsigned int launch_id, void* stream);
+/* The same protocol with 2 ranks emulated on ONE device in one launch (tests on a single GPU): arrays of n_virtual handles
+ * / buffers, peer_tables[v] = rank v's device array of the receive buffers. */
+int sal_corrnmf_signature_embeddings_emulated(const sal_handle_t* hs, int n_virtual, const void* const* auxT,
+                                              const void* const* a, const void* const* b, void* const* L,
+                                              const void* const* U, int m, double variance,
+                                              const void* const* peer_tables, unsigned int launch_id, void* stream);
 /* out[0] = sum L^2, out[1] = sum U^2 (update_variance corrnmf_det.py:60-69, ELBO priors _utils_corrnmf.py:93-98),
  * out[2] = sum lnGamma(1 + X) when X != NULL (constant of poisson_llh, _utils_klnmf.py:159) */
 int sal_corrnmf_norms(sal_handle_t h, const void* L, const void* U, int m, const void* X_or_null, double* out,

@@ -394,6 +394,25 @@ def klnmf_period_emulated(workspaces, Xs, W_ins, W_outs, H_ins, H_outs, n_given:
     )
 
 
+def corrnmf_signature_embeddings_emulated(workspaces, auxTs, a_s, bs, Ls, Us, m: int, variance: float, peer_tables, launch_id: int) -> None:
+    """1 or 2 emulated ranks (one Workspace, sample shard and receive buffer each) inside ONE launch on one GPU
+    (sal_corrnmf_signature_embeddings_emulated): the in-kernel exchange of the signature-embedding solver without a second GPU."""
+    n = len(workspaces)
+    lib = workspaces[0].lib
+
+    def arr(tensors):
+        return (C.c_void_p * n)(*[int(t.data_ptr()) for t in tensors])
+
+    hs = (C.c_void_p * n)(*[w._h.value if isinstance(w._h, C.c_void_p) else w._h for w in workspaces])
+    _lib.check(
+        lib.sal_corrnmf_signature_embeddings_emulated(
+            hs, n, arr(auxTs), arr(a_s), arr(bs), arr(Ls), arr(Us), int(m), float(variance), arr(peer_tables), int(launch_id),
+            workspaces[0]._stream(),
+        ),
+        "sal_corrnmf_signature_embeddings_emulated",
+    )
+
+
 def trim_device_scratch() -> None:
     """Free the workspace scratch buffers that finished fits left on the library's per-device free list (sal_trim_scratch)."""
     _lib.check(_lib.load().sal_trim_scratch(), "sal_trim_scratch")

@@ -112,7 +112,7 @@ class PeerExchange:
         dist.barrier()  # every buffer is zeroed and mapped before anybody publishes into it
 
 
-_PEER_EXCHANGES: dict[tuple[int, int], PeerExchange] = {}
+_PEER_EXCHANGES: dict[tuple[int, int, str], PeerExchange] = {}
 
 
 def drop_peer_exchanges() -> None:
@@ -122,16 +122,35 @@ def drop_peer_exchanges() -> None:
     _PEER_EXCHANGES.clear()
 
 
-def shared_peer_exchange(nbytes: int, device: torch.device) -> PeerExchange:
-    """One exchange buffer per process and device, created collectively at first use and kept: allocating symmetric
-    memory and the rendezvous cost ~100 ms, a fit at 8 GPUs lasts about as long.  Safe to share between consecutive fits:
-    the sequence number that tags every word lives with the buffer and only ever increases, so words left over from an
-    earlier fit (even one with another k, i.e. another layout) can never carry a tag a later update waits for.  Every
-    rank must ask for the same size in the same order (callers pass the size for the largest supported k)."""
-    key = (device.index if device.index is not None else torch.cuda.current_device(), world()[1])
+def shared_peer_exchange(nbytes: int, device: torch.device, name: str = "klnmf") -> PeerExchange:
+    """One exchange buffer per process, device and protocol (``name``), created collectively at first use and kept:
+    allocating symmetric memory and the rendezvous cost ~100 ms, a fit at 8 GPUs lasts about as long.  Safe to share between
+    consecutive fits: the sequence number that tags every word lives with the buffer and only ever increases, so words left
+    over from an earlier fit (even one with another k, i.e. another layout) can never carry a tag a later update waits for.
+    Every rank must ask for the same size in the same order (callers pass the size for the largest supported k)."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), world()[1], name)
     px = _PEER_EXCHANGES.get(key)
     if px is None or px.nbytes < nbytes:
         px = PeerExchange(nbytes, device)
         px.nbytes = nbytes
+        px.launch_id = 0
         _PEER_EXCHANGES[key] = px
     return px
+
+
+LAUNCH_ID_LIMIT = 1 << 15
+
+
+def next_launch_id(px: PeerExchange) -> int:
+    """Launch number that prefixes the tags of a kernel exchanging through ``px`` (the CorrNMF signature-embedding solver): 1, 2,
+    ... on every rank alike.  Before the 15-bit prefix would repeat, the buffers are zeroed behind a barrier and the count
+    starts over -- every rank gets here at the same launch."""
+    px.launch_id += 1
+    if px.launch_id >= LAUNCH_ID_LIMIT:
+        torch.cuda.synchronize()
+        dist.barrier()
+        px.buf.zero_()
+        torch.cuda.synchronize()
+        dist.barrier()
+        px.launch_id = 1
+    return px.launch_id

@@ -532,6 +532,39 @@ int sal_corrnmf_signature_embeddings_range(sal_handle_t h, const void* auxT, con
     return sal_launch_corrnmf_signature_embeddings(h, auxT, a, b, L, U, m, variance, sig_begin, sig_count, (cudaStream_t)stream);
 }
 
+size_t sal_corrnmf_sig_exchange_bytes(int k, int n_ranks) { return sal_corrnmf_sig_exchange_words(k, n_ranks) * 16; }
+
+int sal_corrnmf_signature_embeddings_p2p(sal_handle_t h, const void* auxT, const void* a, const void* b, void* L, const void* U, int m,
+                                         double variance, const void* peers, int n_ranks, int rank, unsigned int launch_id,
+                                         void* stream) {
+    SAL_CORR_COMMON(m);
+    SAL_CHECK_ARG(a && L && (h->D == 0 || (auxT && b && U)), "null argument");
+    SAL_CHECK_ARG(variance > 0.0, "variance must be positive");
+    SAL_CHECK_ARG(n_ranks >= 1 && n_ranks <= 8 && rank >= 0 && rank < n_ranks, "1 .. 8 ranks, 0 <= rank < n_ranks");
+    SAL_CHECK_ARG(n_ranks == 1 || peers, "peers is null");
+    SAL_CHECK_ARG(launch_id >= 1 && launch_id < (1u << 15), "launch_id must be in 1 .. 32767 (zero the receive buffers and start over)");
+    const SigLaunchRank r = {h, auxT, a, b, U, L, peers, rank};
+    return sal_launch_corrnmf_signature_embeddings_v(&r, 1, m, variance, 0, h->k, n_ranks, launch_id, (cudaStream_t)stream);
+}
+
+int sal_corrnmf_signature_embeddings_emulated(const sal_handle_t* hs, int n_virtual, const void* const* auxT, const void* const* a,
+                                              const void* const* b, void* const* L, const void* const* U, int m, double variance,
+                                              const void* const* peer_tables, unsigned int launch_id, void* stream) {
+    SAL_CHECK_ARG(hs && n_virtual >= 1 && n_virtual <= 2, "1 or 2 emulated ranks");
+    SAL_CHECK_ARG(auxT && a && b && L && U && peer_tables, "null argument array");
+    sal_handle_t h = hs[0];
+    SAL_CORR_COMMON(m);
+    SAL_CHECK_ARG(variance > 0.0, "variance must be positive");
+    SAL_CHECK_ARG(launch_id >= 1 && launch_id < (1u << 15), "launch_id must be in 1 .. 32767");
+    SigLaunchRank rs[2];
+    for (int v = 0; v < n_virtual; ++v) {
+        SAL_CHECK_ARG(hs[v] && hs[v]->device == h->device && hs[v]->k == h->k && hs[v]->dtype == h->dtype, "emulated ranks must share device, k and dtype");
+        SAL_CHECK_ARG(a[v] && L[v] && peer_tables[v] && (hs[v]->D == 0 || (auxT[v] && b[v] && U[v])), "null argument");
+        rs[v] = {hs[v], auxT[v], a[v], b[v], U[v], L[v], peer_tables[v], v};
+    }
+    return sal_launch_corrnmf_signature_embeddings_v(rs, n_virtual, m, variance, 0, h->k, n_virtual, launch_id, (cudaStream_t)stream);
+}
+
 int sal_corrnmf_norms(sal_handle_t h, const void* L, const void* U, int m, const void* X_or_null, double* out, void* stream) {
     SAL_CORR_COMMON(m);
     SAL_CHECK_ARG(L && out, "null argument");

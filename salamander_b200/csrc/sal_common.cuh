@@ -144,6 +144,17 @@ int sal_launch_corrnmf_sample_embeddings(sal_ctx* c, const void* auxT, const voi
                                          void* U, int m, double variance, int maxiter, cudaStream_t st);
 int sal_launch_corrnmf_signature_embeddings(sal_ctx* c, const void* auxT, const void* a, const void* b, void* L, const void* U, int m,
                                             double variance, int sig_begin, int sig_count, cudaStream_t st);
+// (several GPUs / emulated ranks: one entry per rank served by this launch; peers = device array [n_gpus] of receive buffers)
+struct SigLaunchRank {
+    sal_ctx* c;
+    const void *auxT, *a, *b, *U;
+    void* L;
+    const void* peers;
+    int gpu;
+};
+int sal_launch_corrnmf_signature_embeddings_v(const SigLaunchRank* rs, int n_virtual, int m, double variance, int sig_begin, int sig_count,
+                                              int n_gpus, unsigned int launch_id, cudaStream_t st);
+size_t sal_corrnmf_sig_exchange_words(int k, int n_gpus);  // 16-byte words of one receive buffer
 int sal_launch_corrnmf_norms(sal_ctx* c, const void* L, const void* U, int m, const void* X_or_null, double* out, cudaStream_t st);
 
 // ---- persistent period kernel (klnmf_period_tf32.cu) ------------------------------------------------------

@@ -95,6 +95,21 @@ class CorrState:
         self.lgamma_sum = None  # sum lnGamma(1 + x), constant of the ELBO, computed at the first objective
 
     # -- ranks -----------------------------------------------------------------------------------
+    def sig_exchange(self):
+        """Symmetric receive buffers of the signature-embedding solver's in-kernel exchange (``None``: single GPU, or peer
+        memory is unavailable on at least one rank -- decided collectively, once per device state)."""
+        if self.world == 1 or getattr(self.model, "allreduce", "auto") == "nccl":
+            return None
+        if not hasattr(self, "_sig_px"):
+            px = None
+            try:
+                nbytes = int(self.lib.sal_corrnmf_sig_exchange_bytes(32, self.world))  # sized for the largest k: shared by all fits
+                px = _dist.shared_peer_exchange(nbytes, self.device, name="corrnmf_sig")
+            except Exception:  # pragma: no cover - depends on the system
+                px = None
+            self._sig_px = px if _dist.all_ranks_agree(px is not None, self.device) else None
+        return self._sig_px
+
     def allreduce(self, t: torch.Tensor) -> torch.Tensor:
         if self.world > 1:
             _dist.allreduce_sum_(t)
@@ -270,8 +285,17 @@ class CorrNMFDet(CorrNMF):
             if st.world == 1:
                 st.call("sal_corrnmf_signature_embeddings", st.auxT, st.a, st.b, st.L, st.U, st.m, float(self.variance))
                 return
-            # every rank: all samples' aux / scalings / embeddings, Newton-CG for its share of the signatures; the rows
-            # of L are then exchanged by summing arrays that are zero outside the owner's rows (exact)
+            px = st.sig_exchange()
+            if px is not None:
+                # every rank: Newton-CG of ALL signatures on ITS samples; the totals of each evaluation are exchanged inside the
+                # kernel over NVLink and summed in rank order, so the ranks' solvers run in lock step and L stays bit-identical
+                st.call(
+                    "sal_corrnmf_signature_embeddings_p2p", st.auxT, st.a, st.b, st.L, st.U, st.m, float(self.variance),
+                    px.peers, st.world, st.rank, _dist.next_launch_id(px),
+                )
+                return
+            # fallback without peer memory -- every rank: all samples' aux / scalings / embeddings, Newton-CG for its share of the
+            # signatures; the rows of L are then exchanged by summing arrays that are zero outside the owner's rows (exact)
             aux_all, b_all, U_all = (_dist.gather_rows(t, st.D_total) for t in (st.auxT, st.b, st.U))
             j0, j1 = _dist.shard_bounds(st.k, st.world, st.rank)
             st.call(

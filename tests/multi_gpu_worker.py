@@ -69,6 +69,7 @@ for _ in range(n_iter):
     hist_ref.append(oracle_corr.elbo(X, W, H, L, U, var))
 with mc._resident() as st_c:
     assert st_c.world == world and st_c.D == len(range(*sal_dist.shard_bounds(192, world, rank)))
+    assert st_c.sig_exchange() is not None  # the signature-embedding solver exchanges its sums inside the kernel (NVLink)
     mc._in_fit = True
     hist_c = []
     for _ in range(n_iter):

@@ -6,9 +6,12 @@ reference's golden fixtures (tests/golden/models/corrnmf), plus several whole it
 
 import os
 
+import ctypes as C
+
 import numpy as np
 import pandas as pd
 import pytest
+import torch
 from conftest import ROOT, golden_path
 
 import salamander_b200 as sal
@@ -223,3 +226,46 @@ def test_fit_matches_the_live_reference_trajectory(tag):
     assert np.allclose(model.asignatures.obsm["embeddings"], z["L"], rtol=1e-5, atol=1e-8)
     assert np.allclose(model.adata.obsm["embeddings"], z["U"], rtol=1e-5, atol=1e-7)
     assert np.isclose(model.variance, float(z["var"]), rtol=1e-7)
+
+
+@pytest.mark.parametrize("D,k,m", [(192, 3, 2), (5000, 5, 4), (40_000, 4, 3), (70_001, 2, 6)])
+def test_signature_embeddings_exchange_with_emulated_ranks(D, k, m):
+    """The multi-GPU protocol of the signature-embedding solver (sal_corrnmf_signature_embeddings_p2p: every rank sweeps its own
+    samples, the totals of each evaluation travel as tagged words and are summed in rank order) with two ranks emulated on ONE
+    GPU: both ranks must arrive at bit-identical embeddings, equal to the single-rank solve to rounding, launch after launch
+    on the same receive buffers."""
+    from salamander_b200 import _lib
+    from salamander_b200._device import Workspace, corrnmf_signature_embeddings_emulated
+
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(D + k)
+    tens = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)  # noqa: E731
+    lib = _lib.load()
+    n_words = int(lib.sal_corrnmf_sig_exchange_bytes(k, 2)) // 16
+    recv = [torch.zeros((n_words, 4), dtype=torch.int32, device=dev) for _ in range(2)]
+    table = [torch.tensor([recv[0].data_ptr(), recv[1].data_ptr()], dtype=torch.int64, device=dev) for _ in range(2)]
+    cut = D // 3  # unequal shards
+    for launch in range(1, 4):
+        U = rng.normal(size=(D, m)) * 0.5
+        b = rng.normal(size=D) * 0.3 + 2.0
+        a = rng.normal(size=k) * 0.2
+        L0 = rng.normal(size=(k, m)) * 0.5
+        H = np.exp(a[None, :] + b[:, None] + U @ L0.T)
+        aux = H * rng.uniform(0.5, 1.5, size=(D, k))
+        var = 0.7 + 0.1 * launch
+        ws_all = Workspace(96, D, k, torch.float64, dev)
+        L_one = tens(L0)
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(lib.sal_corrnmf_signature_embeddings(ws_all._h, *(C.c_void_p(t.data_ptr()) for t in (tens(aux), tens(a), tens(b), L_one, tens(U))),
+                                                        m, var, stream), "sal_corrnmf_signature_embeddings")
+        shards = [slice(0, cut), slice(cut, D)]
+        wss = [Workspace(96, sl.stop - sl.start, k, torch.float64, dev) for sl in shards]
+        Ls = [tens(L0), tens(L0)]
+        keep = [[tens(aux[sl]) for sl in shards], [tens(a), tens(a)], [tens(b[sl]) for sl in shards], [tens(U[sl]) for sl in shards]]
+        corrnmf_signature_embeddings_emulated(wss, keep[0], keep[1], keep[2], Ls, keep[3], m, var, table, launch)
+        torch.cuda.synchronize()
+        assert torch.equal(Ls[0], Ls[1]), "emulated ranks must hold bit-identical signature embeddings"
+        assert not torch.equal(Ls[0], tens(L0))
+        assert np.allclose(Ls[0].cpu().numpy(), L_one.cpu().numpy(), rtol=1e-7, atol=1e-10), (Ls[0], L_one)
+        for w in wss + [ws_all]:
+            w.close()
