@@ -134,7 +134,7 @@ __device__ double block_sum_256(double v, double* s_red) {
 
 // sums[j] = sum_d aux_dj, sums[k + j] = sum_d exp(b_d + l_j.u_d)  (this rank's samples).  SCAL_BLOCKS CTAs per signature
 // (blockIdx.y = signature) each leave a partial pair; the last one to finish adds them in block order (deterministic).
-constexpr int SCAL_BLOCKS = 32;
+constexpr int SCAL_BLOCKS = 128;  // <= 256: the last block adds the partials one per thread
 template <typename T>
 __global__ void __launch_bounds__(256) signature_scalings_kernel(const T* auxT, const T* b, const T* L, const T* U, int64_t D, int k, int m,
                                                                 double* partial, unsigned int* counter, double* sums) {
@@ -144,6 +144,7 @@ __global__ void __launch_bounds__(256) signature_scalings_kernel(const T* auxT, 
     double l[MAXM];
     for (int q = 0; q < m; ++q) l[q] = (double)L[j * m + q];
     double s1 = 0.0, s2 = 0.0;
+#pragma unroll 2
     for (int64_t d = (int64_t)blockIdx.x * 256 + threadIdx.x; d < D; d += (int64_t)SCAL_BLOCKS * 256) {
         double sp = 0.0;
         for (int q = 0; q < m; ++q) sp += l[q] * (double)U[d * m + q];
@@ -159,15 +160,17 @@ __global__ void __launch_bounds__(256) signature_scalings_kernel(const T* auxT, 
         last = atomicAdd(&counter[j], 1u) == SCAL_BLOCKS - 1;
     }
     __syncthreads();
-    if (last && threadIdx.x == 0) {
+    if (last) {  // (block-uniform) one partial per thread, then the fixed-order tree of block_sum_256
         __threadfence();
-        double t1 = 0.0, t2 = 0.0;
-        for (int i = 0; i < SCAL_BLOCKS; ++i) {
-            t1 += ((volatile double*)partial)[(2 * j) * SCAL_BLOCKS + i];
-            t2 += ((volatile double*)partial)[(2 * j + 1) * SCAL_BLOCKS + i];
+        const int i = threadIdx.x;
+        double t1 = i < SCAL_BLOCKS ? ((volatile double*)partial)[(2 * j) * SCAL_BLOCKS + i] : 0.0;
+        double t2 = i < SCAL_BLOCKS ? ((volatile double*)partial)[(2 * j + 1) * SCAL_BLOCKS + i] : 0.0;
+        t1 = block_sum_256(t1, s_red);
+        t2 = block_sum_256(t2, s_red);
+        if (threadIdx.x == 0) {
+            sums[j] = t1, sums[k + j] = t2;
+            counter[j] = 0;
         }
-        sums[j] = t1, sums[k + j] = t2;
-        counter[j] = 0;
     }
 }
 
@@ -179,7 +182,7 @@ __global__ void signature_scalings_finish_kernel(const double* sums, int k, T* a
 
 // out[0] = sum L^2, out[1] = sum U^2 (this rank's samples), out[2] = sum_x lnGamma(1 + x) when X != null.
 // blockIdx.y selects the quantity, NORM_BLOCKS blocks each leave a partial; the last block to finish adds them in order.
-constexpr int NORM_BLOCKS = 64;
+constexpr int NORM_BLOCKS = 256;  // <= 256: the last block adds the partials one per thread
 template <typename T>
 __global__ void __launch_bounds__(256) norms_kernel(const T* L, int64_t nL, const T* U, int64_t nU, const T* X, int64_t nX,
                                                    double* partial, unsigned int* counter, double* out) {
@@ -189,6 +192,7 @@ __global__ void __launch_bounds__(256) norms_kernel(const T* L, int64_t nL, cons
     const T* src = q == 0 ? L : q == 1 ? U : X;
     const int64_t n = q == 0 ? nL : q == 1 ? nU : nX;
     double s = 0.0;
+#pragma unroll 4
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)NORM_BLOCKS * 256) {
         const double v = (double)src[i];
         s += q < 2 ? v * v : lgamma(1.0 + v);
@@ -200,12 +204,14 @@ __global__ void __launch_bounds__(256) norms_kernel(const T* L, int64_t nL, cons
         last = atomicAdd(&counter[q], 1u) == NORM_BLOCKS - 1;
     }
     __syncthreads();
-    if (last && threadIdx.x == 0) {
+    if (last) {  // (block-uniform)
         __threadfence();
-        double t = 0.0;
-        for (int b = 0; b < NORM_BLOCKS; ++b) t += ((volatile double*)partial)[q * NORM_BLOCKS + b];
-        out[q] = t;
-        counter[q] = 0;
+        double t = threadIdx.x < NORM_BLOCKS ? ((volatile double*)partial)[q * NORM_BLOCKS + threadIdx.x] : 0.0;
+        t = block_sum_256(t, s_red);
+        if (threadIdx.x == 0) {
+            out[q] = t;
+            counter[q] = 0;
+        }
     }
 }
 

@@ -24,8 +24,12 @@ with model._resident():
         model._update_parameters(None)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for _ in range(n_it):
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(n_it + 1)]
+    evs[0].record()
+    for i in range(n_it):
         model._update_parameters(None)
+        evs[i + 1].record()
     torch.cuda.synchronize()
     print(f"CorrNMFDet 96 x {D}: {(time.perf_counter() - t0) / n_it * 1e3:.3f} ms / iteration")
+    print("per iteration (device, ms):", " ".join(f"{evs[i].elapsed_time(evs[i + 1]):.3f}" for i in range(n_it)))
     model._in_fit = False
