@@ -60,9 +60,13 @@ enum {
     SAL_PASS_POISSON = 32,   /* objective = sum x ln(wh) - wh  (Poisson llh w/o ln Gamma)    */
     SAL_PASS_NOCLIP = 64,    /* with UPDATE_H: H_out = H * W^T A without the clip -- this is CorrNMF's
                                 aux^T [D][k] (compute_aux, _utils_corrnmf.py:28-52) when H_in holds the exposures */
-    SAL_PASS_PARTIALS_ONLY = 128 /* measurement aid: run the streaming kernel only and leave its per-CTA partial sums in
+    SAL_PASS_PARTIALS_ONLY = 128, /* measurement aid: run the streaming kernel only and leave its per-CTA partial sums in
                                 the workspace (Wnum / objective / hsum are NOT written), so that a caller can time the
                                 kernel back to back between one pair of events (bench.py roofline leg) */
+    SAL_PASS_SCALED_UPDATE = 256 /* with h_scale and UPDATE_H: H_out = the multiplicative update of the rescaled exposures
+                                Hs = clip(H_in * h_scale), i.e. MvNMF's next H step (mvnmf.py:197-203 after the
+                                normalisation of :80-88) fused into the line-search trial's objective pass, instead of
+                                Hs itself; the objective is still KL(X || W Hs) */
 };
 
 const char* sal_last_error(void);

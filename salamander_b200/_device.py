@@ -20,6 +20,7 @@ from ._lib import (  # noqa: F401  (re-exported for callers)
     PASS_OBJECTIVE,
     PASS_POISSON,
     PASS_SAMPLEWISE,
+    PASS_SCALED_UPDATE,
     PASS_UPDATE_H,
     PASS_WNUM,
 )

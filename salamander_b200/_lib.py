@@ -18,6 +18,7 @@ SAL_F32, SAL_F64 = 0, 1
 MATH_FMA, MATH_TF32, MATH_TF32_ALWAYS = 0, 1, 2
 PASS_UPDATE_H, PASS_WNUM, PASS_OBJECTIVE, PASS_SAMPLEWISE, PASS_HSUM, PASS_POISSON, PASS_NOCLIP = 1, 2, 4, 8, 16, 32, 64
 PASS_PARTIALS_ONLY = 128
+PASS_SCALED_UPDATE = 256
 
 _vp, _i, _i64, _d = C.c_void_p, C.c_int, C.c_int64, C.c_double
 

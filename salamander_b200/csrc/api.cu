@@ -243,6 +243,8 @@ int sal_klnmf_pass(sal_handle_t h, const void* X, const void* W, const void* H_i
     SAL_CHECK_ARG(!((flags & SAL_PASS_SAMPLEWISE) && (flags & SAL_PASS_POISSON)), "SAMPLEWISE and POISSON are exclusive");
     SAL_CHECK_ARG(!(flags & SAL_PASS_SAMPLEWISE) || per_sample || h->D == 0, "SAMPLEWISE needs per_sample");
     SAL_CHECK_ARG(!(flags & SAL_PASS_HSUM) || hsum, "HSUM needs hsum");
+    SAL_CHECK_ARG(!(flags & SAL_PASS_SCALED_UPDATE) || (h_scale && (flags & SAL_PASS_UPDATE_H) && !w_kl && !w_lhalf && !(flags & SAL_PASS_NOCLIP)),
+                  "SCALED_UPDATE needs h_scale and UPDATE_H (no weights, no NOCLIP)");
     SAL_CUDA(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
     if (h->D == 0) {  // empty shard: outputs are exact zeros

@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(NT, pass_occ<T, KP>()) klnmf_pass_kernel(PassP
                     obj_acc += o;
                 }
                 if (do_h && half == 0) {
-                    if (p.h_scale) {
+                    if (p.h_scale && !(p.flags & SAL_PASS_SCALED_UPDATE)) {
 #pragma unroll
                         for (int j = 0; j < KP; ++j) hn[j] = h[j];
                     } else if (p.flags & SAL_PASS_NOCLIP) {

@@ -507,7 +507,7 @@ klnmf_pass_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
 // Column sums of H [D][k] (SAL_PASS_HSUM, MvNMF's rowsums_H): block b owns a contiguous run of rows and reads it as a flat
 // array; HSUM_THREADS is rounded down to a multiple of k by masking, so a thread always meets the same column.  The
 // partials land in partial_hsum[b][SAL_KMAX]; the reduction kernel adds the blocks in order.
-constexpr int HSUM_THREADS = 256;
+constexpr int HSUM_THREADS = 1024;
 __global__ void __launch_bounds__(HSUM_THREADS) hsum_partials_kernel(const float* H, int64_t D, int k, double* partial_hsum) {
     __shared__ double s_acc[HSUM_THREADS];
     const int tid = threadIdx.x;
@@ -517,16 +517,22 @@ __global__ void __launch_bounds__(HSUM_THREADS) hsum_partials_kernel(const float
     double acc = 0.0;
     if (tid < active && r0 < r1) {
         const float* base = H + r0 * k;
-        const int64_t n = (r1 - r0) * k;
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        const int64_t n = (r1 - r0) * k, step = active;
+        float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         int64_t e = tid;
-        for (; e + 3 * (int64_t)active < n; e += 4 * (int64_t)active) {
-            a0 += __ldg(base + e), a1 += __ldg(base + e + active), a2 += __ldg(base + e + 2 * (int64_t)active);
-            a3 += __ldg(base + e + 3 * (int64_t)active);
-            if (((e / active) & 63) == 60) acc += (double)((a0 + a1) + (a2 + a3)), a0 = a1 = a2 = a3 = 0.f;  // keep fp32 runs short
+        int rounds = 0;
+        for (; e + 7 * step < n; e += 8 * step) {  // eight independent loads in flight per thread
+#pragma unroll
+            for (int z = 0; z < 8; ++z) a[z] += __ldg(base + e + z * step);
+            if (++rounds == 16) {  // keep the fp32 runs short
+                acc += (double)(((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7])));
+#pragma unroll
+                for (int z = 0; z < 8; ++z) a[z] = 0.f;
+                rounds = 0;
+            }
         }
-        for (; e < n; e += active) a0 += __ldg(base + e);
-        acc += (double)((a0 + a1) + (a2 + a3));
+        for (; e < n; e += step) a[0] += __ldg(base + e);
+        acc += (double)(((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7])));
     }
     s_acc[tid] = acc;
     __syncthreads();
@@ -592,6 +598,8 @@ int launch_tc(sal_ctx* c, const PassArgs& a, cudaStream_t st) {
 #define SAL_TC(R_, KL_, HS_)                                                                               \
     (gk ? (wt ? launch_tc_v<KP8, R_, KL_, true, HS_, true>(c, a, st) : launch_tc_v<KP8, R_, KL_, true, HS_, false>(c, a, st)) \
         : (wt ? launch_tc_v<KP8, R_, KL_, false, HS_, true>(c, a, st) : launch_tc_v<KP8, R_, KL_, false, HS_, false>(c, a, st)))
+    if (a.h_scale && (a.flags & SAL_PASS_SCALED_UPDATE))  // the trial's objective + the next H step from the rescaled exposures
+        return gk ? launch_tc_v<KP8, true, true, true, true, false>(c, a, st) : launch_tc_v<KP8, true, true, false, true, false>(c, a, st);
     if (a.h_scale) return gk ? launch_tc_v<KP8, false, true, true, true, false>(c, a, st) : launch_tc_v<KP8, false, true, false, true, false>(c, a, st);
     if (r && !kl) return SAL_TC(true, false, false);
     if (!r && kl) return SAL_TC(false, true, false);
@@ -602,12 +610,12 @@ int launch_tc(sal_ctx* c, const PassArgs& a, cudaStream_t st) {
 }  // namespace
 
 bool sal_pass_tf32_supported(const sal_ctx* c, const PassArgs& a) {
-    const int allowed = SAL_PASS_UPDATE_H | SAL_PASS_WNUM | SAL_PASS_OBJECTIVE | SAL_PASS_HSUM;
+    const int allowed = SAL_PASS_UPDATE_H | SAL_PASS_WNUM | SAL_PASS_OBJECTIVE | SAL_PASS_HSUM | SAL_PASS_SCALED_UPDATE;
     if (c->dtype != SAL_F32 || c->V != VT || c->k > 32) return false;
     if (a.flags & ~allowed) return false;
     if ((a.w_kl || a.w_lhalf) && (a.h_scale || (a.flags & SAL_PASS_HSUM))) return false;  // weights are a KLNMF feature
     if ((a.flags & SAL_PASS_HSUM) && !(a.flags & ~SAL_PASS_HSUM)) return false;  // row sums alone: not worth this kernel
-    if (a.h_scale && a.flags != (SAL_PASS_UPDATE_H | SAL_PASS_OBJECTIVE)) return false;  // the MvNMF trial pass only
+    if (a.h_scale && (a.flags & ~SAL_PASS_SCALED_UPDATE) != (SAL_PASS_UPDATE_H | SAL_PASS_OBJECTIVE)) return false;  // the MvNMF trial pass only
     if (((uintptr_t)a.X | (uintptr_t)a.H_in | (uintptr_t)a.H_out) & 15) return false;
     if (c->D >= (int64_t)1 << 31) return false;
     if (c->math != SAL_MATH_TF32_ALWAYS && c->D < SAL_TF32_MIN_SAMPLES) return false;

@@ -20,7 +20,7 @@ import numpy as np
 import torch
 
 from .. import _dist
-from .._device import PASS_HSUM, PASS_OBJECTIVE, PASS_UPDATE_H, PASS_WNUM
+from .._device import PASS_HSUM, PASS_OBJECTIVE, PASS_SCALED_UPDATE, PASS_UPDATE_H, PASS_WNUM
 from .standard_nmf import StandardNMF
 
 
@@ -42,6 +42,8 @@ class MvNMF(StandardNMF):
         self.delta = delta
         self._gamma = 1.0
         self.use_small_kernel = True  # problems that fit one SM: whole iterations in a persistent single-CTA kernel
+        self.run_ahead = True         # larger problems: optimistic line search, the host runs ahead of the GPU
+        self.fuse_h_step = True       # ... and the next iteration's H step rides on the line-search trial's pass: 2 passes per iteration
 
     @property
     def objective(self) -> Literal["minimize", "maximize"]:
@@ -52,6 +54,7 @@ class MvNMF(StandardNMF):
         st.weights["kl"] = None
         st.weights["lhalf"] = None
         st.W_unc = torch.empty_like(st.W)
+        st.W_unc_spare = torch.empty_like(st.W)  # run-ahead driver: the previous iteration's W_unconstrained stays intact
         st.W_trial = torch.empty_like(st.W)
         st.H_trial = torch.empty_like(st.H)
         st.h_scale = torch.empty(st.k, dtype=st.dtype, device=st.device)
@@ -72,25 +75,34 @@ class MvNMF(StandardNMF):
         with self._resident() as st:
             st.ws.klnmf_pass(st.X, st.W, st.H, PASS_UPDATE_H, H_out=st.H)
 
-    def _update_W_unconstrained(self, n_given_signatures: int = 0) -> None:
-        """Leaves W_unconstrained in ``st.W_unc`` and the previous objective parts in kl2[0], ld2[0]."""
+    def _update_W_unconstrained(self, n_given_signatures: int = 0, logdet_known: bool = False) -> None:
+        """Leaves W_unconstrained in ``st.W_unc`` and the previous objective parts in kl2[0], ld2[0].  ``logdet_known``: W is the
+        candidate the last line-search trial accepted, whose log-determinant that trial left in ld2[1] (same kernel
+        arithmetic on the same numbers): copied instead of recomputed."""
         st = self._dev
         st.ws.klnmf_pass(
             st.X, st.W, st.H, PASS_WNUM | PASS_HSUM | PASS_OBJECTIVE, Wnum=st.Wnum, hsum=st.hsum, objective=st.kl2[0:1]
         )
         st.allreduce(st.Wnum)
         st.allreduce(st.hsum)
-        st.ws.mvnmf_logdet(st.W, self.delta, st.ld2[0:1])
+        if logdet_known:
+            st.ld2[0:1].copy_(st.ld2[1:2])
+        else:
+            st.ws.mvnmf_logdet(st.W, self.delta, st.ld2[0:1])
         st.ws.mvnmf_w_unconstrained(st.W, st.Wnum, st.hsum, self.lam, self.delta, n_given_signatures, st.W_unc)
 
-    def _trial(self, gamma_blend: float) -> float:
+    def _trial(self, gamma_blend: float, fuse_h_step: bool = False) -> float:
+        """One line-search candidate: W_trial, the rescaled exposures and the candidate's objective parts (kl2[1], ld2[1]).
+        ``fuse_h_step``: the pass also applies the NEXT iteration's H step to the rescaled exposures (it has W_trial, the
+        rescaled exposures and the quotient in hand: SAL_PASS_SCALED_UPDATE) -- H_trial then holds update_H's result and the
+        next iteration starts at its W step."""
         st = self._dev
         st.ws.mvnmf_trial(st.W, st.W_unc, gamma_blend, self.delta, st.W_trial, st.h_scale, st.ld2[1:2])
         st.ws.klnmf_pass(
             st.X,
             st.W_trial,
             st.H,
-            PASS_OBJECTIVE | PASS_UPDATE_H,
+            PASS_OBJECTIVE | PASS_UPDATE_H | (PASS_SCALED_UPDATE if fuse_h_step else 0),
             H_out=st.H_trial,
             h_scale=st.h_scale,
             objective=st.kl2[1:2],
@@ -128,12 +140,105 @@ class MvNMF(StandardNMF):
             self._update_H()
             self._update_W(self._n_given(given_parameters))
 
-    # ---- device-side fit driver for problems that fit one SM (BASELINE config 1) ---------------------
+    # ---- fit drivers -------------------------------------------------------------------------------------
     def _fit_loop(self, given_parameters, verbose, verbosity_freq):
         st = self._dev
+        n_given = self._n_given(given_parameters)
         if self.use_small_kernel and st.world == 1 and not st.ws.timing and st.ws.mvnmf_small_supported():
-            return self._fit_loop_small(self._n_given(given_parameters), verbose, verbosity_freq)
+            return self._fit_loop_small(n_given, verbose, verbosity_freq)
+        if self.run_ahead and n_given < self.n_signatures and not st.ws.timing:
+            return self._fit_loop_run_ahead(n_given, verbose, verbosity_freq)
         return super()._fit_loop(given_parameters, verbose, verbosity_freq)
+
+    # -- optimistic line search: the host never waits for the iteration it has just launched ---------------
+    # _first_trial launches the full step (reference mvnmf.py:80-88) and adopts the candidate without looking at the objective;
+    # the four numbers the decision needs travel to a pinned slot behind it, and _confirm checks them later.
+    def _first_trial(self, ring, fused: bool) -> dict:
+        st = self._dev
+        self._trial(-1.0, fused)
+        st.allreduce(st.kl2)
+        slot = ring["next"] % len(ring["events"])
+        ring["next"] += 1
+        ring["host"][slot].copy_(torch.cat([st.kl2, st.ld2]), non_blocking=True)
+        ring["events"][slot].record()
+        rec = {"slot": slot, "W": st.W, "W_trial": st.W_trial, "H": st.H, "H_trial": st.H_trial, "W_unc": st.W_unc,
+               "W_unc_spare": st.W_unc_spare, "gamma": self._gamma, "fused": fused}
+        # adopt the candidate; the next iteration must not overwrite this iteration's W_unconstrained (a back-track needs it)
+        st.W, st.W_trial = st.W_trial, st.W
+        st.H, st.H_trial = st.H_trial, st.H
+        st.W_unc, st.W_unc_spare = st.W_unc_spare, st.W_unc
+        self._gamma = min(1.0, 1.2 * self._gamma)
+        return rec
+
+    def _confirm(self, rec, ring) -> bool:
+        """Was the optimistic iteration's full step accepted?  If not: drop whatever was launched on top of it, restore the
+        iteration's buffers (nothing that a back-track reads has been overwritten: the driver runs at most the H step and the
+        unconstrained W step of the NEXT iteration ahead, which touch neither the kept exposures, the previous W nor the kept
+        W_unconstrained) and run the reference's back-tracking loop.  Returns False when it had to do that."""
+        st = self._dev
+        ring["events"][rec["slot"]].synchronize()
+        kl_prev, kl_new, ld_prev, ld_new = ring["host"][rec["slot"]].tolist()
+        prev_of_value = kl_prev + self.lam * ld_prev
+        of_value = kl_new + self.lam * ld_new
+        if not of_value > prev_of_value:
+            return True
+        torch.cuda.current_stream(st.device).synchronize()
+        st.W, st.W_trial, st.H, st.H_trial = rec["W"], rec["W_trial"], rec["H"], rec["H_trial"]
+        st.W_unc, st.W_unc_spare = rec["W_unc"], rec["W_unc_spare"]
+        gamma = rec["gamma"]
+        while of_value > prev_of_value and gamma > 1e-16:
+            gamma *= 0.8
+            self._trial(gamma, rec["fused"])
+            st.allreduce(st.kl2[1:2])
+            kl_new, ld_new = torch.stack([st.kl2[1], st.ld2[1]]).tolist()
+            of_value = kl_new + self.lam * ld_new
+        self._gamma = min(1.0, 1.2 * gamma)
+        st.W, st.W_trial = st.W_trial, st.W
+        st.H, st.H_trial = st.H_trial, st.H
+        self.launch_stats["back_tracked_iterations"] += 1
+        return False
+
+    def _fit_loop_run_ahead(self, n_given: int, verbose, verbosity_freq):
+        """The reference loop (signature_nmf.py:361-380 around mvnmf.py:197-210) without a host round trip per iteration.
+        The reference looks at the objective after the first line-search trial to decide whether to back-track
+        (mvnmf.py:69-92); here the H step and the unconstrained W step of iteration n + 1 are already queued behind iteration
+        n when the host reads n's decision -- by then it has long arrived -- and only a rejected full step (rare: gamma adapts)
+        costs a synchronisation and the two wasted passes.  Same iterates, objective history and gamma as the reference."""
+        st = self._dev
+        ring = {"host": torch.zeros((4, 4), dtype=torch.float64).pin_memory(), "events": [torch.cuda.Event() for _ in range(4)], "next": 0}
+        self.launch_stats = {"graphs": 0, "driver": "run-ahead line search", "back_tracked_iterations": 0}
+        of_values = [self.objective_function()]
+        n_iteration, converged, pending = 0, False, None
+        h_step_done = False    # the accepted trial already applied this iteration's H step (fused pass)
+        logdet_known = False   # ld2[1] holds ln det of the current W (left there by the trial that produced it)
+        freq, max_it = int(self.conv_test_freq), int(self.max_iterations)
+        while not converged:
+            n_iteration += 1
+            if verbose and n_iteration % verbosity_freq == 0:
+                print(f"iteration: {n_iteration}; objective: {of_values[-1]:.2f}")
+            if not h_step_done:
+                self._update_H()
+            self._update_W_unconstrained(n_given, logdet_known)
+            if pending is not None and not self._confirm(pending, ring):
+                # iteration n - 1 had to back-track: what was just queued started from the wrong iterate
+                if not pending["fused"]:
+                    self._update_H()
+                self._update_W_unconstrained(n_given, True)
+            # the H step of iteration n + 1 rides on this iteration's trial pass -- unless the iterate itself is needed next:
+            # for the objective of the convergence test or as the final state
+            fused = bool(self.fuse_h_step) and n_iteration % freq != 0 and n_iteration < max_it
+            pending = self._first_trial(ring, fused)
+            h_step_done, logdet_known = fused, True
+            if n_iteration % freq == 0 or n_iteration >= max_it:
+                self._confirm(pending, ring)  # the objective below (and the final state) need the true iterate
+                pending = None
+            if n_iteration % freq == 0:
+                prev = of_values[-1]
+                of_values.append(self.objective_function())
+                rel_change = np.abs(prev - of_values[-1]) / np.abs(prev)
+                converged = bool(rel_change < self.tol and n_iteration >= self.min_iterations)
+            converged |= n_iteration >= max_it
+        return of_values, n_iteration
 
     def _fit_loop_small(self, n_given: int, verbose, verbosity_freq):
         """One launch of the persistent single-CTA kernel (sal_mvnmf_small_updates) per convergence-test period: the penalised

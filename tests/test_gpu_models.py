@@ -174,8 +174,12 @@ def test_klnmf_trajectory(tag, dtype):
     assert model.signatures.shape == (96, kk) and model.exposures.shape == (192, kk)
 
 
+@pytest.mark.parametrize("driver", ["single-CTA persistent kernel", "run-ahead line search", "host loop"])
 @pytest.mark.parametrize("tag", ["mvnmf_pcawg_k10_seed0", "mvnmf_pcawg_k3_lam50"])
-def test_mvnmf_trajectory(tag, dtype):
+def test_mvnmf_trajectory(tag, dtype, driver):
+    """Every fit driver of MvNMF against the live-reference trajectory: the persistent single-CTA kernel (small problems), the
+    run-ahead driver of the larger ones (optimistic line search + roll-back when the full step is rejected) and the plain
+    reference loop with a host decision per trial."""
     z = np.load(os.path.join(TRAJ, f"{tag}.npz"))
     model = sal.models.MvNMF(
         n_signatures=int(z["k"]),
@@ -186,7 +190,11 @@ def test_mvnmf_trajectory(tag, dtype):
         max_iterations=_ctor(z, "max_iterations", 10000),
         dtype=dtype,
     )
+    model.use_small_kernel = driver == "single-CTA persistent kernel"
+    model.run_ahead = driver == "run-ahead line search"
     model.fit(pcawg_adata(), init_kwargs={"seed": int(z["seed"])})
+    if driver != "host loop":
+        assert model.launch_stats["driver"] == driver, model.launch_stats
     hist = np.array(model.history["objective_function"])
     ref = z["history"]
     if dtype == "float64":
@@ -196,6 +204,30 @@ def test_mvnmf_trajectory(tag, dtype):
     else:
         assert abs(hist[-1] - ref[-1]) / abs(ref[-1]) < 1e-4
         assert _cosine(model.asignatures.X, z["W"]).min() >= 0.9999
+
+
+@pytest.mark.parametrize("k,lam,delta,seed", [(3, 1e4, 0.1, 3), (6, 1e4, 1e-3, 0)])
+def test_mvnmf_run_ahead_rolls_back_rejected_steps(k, lam, delta, seed):
+    """A strongly penalised problem in which about every second iteration rejects the full step: the run-ahead driver has to
+    drop what it queued on top of the optimistic iterate, restore the buffers and back-track like the reference
+    (mvnmf.py:69-92).  Objective history, gamma and the final factors against the oracle."""
+    from oracle import EPSILON
+    from oracle import mvnmf as omv
+    from salamander_b200.initialization.initialize import initialize_mat
+
+    adata = pcawg_adata()
+    Xp = np.asarray(adata.X, dtype=float).clip(EPSILON)
+    W0, H0 = initialize_mat(Xp, k, "random", seed=seed)
+    W, H, gamma, n, hist = omv.fit_mvnmf(Xp.T, W0.T, H0.T, lam=lam, delta=delta, min_iterations=60, max_iterations=60)
+    assert gamma < 1.0  # the oracle did back-track
+    model = sal.models.MvNMF(n_signatures=k, init_method="random", lam=lam, delta=delta, min_iterations=60, max_iterations=60, dtype="float64")
+    model.use_small_kernel = False
+    model.fit(adata, init_kwargs={"seed": seed})
+    assert model.launch_stats["driver"] == "run-ahead line search" and model.launch_stats["back_tracked_iterations"] >= 10
+    assert np.allclose(model.history["objective_function"], hist, rtol=1e-9, atol=0)
+    assert np.isclose(model._gamma, gamma, rtol=1e-12)
+    assert np.allclose(model.asignatures.X, W.T, rtol=1e-6, atol=1e-12)
+    assert np.allclose(model.adata.obsm["exposures"], H.T, rtol=1e-6, atol=1e-10)
 
 
 def test_reconstruction_error(dtype):

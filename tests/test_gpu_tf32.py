@@ -237,11 +237,30 @@ def test_mvnmf_pass_variants(D, k):
     Hout = torch.full_like(Hf, -1.0)
     ws.klnmf_pass(Xf, Wf, Hf, PASS_OBJECTIVE | PASS_UPDATE_H, H_out=Hout, h_scale=scale.float(), objective=obj)
     torch.cuda.synchronize()
-    ws.close()
     Rs = X / (Hs @ W)
     kl_s = float((X * torch.log(Rs) - X + Hs @ W).sum())
     assert _relerr(Hout.double(), Hs) < 1e-6
     assert abs(float(obj.item()) - kl_s) / abs(kl_s) < 2e-5
+    # the same trial with the NEXT H step fused in (SAL_PASS_SCALED_UPDATE): objective of the rescaled exposures, output = their
+    # multiplicative update
+    from salamander_b200._device import PASS_SCALED_UPDATE
+
+    Hnext = torch.full_like(Hf, -1.0)
+    ws.klnmf_pass(Xf, Wf, Hf, PASS_OBJECTIVE | PASS_UPDATE_H | PASS_SCALED_UPDATE, H_out=Hnext, h_scale=scale.float(), objective=obj)
+    torch.cuda.synchronize()
+    assert abs(float(obj.item()) - kl_s) / abs(kl_s) < 2e-5
+    assert _relerr(Hnext.double(), (Hs * (Rs @ W.T)).clamp_min(EPS)) < RTOL
+    # ... and on the exact kernels in float64: bit-identical to the two separate passes
+    ws64 = Workspace(96, D, k, torch.float64, dev)
+    Hs64, Hn_two, Hn_one = torch.empty_like(H), torch.empty_like(H), torch.empty_like(H)
+    o1, o2 = torch.zeros(1, dtype=torch.float64, device=dev), torch.zeros(1, dtype=torch.float64, device=dev)
+    ws64.klnmf_pass(X, W, H, PASS_OBJECTIVE | PASS_UPDATE_H, H_out=Hs64, h_scale=scale, objective=o1)
+    ws64.klnmf_pass(X, W, Hs64, PASS_UPDATE_H, H_out=Hn_two)
+    ws64.klnmf_pass(X, W, H, PASS_OBJECTIVE | PASS_UPDATE_H | PASS_SCALED_UPDATE, H_out=Hn_one, h_scale=scale, objective=o2)
+    torch.cuda.synchronize()
+    assert torch.equal(Hn_one, Hn_two) and float(o1.item()) == float(o2.item())
+    ws64.close()
+    ws.close()
 
 
 def test_mvnmf_fit_on_tensor_cores_tracks_float64():
