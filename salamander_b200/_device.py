@@ -116,6 +116,14 @@ class Workspace:
             raise ValueError(f"'{name}' has to be a contiguous {want} tensor with {numel} elements.")
         return C.c_void_p(t.data_ptr())
 
+    def _objectives_ptr(self, t: torch.Tensor):
+        """The objectives of the period kernel may be written straight into PAGE-LOCKED host memory (unified addressing: the
+        kernel's few 8-byte stores travel over PCIe and are visible once the launch has completed), which saves the
+        device-to-host copy behind every launch; a device tensor is accepted as well."""
+        if isinstance(t, torch.Tensor) and t.device.type == "cpu" and t.is_pinned() and t.dtype == torch.float64 and t.is_contiguous():
+            return C.c_void_p(t.data_ptr())
+        return self._ptr(t, t.numel(), "objectives", torch.float64)
+
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
@@ -228,7 +236,7 @@ class Workspace:
                 int(n_updates),
                 int(objective_every),
                 int(bool(final_objective)),
-                None if objectives is None else self._ptr(objectives, objectives.numel(), "objectives", torch.float64),
+                None if objectives is None else self._objectives_ptr(objectives),
                 None if peers is None else self._ptr(peers, n_ranks, "peers", torch.int64),
                 None if state is None else self._ptr(state, 2, "state", torch.int32),
                 int(n_ranks),

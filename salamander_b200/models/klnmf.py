@@ -68,6 +68,7 @@ class KLNMF(StandardNMF):
         self.use_period_kernel = True
         self.loop_start_event = None  # optional torch.cuda.Event the period driver records right before its first launch
         self.loop_end_event = None    # ... and right behind the last planned launch and the copy of its objectives to the host
+        self.objectives_to_host = True  # period kernel: objectives stored straight into page-locked host memory
         self.use_small_kernel = True  # problems that fit one SM: persistent single-CTA kernel (see _fit_loop_small)
         # multi-GPU all-reduce of the numerator: "auto" / "p2p" = one-shot NVLink exchange fused into the reduction
         # kernel (sal_klnmf_update_p2p), "nccl" = library collective between separate kernels
@@ -289,12 +290,15 @@ class KLNMF(StandardNMF):
                 slot, nxt = n_launched % ring, (cur + 1) % 3
                 if n_launched == 0 and self.loop_start_event is not None:
                     self.loop_start_event.record()  # measurement aid: device time from the driver's first launch on
+                # (the kernel writes its objectives straight into the page-locked ring: no copy behind the launch)
                 st.ws.klnmf_period(
-                    st.X, Ws[cur], Ws[nxt], Hs[cur], Hs[nxt], n_given, True, n1 - n0, freq, fin, objectives=obj_dev[slot],
+                    st.X, Ws[cur], Ws[nxt], Hs[cur], Hs[nxt], n_given, True, n1 - n0, freq, fin,
+                    objectives=obj_host[slot] if self.objectives_to_host else obj_dev[slot],
                     peers=None if px is None else px.peers, state=None if px is None else px.state,
                     n_ranks=st.world if px is not None else 1, rank=st.rank if px is not None else 0,
                 )
-                obj_host[slot].copy_(obj_dev[slot], non_blocking=True)
+                if not self.objectives_to_host:
+                    obj_host[slot].copy_(obj_dev[slot], non_blocking=True)
                 events[slot].record()
                 if nxt_launch + 1 == len(plan) and self.loop_end_event is not None:
                     self.loop_end_event.record()  # measurement aid: everything the loop asked of the device has been enqueued
