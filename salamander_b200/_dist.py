@@ -147,10 +147,13 @@ def next_launch_id(px: PeerExchange) -> int:
     starts over -- every rank gets here at the same launch."""
     px.launch_id += 1
     if px.launch_id >= LAUNCH_ID_LIMIT:
-        torch.cuda.synchronize()
-        dist.barrier()
+        on_gpu = px.buf.is_cuda
+        if on_gpu:
+            torch.cuda.synchronize(px.buf.device)  # every kernel that reads or writes the buffers has finished here ...
+        dist.barrier()                             # ... and on every peer
         px.buf.zero_()
-        torch.cuda.synchronize()
+        if on_gpu:
+            torch.cuda.synchronize(px.buf.device)
         dist.barrier()
         px.launch_id = 1
     return px.launch_id

@@ -128,6 +128,14 @@ assert torch.equal(norms, torch.tensor([7.0, 3.0, 30.0], dtype=torch.float64)), 
 assert _dist.all_ranks_agree(True, torch.device("cpu")) is True
 assert _dist.all_ranks_agree(rank == 0, torch.device("cpu")) is False
 assert _dist.all_ranks_agree(False, torch.device("cpu")) is False
+# launch numbers of the CorrNMF signature solver's exchange: the same on both ranks, and before the 15-bit tag prefix would
+# repeat the receive buffers are zeroed behind a barrier and the count starts over
+class _FakeExchange:
+    buf = torch.ones(8, dtype=torch.int32)
+    launch_id = _dist.LAUNCH_ID_LIMIT - 3
+ids = [_dist.next_launch_id(_FakeExchange) for _ in range(4)]
+assert ids == [_dist.LAUNCH_ID_LIMIT - 2, _dist.LAUNCH_ID_LIMIT - 1, 1, 2], ids
+assert int(_FakeExchange.buf.abs().sum()) == 0
 # the period driver's launch plan is a pure function of (min, max, freq): both ranks issue the same launches
 from salamander_b200.models.klnmf import period_launch_plan
 plan = period_launch_plan(min_iterations=35, max_iterations=100, freq=10, per_launch=16)
