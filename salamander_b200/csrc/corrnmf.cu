@@ -42,16 +42,34 @@ struct SampleProblem {
         const int m = M > 0 ? M : m_rt;
         double acc = 0.0, nrm = 0.0;
         _Pragma("unroll") for (int j = 0; j < m * m; ++j) A[j] = 0.0;
-        _Pragma("unroll") for (int j = 0; j < m; ++j) g[j] = x[j] * inv_var, nrm += x[j] * x[j], A[j * m + j] = inv_var;
-        for (int i = 0; i < k; ++i) {
-            double sp = 0.0;
-            _Pragma("unroll") for (int j = 0; j < m; ++j) sp += others[i * m + j] * x[j];
-            const double e = exp(s_vec[i] + s_others[i] + sp);
+        _Pragma("unroll") for (int j = 0; j < m; ++j) g[j] = x[j] * inv_var, nrm += x[j] * x[j];
+        // one term: only the upper triangle of the (symmetric) Hessian is accumulated, mirrored at the end
+        auto term = [&](int i, double sp, double e) {
             acc += sp * aux[i] - e;
             const double w = e - aux[i];
             _Pragma("unroll") for (int j = 0; j < m; ++j) g[j] += w * others[i * m + j];
-            _Pragma("unroll") for (int p = 0; p < m; ++p)
-                _Pragma("unroll") for (int q = 0; q < m; ++q) A[p * m + q] += e * others[i * m + p] * others[i * m + q];
+            _Pragma("unroll") for (int p = 0; p < m; ++p) {
+                const double eo = e * others[i * m + p];
+                _Pragma("unroll") for (int q = p; q < m; ++q) A[p * m + q] += eo * others[i * m + q];
+            }
+        };
+        // two "others" per trip: their exp() chains are independent (one Newton-CG per THREAD: the only parallelism a thread has)
+        int i = 0;
+        for (; i + 1 < k; i += 2) {
+            double sp0 = 0.0, sp1 = 0.0;
+            _Pragma("unroll") for (int j = 0; j < m; ++j) sp0 += others[i * m + j] * x[j], sp1 += others[(i + 1) * m + j] * x[j];
+            const double e0 = exp(s_vec[i] + s_others[i] + sp0), e1 = exp(s_vec[i + 1] + s_others[i + 1] + sp1);
+            term(i, sp0, e0);
+            term(i + 1, sp1, e1);
+        }
+        if (i < k) {
+            double sp = 0.0;
+            _Pragma("unroll") for (int j = 0; j < m; ++j) sp += others[i * m + j] * x[j];
+            term(i, sp, exp(s_vec[i] + s_others[i] + sp));
+        }
+        _Pragma("unroll") for (int p = 0; p < m; ++p) {
+            _Pragma("unroll") for (int q = p + 1; q < m; ++q) A[q * m + p] = A[p * m + q];
+            A[p * m + p] += inv_var;
         }
         return -(acc - 0.5 * nrm * inv_var);
     }

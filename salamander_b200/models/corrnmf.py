@@ -42,10 +42,7 @@ class CorrState:
         dev = model._resolved_device()
         dt = model.dtype
         self.rank, self.world = (0, 1) if getattr(model, "replica", False) else _dist.world()
-        if self.world > 1 and not allow_shard:
-            # MultimodalCorrNMF under torchrun: REPLICAS ONLY -- every rank fits the whole (PCAWG-sized) problem on its own GPU
-            # and, started from the same seed, arrives at the same bits; the joint sample embeddings couple all modalities of
-            # a sample, and at a few hundred samples there is nothing for a second GPU to do (multi-GPU)
+        if self.world > 1 and not allow_shard:  # replicas: every rank holds and fits the whole problem
             self.rank, self.world = 0, 1
         model.transfer_bytes = {"h2d": 0, "d2h": 0}
         self.model, self.device, self.dtype = model, dev, dt
@@ -282,27 +279,7 @@ class CorrNMFDet(CorrNMF):
     def update_signature_embeddings(self, aux=None) -> None:
         with self._resident() as st:
             self._aux_to_device(st, aux)
-            if st.world == 1:
-                st.call("sal_corrnmf_signature_embeddings", st.auxT, st.a, st.b, st.L, st.U, st.m, float(self.variance))
-                return
-            px = st.sig_exchange()
-            if px is not None:
-                # every rank: Newton-CG of ALL signatures on ITS samples; the totals of each evaluation are exchanged inside the
-                # kernel over NVLink and summed in rank order, so the ranks' solvers run in lock step and L stays bit-identical
-                st.call(
-                    "sal_corrnmf_signature_embeddings_p2p", st.auxT, st.a, st.b, st.L, st.U, st.m, float(self.variance),
-                    px.peers, st.world, st.rank, _dist.next_launch_id(px),
-                )
-                return
-            # fallback without peer memory -- every rank: all samples' aux / scalings / embeddings, Newton-CG for its share of the
-            # signatures; the rows of L are then exchanged by summing arrays that are zero outside the owner's rows (exact)
-            aux_all, b_all, U_all = (_dist.gather_rows(t, st.D_total) for t in (st.auxT, st.b, st.U))
-            j0, j1 = _dist.shard_bounds(st.k, st.world, st.rank)
-            st.call(
-                "sal_corrnmf_signature_embeddings_range", aux_all, st.a, b_all, st.L, U_all, st.m, float(self.variance),
-                j0, j1 - j0, ws=st.ws_full,
-            )
-            _dist.exchange_owned_rows(st.L, j0, j1)
+            signature_embeddings_update(st, float(self.variance))
 
     def update_sample_embeddings(self, aux=None) -> None:
         with self._resident() as st:
@@ -331,6 +308,32 @@ class CorrNMFDet(CorrNMF):
                 self.update_signatures(given_parameters)
             finally:
                 self._in_fit = in_fit
+
+
+def signature_embeddings_update(st: CorrState, variance: float) -> None:
+    """Newton-CG update of every signature embedding of one (modality's) device state (reference corrnmf_det.py:88-113 /
+    mmcorrnmf.py:337-396), whatever the number of ranks."""
+    if st.world == 1:
+        st.call("sal_corrnmf_signature_embeddings", st.auxT, st.a, st.b, st.L, st.U, st.m, variance)
+        return
+    px = st.sig_exchange()
+    if px is not None:
+        # every rank: Newton-CG of ALL signatures on ITS samples; the totals of each evaluation are exchanged inside the
+        # kernel over NVLink and summed in rank order, so the ranks' solvers run in lock step and L stays bit-identical
+        st.call(
+            "sal_corrnmf_signature_embeddings_p2p", st.auxT, st.a, st.b, st.L, st.U, st.m, variance,
+            px.peers, st.world, st.rank, _dist.next_launch_id(px),
+        )
+        return
+    # fallback without peer memory -- every rank: all samples' aux / scalings / embeddings, Newton-CG for its share of the
+    # signatures; the rows of L are then exchanged by summing arrays that are zero outside the owner's rows (exact)
+    aux_all, b_all, U_all = (_dist.gather_rows(t, st.D_total) for t in (st.auxT, st.b, st.U))
+    j0, j1 = _dist.shard_bounds(st.k, st.world, st.rank)
+    st.call(
+        "sal_corrnmf_signature_embeddings_range", aux_all, st.a, b_all, st.L, U_all, st.m, variance,
+        j0, j1 - j0, ws=st.ws_full,
+    )
+    _dist.exchange_owned_rows(st.L, j0, j1)
 
 
 def _lib_eps() -> float:

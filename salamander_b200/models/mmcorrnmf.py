@@ -22,7 +22,7 @@ from .._device import PASS_NOCLIP, PASS_POISSON, PASS_SAMPLEWISE, PASS_UPDATE_H,
 from ..initialization.initialize import initialize_mmcorrnmf
 from ..initialization.methods import _INIT_METHODS
 from ..utils import EPSILON, type_checker, value_checker
-from .corrnmf import CorrState
+from .corrnmf import CorrState, signature_embeddings_update
 
 
 class _ModView:
@@ -47,11 +47,16 @@ class _MMState:
         for mod_name, k in zip(model.mod_names, model.ns_signatures):
             adata = model.mdata[mod_name]
             adata.obsm["embeddings"] = U_host  # CorrState uploads it; replaced by the shared tensor below
-            st = CorrState(_ModView(model, mod_name, k), allow_shard=False)
+            # several GPUs: samples sharded by contiguous row blocks, identically for every modality; the
+            # per-modality parameters W / a / L and the variance are replicated, b / H / aux and the SHARED sample embeddings
+            # are this rank's rows.  ``model.shard = False`` keeps every rank a replica of the whole problem instead.
+            st = CorrState(_ModView(model, mod_name, k), allow_shard=bool(getattr(model, "shard", True)))
             del adata.obsm["embeddings"]
             self.mods[mod_name] = st
         first = next(iter(self.mods.values()))
-        self.device, self.dtype, self.D, self.m = first.device, first.dtype, first.D, first.m
+        self.device, self.dtype, self.D, self.m = first.device, first.dtype, first.D, first.m  # D: this rank's samples
+        self.D_total, self.world = first.D_total, first.world
+        model.shard_info = {"world": first.world, "rank": first.rank, "local_samples": first.D, "samples": first.D_total}
         self.U = first.U
         for st in self.mods.values():
             st.U = self.U
@@ -158,9 +163,9 @@ class MultimodalCorrNMF:
             asigs.X = st.download(st.W)
             asigs.obs["scalings"] = st.download(st.a)
             asigs.obsm["embeddings"] = st.download(st.L)
-            adata.obs["scalings"] = st.download(st.b)
-            adata.obsm["exposures"] = st.download(st.H)
-        self.mdata.obsm["embeddings"] = next(iter(dev.mods.values())).download(dev.U)
+            adata.obs["scalings"] = st.rows_to_host(st.b)
+            adata.obsm["exposures"] = st.rows_to_host(st.H)
+        self.mdata.obsm["embeddings"] = next(iter(dev.mods.values())).rows_to_host(dev.U)
 
     # ---- numerics (reference :106-115, :168-194, :233-453) ---------------------------------------------
     def compute_exposures(self) -> None:
@@ -174,7 +179,7 @@ class MultimodalCorrNMF:
                 st.call("sal_corrnmf_exposures", st.a, st.b, st.L, st.U, st.m, st.H)
                 out = torch.empty(st.D, dtype=st.dtype, device=st.device)
                 st.ws.klnmf_pass(st.X, st.W, st.H, PASS_SAMPLEWISE, per_sample=out)
-                self.mdata[name].obs["reconstruction_error"] = st.download(out)
+                self.mdata[name].obs["reconstruction_error"] = st.rows_to_host(out)
 
     @property
     def reconstruction_errors(self) -> dict[str, float]:
@@ -193,26 +198,27 @@ class MultimodalCorrNMF:
             elbo, sumU2 = 0.0, 0.0
             for st in dev.mods.values():
                 st.ws.klnmf_pass(st.X, st.W, st.H, PASS_POISSON, objective=st.obj)
+                st.allreduce(st.obj)
                 need = st.lgamma_sum is None
-                st.call("sal_corrnmf_norms", st.L, st.U, st.m, st.X if need else None, st.norms)
-                vals = torch.cat([st.obj, st.norms]).tolist()
+                norms = st.norms_all(need)  # [sum L^2, sum U^2 and sum lnGamma(1 + x) over ALL samples]
                 if need:
-                    st.lgamma_sum = vals[3]
-                elbo += vals[0] - st.lgamma_sum - 0.5 * m * st.k * np.log(2 * np.pi * var) - vals[1] / (2 * var)
-                sumU2 = vals[2]
-            elbo -= 0.5 * m * dev.D * np.log(2 * np.pi * var) + sumU2 / (2 * var)
+                    st.lgamma_sum = norms[2]
+                elbo += float(st.obj.item()) - st.lgamma_sum - 0.5 * m * st.k * np.log(2 * np.pi * var) - norms[0] / (2 * var)
+                sumU2 = norms[1]
+            elbo -= 0.5 * m * dev.D_total * np.log(2 * np.pi * var) + sumU2 / (2 * var)
             return float(elbo)
 
     def _compute_auxs(self):
         with self._resident() as dev:
             for st in dev.mods.values():
                 st.ws.klnmf_pass(st.X, st.W, st.H, PASS_UPDATE_H | PASS_WNUM | PASS_NOCLIP, H_out=st.auxT, Wnum=st.Wnum)
-            return None if self._in_fit else {name: st.download(st.auxT).T for name, st in dev.mods.items()}
+                st.allreduce(st.Wnum)
+            return None if self._in_fit else {name: st.rows_to_host(st.auxT).T for name, st in dev.mods.items()}
 
     @staticmethod
     def _aux_up(st, aux) -> None:
-        if aux is not None:
-            st.auxT = st.upload(np.asarray(aux, dtype=np.float64).T)
+        if aux is not None:  # (k, n_samples) host array over ALL samples, like the reference's
+            st.auxT = st.upload(np.asarray(aux, dtype=np.float64).T[st.lo : st.hi])
 
     def update_sample_scalings(self, given_parameters: dict[str, Any] | None = None) -> None:
         given_parameters = given_parameters or {}
@@ -228,6 +234,7 @@ class MultimodalCorrNMF:
                 self._aux_up(st, None if auxs is None else auxs[name])
                 if "signature_scalings" not in given_parameters.get(name, {}):
                     st.call("sal_corrnmf_signature_scalings_sums", st.auxT, st.b, st.L, st.U, st.m, st.sums)
+                    st.allreduce(st.sums)
                     st.call("sal_corrnmf_signature_scalings_finish", st.sums, st.a)
 
     def update_variance(self, given_parameters: dict[str, Any] | None = None) -> None:
@@ -236,12 +243,11 @@ class MultimodalCorrNMF:
         with self._resident() as dev:
             total, count = 0.0, 0
             for st in dev.mods.values():
-                st.call("sal_corrnmf_norms", st.L, st.U, st.m, None, st.norms)
-                sumL2, sumU2 = st.norms[:2].tolist()
+                sumL2, sumU2 = st.norms_all(False)[:2]
                 total += sumL2
                 count += st.k * st.m
             total += sumU2
-            count += dev.D * dev.m
+            count += dev.D_total * dev.m
             self.variance = float(np.clip(total / count, EPSILON, None))
 
     def update_signatures(self, given_parameters: dict[str, Any] | None = None) -> None:
@@ -252,6 +258,7 @@ class MultimodalCorrNMF:
                 n_given = gm["asignatures"].n_obs if "asignatures" in gm else 0
                 if not self._in_fit:
                     st.ws.klnmf_pass(st.X, st.W, st.H, PASS_WNUM, Wnum=st.Wnum)
+                    st.allreduce(st.Wnum)
                 st.ws.w_epilogue(st.W, st.Wnum, n_given, False, st.W)
 
     def update_signature_embeddings(self, auxs=None, given_parameters: dict[str, Any] | None = None) -> None:
@@ -260,7 +267,7 @@ class MultimodalCorrNMF:
             for name, st in dev.mods.items():
                 self._aux_up(st, None if auxs is None else auxs[name])
                 if "signature_embeddings" not in given_parameters.get(name, {}):
-                    st.call("sal_corrnmf_signature_embeddings", st.auxT, st.a, st.b, st.L, st.U, st.m, float(self.variance))
+                    signature_embeddings_update(st, float(self.variance))
 
     def update_sample_embeddings(self, auxs=None) -> None:
         with self._resident() as dev:

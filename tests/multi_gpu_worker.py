@@ -90,6 +90,28 @@ Lref = Lc.clone()
 dist.broadcast(Lref, src=0)
 assert torch.equal(Lc, Lref)  # replicated parameters are bit-identical on all ranks
 
+# MultimodalCorrNMF, samples sharded (every modality alike, shared sample embeddings local): whole fit against the
+# live-reference trajectory of the three PCAWG modalities
+from salamander_b200 import MuData  # noqa: E402
+
+z = np.load(os.path.join(ROOT, "tests", "golden", "trajectories", "mmcorrnmf_pcawg_ns322_dim2_seed5.npz"))
+ns, dim, seed, n_it = [int(v) for v in z["ns"]], int(z["dim"]), int(z["seed"]), int(z["n_iter"])
+data_dir = os.path.join(ROOT, "salamander_b200", "data")
+frames = {name: pd.read_csv(os.path.join(data_dir, f"pcawg_breast_{name}.csv"), index_col=0).T.astype(float).clip(lower=1.1920928955078125e-07)
+          for name in ("sbs", "indel", "sv")}
+mm = sal.models.MultimodalCorrNMF(ns_signatures=ns, dim_embeddings=dim, init_method="random", min_iterations=n_it, max_iterations=n_it,
+                                  conv_test_freq=1, device=f"cuda:{local}")
+np.random.seed(seed)
+mm.fit(MuData({name: AnnData(df) for name, df in frames.items()}), init_kwargs={"seed": seed})
+assert mm.shard_info["world"] == world and mm.shard_info["local_samples"] < mm.shard_info["samples"], mm.shard_info
+assert np.allclose(mm.history["objective_function"], z["history"], rtol=1e-8, atol=0), (mm.history["objective_function"], z["history"])
+for name in ("sbs", "indel", "sv"):
+    assert np.allclose(mm.asignatures[name].X, z[f"{name}_W"], rtol=1e-6, atol=1e-12), name
+    assert np.allclose(mm.asignatures[name].obsm["embeddings"], z[f"{name}_L"], rtol=1e-5, atol=1e-8), name
+    assert np.allclose(mm.mdata[name].obs["scalings"].values, z[f"{name}_b"], rtol=1e-6), name
+assert np.allclose(mm.mdata.obsm["embeddings"], z["U"], rtol=1e-5, atol=1e-7)
+assert np.isclose(mm.variance, float(z["var"]), rtol=1e-7)
+
 # replicas stay bit-identical
 W = torch.as_tensor(model.asignatures.X).cuda()
 ref = W.clone()
