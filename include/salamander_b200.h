@@ -298,6 +298,18 @@ int sal_corrnmf_signature_embeddings_emulated(const sal_handle_t* hs, int n_virt
                                               const void* const* a, const void* const* b, void* const* L,
                                               const void* const* U, int m, double variance,
                                               const void* const* peer_tables, unsigned int launch_id, void* stream);
+/* The few-KB sums of a sample-sharded iteration (W numerator, scaling sums, norms, likelihood: the places where the
+ * reference sums over ALL samples, e.g. corrnmf_det.py:39-86) summed over the ranks through peer memory instead of a
+ * library collective: values[0 .. n) (n <= sal_p2p_allreduce_max_values()) are replaced in place by the sum over ranks, added
+ * in rank order (bit-identical everywhere).  peers = device array [n_ranks] of receive buffers of
+ * sal_p2p_allreduce_bytes(n_ranks) bytes, zeroed once; launch_id as for sal_corrnmf_signature_embeddings_p2p (own counter
+ * per set of buffers).  _emulated: two ranks on one device in one launch (tests). */
+size_t sal_p2p_allreduce_bytes(int n_ranks);
+int sal_p2p_allreduce_max_values(void);
+int sal_p2p_allreduce_f64(sal_handle_t h, double* values, int n, const void* peers, int n_ranks, int rank,
+                          unsigned int launch_id, void* stream);
+int sal_p2p_allreduce_f64_emulated(sal_handle_t h, double* const* values, int n, const void* const* peer_tables,
+                                   int n_virtual, unsigned int launch_id, void* stream);
 /* out[0] = sum L^2, out[1] = sum U^2 (update_variance corrnmf_det.py:60-69, ELBO priors _utils_corrnmf.py:93-98),
  * out[2] = sum lnGamma(1 + X) when X != NULL (constant of poisson_llh, _utils_klnmf.py:159) */
 int sal_corrnmf_norms(sal_handle_t h, const void* L, const void* U, int m, const void* X_or_null, double* out,

@@ -63,6 +63,10 @@ SYMBOLS = {
     "sal_corrnmf_signature_embeddings": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _d, _vp]),
     "sal_corrnmf_signature_embeddings_range": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _d, _i, _i, _vp]),
     "sal_corrnmf_sig_exchange_bytes": (C.c_size_t, [_i, _i]),
+    "sal_p2p_allreduce_bytes": (C.c_size_t, [_i]),
+    "sal_p2p_allreduce_max_values": (_i, []),
+    "sal_p2p_allreduce_f64": (_i, [_vp, _vp, _i, _vp, _i, _i, C.c_uint, _vp]),
+    "sal_p2p_allreduce_f64_emulated": (_i, [_vp, _vp, _i, _vp, _i, C.c_uint, _vp]),
     "sal_corrnmf_signature_embeddings_p2p": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _d, _vp, _i, _i, C.c_uint, _vp]),
     "sal_corrnmf_signature_embeddings_emulated": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _d, _vp, C.c_uint, _vp]),
     "sal_corrnmf_norms": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp]),

@@ -567,6 +567,30 @@ int sal_corrnmf_signature_embeddings_emulated(const sal_handle_t* hs, int n_virt
     return sal_launch_corrnmf_signature_embeddings_v(rs, n_virtual, m, variance, 0, h->k, n_virtual, launch_id, (cudaStream_t)stream);
 }
 
+size_t sal_p2p_allreduce_bytes(int n_ranks) { return sal_p2p_allreduce_words(n_ranks) * 16; }
+int sal_p2p_allreduce_max_values(void) { return sal_p2p_allreduce_max(); }
+
+int sal_p2p_allreduce_f64(sal_handle_t h, double* values, int n, const void* peers, int n_ranks, int rank, unsigned int launch_id,
+                          void* stream) {
+    SAL_CHECK_ARG(h != nullptr, "handle is null");
+    SAL_CHECK_ARG(values && peers && n >= 0, "null argument");
+    SAL_CHECK_ARG(n_ranks >= 2 && n_ranks <= 8 && rank >= 0 && rank < n_ranks, "2 .. 8 ranks, 0 <= rank < n_ranks");
+    SAL_CHECK_ARG(launch_id >= 1 && launch_id < (1u << 15), "launch_id must be in 1 .. 32767 (zero the receive buffers and start over)");
+    SAL_CUDA(cudaSetDevice(h->device));
+    h->launches++;
+    return sal_launch_p2p_allreduce(1, &values, &peers, &rank, n, n_ranks, launch_id, (cudaStream_t)stream);
+}
+
+int sal_p2p_allreduce_f64_emulated(sal_handle_t h, double* const* values, int n, const void* const* peer_tables, int n_virtual,
+                                   unsigned int launch_id, void* stream) {
+    SAL_CHECK_ARG(h != nullptr, "handle is null");
+    SAL_CHECK_ARG(values && peer_tables && n >= 0 && n_virtual == 2, "two emulated ranks");
+    SAL_CHECK_ARG(launch_id >= 1 && launch_id < (1u << 15), "launch_id must be in 1 .. 32767");
+    SAL_CUDA(cudaSetDevice(h->device));
+    const int gpus[2] = {0, 1};
+    return sal_launch_p2p_allreduce(n_virtual, values, peer_tables, gpus, n, n_virtual, launch_id, (cudaStream_t)stream);
+}
+
 int sal_corrnmf_norms(sal_handle_t h, const void* L, const void* U, int m, const void* X_or_null, double* out, void* stream) {
     SAL_CORR_COMMON(m);
     SAL_CHECK_ARG(L && out, "null argument");

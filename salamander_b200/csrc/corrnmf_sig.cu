@@ -238,7 +238,79 @@ __global__ void __launch_bounds__(SIG_THREADS) signature_embeddings_kernel(const
     if (nrank > 1) cluster.sync();  // nobody leaves while a neighbour may still read its totals
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// small all-reduce over peer memory: the few-KB sums of a CorrNMF iteration (W numerator, scaling sums, norms, likelihood)
+// ---------------------------------------------------------------------------------------------------------
+// Thread i pushes buf[i] as a tagged word into every peer's receive buffer [2 slots][n_gpus][P2P_AR_MAX], polls its own GPU's
+// buffer and replaces buf[i] by the sum of the contributions in rank order (bit-identical on all ranks).  One tag per call
+// (the callers' launch number, counted alike on every rank); two slots by tag parity suffice: a rank finishes call t only
+// after it has read every peer's words of call t, and pushes the words of call t + 1 only afterwards.
+constexpr int P2P_AR_MAX = 4096;
+struct AllreduceParams {
+    double* buf[SIG_MAX_VIRTUAL];
+    const void* peers[SIG_MAX_VIRTUAL];
+    int gpu[SIG_MAX_VIRTUAL];
+    int n, n_gpus;
+    unsigned int tag;
+};
+__global__ void __launch_bounds__(256) p2p_allreduce_kernel(const __grid_constant__ AllreduceParams P) {
+    const int vr = blockIdx.y, i = (int)blockIdx.x * 256 + (int)threadIdx.x;
+    if (i >= P.n) return;
+    uint4* const* peers = (uint4* const*)P.peers[vr];
+    const int gpu = P.gpu[vr], n_gpus = P.n_gpus;
+    const unsigned int tag = P.tag;
+    const double mine = P.buf[vr][i];
+    const size_t slot = (size_t)(tag & 1u) * n_gpus;
+    for (int p = 0; p < n_gpus; ++p)
+        if (p != gpu) sig_push(peers[p] + (slot + gpu) * P2P_AR_MAX + i, mine, tag);
+    const uint4* own = peers[gpu] + slot * P2P_AR_MAX + i;
+    double got[SIG_MAX_GPUS];
+    unsigned int pending = ((1u << n_gpus) - 1u) & ~(1u << gpu), spins = 0;
+    unsigned long long t0 = 0;
+    while (pending) {
+#pragma unroll
+        for (int p = 0; p < SIG_MAX_GPUS; ++p)
+            if ((pending >> p) & 1u) {
+                const uint4 wd = sig_peek(own + (size_t)p * P2P_AR_MAX);
+                if (wd.y == tag && wd.w == tag) {
+                    got[p] = __longlong_as_double((long long)(((unsigned long long)wd.z << 32) | wd.x));
+                    pending &= ~(1u << p);
+                }
+            }
+        if (pending && (++spins & 255u) == 0) {
+            const unsigned long long now = sig_global_ns();
+            if (t0 == 0) t0 = now;
+            if (now - t0 > 20ull * 1000 * 1000 * 1000) __trap();
+        }
+    }
+    double sum = 0.0;
+#pragma unroll
+    for (int p = 0; p < SIG_MAX_GPUS; ++p)
+        if (p < n_gpus) sum += p == gpu ? mine : got[p];
+    P.buf[vr][i] = sum;
+}
+
 }  // namespace
+
+size_t sal_p2p_allreduce_words(int n_gpus) { return (size_t)2 * n_gpus * P2P_AR_MAX; }
+int sal_p2p_allreduce_max(void) { return P2P_AR_MAX; }
+
+int sal_launch_p2p_allreduce(int n_virtual, double* const* bufs, const void* const* peer_tables, const int* gpus, int n, int n_gpus,
+                             unsigned int launch_id, cudaStream_t st) {
+    if (n <= 0) return 0;
+    if (n > P2P_AR_MAX || n_virtual < 1 || n_virtual > SIG_MAX_VIRTUAL || n_gpus < 2 || n_gpus > SIG_MAX_GPUS) {
+        sal_set_error("p2p all-reduce: %d values (<= %d), %d emulated ranks (<= %d), %d GPUs (2 .. %d)", n, P2P_AR_MAX, n_virtual, SIG_MAX_VIRTUAL,
+                      n_gpus, SIG_MAX_GPUS);
+        return SAL_EINVAL;
+    }
+    AllreduceParams P;
+    memset(&P, 0, sizeof(P));
+    for (int v = 0; v < n_virtual; ++v) P.buf[v] = bufs[v], P.peers[v] = peer_tables[v], P.gpu[v] = gpus[v];
+    P.n = n, P.n_gpus = n_gpus, P.tag = launch_id;
+    p2p_allreduce_kernel<<<dim3((n + 255) / 256, n_virtual), 256, 0, st>>>(P);
+    SAL_CUDA(cudaGetLastError());
+    return 0;
+}
 
 // the signature-embedding kernel for (dtype, embedding dimension): dimension 2 .. 5 as a template constant, 0 = run time
 static const void* sig_kernel(int dtype, int m) {

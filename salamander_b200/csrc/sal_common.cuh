@@ -155,6 +155,11 @@ struct SigLaunchRank {
 int sal_launch_corrnmf_signature_embeddings_v(const SigLaunchRank* rs, int n_virtual, int m, double variance, int sig_begin, int sig_count,
                                               int n_gpus, unsigned int launch_id, cudaStream_t st);
 size_t sal_corrnmf_sig_exchange_words(int k, int n_gpus);  // 16-byte words of one receive buffer
+// small all-reduce of doubles over peer memory (corrnmf_sig.cu)
+size_t sal_p2p_allreduce_words(int n_gpus);
+int sal_p2p_allreduce_max(void);
+int sal_launch_p2p_allreduce(int n_virtual, double* const* bufs, const void* const* peer_tables, const int* gpus, int n, int n_gpus,
+                             unsigned int launch_id, cudaStream_t st);
 int sal_launch_corrnmf_norms(sal_ctx* c, const void* L, const void* U, int m, const void* X_or_null, double* out, cudaStream_t st);
 
 // ---- persistent period kernel (klnmf_period_tf32.cu) ------------------------------------------------------

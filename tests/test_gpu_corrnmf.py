@@ -269,3 +269,31 @@ def test_signature_embeddings_exchange_with_emulated_ranks(D, k, m):
         assert np.allclose(Ls[0].cpu().numpy(), L_one.cpu().numpy(), rtol=1e-7, atol=1e-10), (Ls[0], L_one)
         for w in wss + [ws_all]:
             w.close()
+
+
+@pytest.mark.parametrize("n", [1, 10, 483, 4096])
+def test_peer_memory_allreduce_with_emulated_ranks(n):
+    """sal_p2p_allreduce_f64 (the few-KB sums of a sharded CorrNMF iteration) with two ranks emulated on one GPU: both end with
+    the same bits, equal to the rank-ordered sum, call after call on the same receive buffers (tags only ever increase)."""
+    from salamander_b200 import _lib
+    from salamander_b200._device import Workspace
+
+    dev = torch.device("cuda", 0)
+    lib = _lib.load()
+    assert n <= int(lib.sal_p2p_allreduce_max_values())
+    ws = Workspace(96, 8, 2, torch.float64, dev)
+    n_words = int(lib.sal_p2p_allreduce_bytes(2)) // 16
+    recv = [torch.zeros((n_words, 4), dtype=torch.int32, device=dev) for _ in range(2)]
+    tables = [torch.tensor([recv[0].data_ptr(), recv[1].data_ptr()], dtype=torch.int64, device=dev) for _ in range(2)]
+    gen = torch.Generator(device=dev).manual_seed(n)
+    for launch in range(1, 6):
+        a = torch.randn(n, dtype=torch.float64, device=dev, generator=gen) * 10.0 ** launch
+        b = torch.randn(n, dtype=torch.float64, device=dev, generator=gen)
+        want = a + b  # rank 0's contribution first
+        bufs = (C.c_void_p * 2)(a.data_ptr(), b.data_ptr())
+        tabs = (C.c_void_p * 2)(tables[0].data_ptr(), tables[1].data_ptr())
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(lib.sal_p2p_allreduce_f64_emulated(ws._h, bufs, n, tabs, 2, launch, stream), "sal_p2p_allreduce_f64_emulated")
+        torch.cuda.synchronize()
+        assert torch.equal(a, b) and torch.equal(a, want)
+    ws.close()
