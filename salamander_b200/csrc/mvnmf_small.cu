@@ -15,7 +15,13 @@
 // The penalised objective of the INCOMING iterate is produced on the way (what the period-wise fit driver needs).
 // Arithmetic in the handle's dtype with fixed summation orders (deterministic); the k x k algebra, the logarithms and every
 // objective sum are float64.  gamma lives in device memory (gamma_in -> gamma_out).
+#include <cooperative_groups.h>
+
+#include <stdlib.h>
+
 #include "sal_common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -57,9 +63,9 @@ __device__ double block_sum(double v, Shared& sh) {  // fixed order; result on e
 }
 
 // G = M M^T + delta I for M [k][WP] in shared memory
-template <typename T>
+template <typename T, int NTH = NT>
 __device__ void gram(const T* M, double* G, int GP, int V, int k, double delta) {
-    for (int i = threadIdx.x; i < k * k; i += NT) {
+    for (int i = threadIdx.x; i < k * k; i += NTH) {
         const int a = i / k, b = i - a * k;
         double t = 0.0;
         for (int v = 0; v < V; ++v) t += (double)M[a * WP + v] * (double)M[b * WP + v];
@@ -394,6 +400,352 @@ mvnmf_small_kernel(const T* X, const T* W_in, T* W_out, const T* H_in, T* H_out,
     if (tid == 0) *gamma_out = gamma;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// The same iterations on a thread-block CLUSTER: CTA r of C owns the samples r, r + C, ... in blocks (a contiguous run of
+// ceil(D / C) samples), keeps THEIR counts in registers and their exposures / quotient rows in its shared memory; W, the k x k
+// algebra and every decision are replicated (same numbers in every CTA, so the CTAs take the same branches).  What needs all
+// samples -- the numerator N, the row sums of H', the KL sums -- is exchanged through distributed shared memory and added in
+// CTA order (deterministic).  One SM's worth of float64 work becomes C SMs' worth; the serial k x k part stays.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int CNT = 256;         // threads per CTA
+constexpr int TPS = 8;           // threads per sample
+constexpr int CVQ = SAL_VMAX / TPS;  // 12 features per thread
+constexpr int SPC = CNT / TPS;   // at most 32 samples per CTA
+constexpr int CMAX = 8;          // portable cluster size
+
+struct CShared {
+    double red[CNT / 32];
+    double colsum[SAL_KMAX];
+    double col[SAL_KMAX];
+    double hsum[SAL_KMAX];
+    double bcast[4];
+    double xch[2][2 + SAL_KMAX];  // [parity][kl | spare | hsum partials]: this CTA's contribution to a cluster-wide sum
+};
+
+__device__ double block_sum_c(double v, CShared& sh) {  // fixed order; result on every thread of the CTA
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh.red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int w = 0; w < CNT / 32; ++w) t += sh.red[w];
+    return t;
+}
+
+template <typename T, int KT>
+__global__ void __launch_bounds__(CNT, 1)
+mvnmf_cluster_kernel(const T* X, const T* W_in, T* W_out, const T* H_in, T* H_out, int D, int V, int k, double lam, double delta,
+                     int n_given, int n_iter, const double* gamma_in, double* gamma_out, double* objective) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int C = (int)cluster.num_blocks(), cr = (int)cluster.block_rank();
+    const int Dl_max = (D + C - 1) / C;                       // samples per CTA (the last CTA may own fewer)
+    const int d_lo = cr * Dl_max, Dl = max(0, min(D - d_lo, Dl_max));
+    extern __shared__ __align__(16) unsigned char raw[];
+    T* sR = reinterpret_cast<T*>(raw);     // [SPC][RP]  quotient rows of this CTA's samples
+    T* sH = sR + (size_t)SPC * RP;         // [SPC][k]
+    T* sW = sH + (size_t)SPC * k;          // [k][WP]
+    T* sWu = sW + (size_t)k * WP;          // [k][WP]  numerator N, then W_unconstrained
+    T* sWt = sWu + (size_t)k * WP;         // [k][WP]  line-search candidate
+    T* sWp = sWt + (size_t)k * WP;         // [k][WP]  this CTA's partial numerator (read by the whole cluster)
+    const int GP = k + 1;
+    const size_t t_bytes = sizeof(T) * ((size_t)SPC * RP + (size_t)SPC * k + 4 * (size_t)k * WP);
+    double* G = reinterpret_cast<double*>(raw + ((t_bytes + 7) & ~(size_t)7));
+    double* Y = G + k * GP;
+    __shared__ CShared sh;
+    const int tid = threadIdx.x, dl = tid / TPS, q = tid % TPS, v0 = q * CVQ;
+    const T eps = (T)SAL_EPS_F32;
+    const bool row = dl < Dl;
+    const int d = d_lo + dl;
+    unsigned int n_xch = 0;  // exchanges so far (parity = buffer)
+
+    T x[CVQ];
+#pragma unroll
+    for (int i = 0; i < CVQ; ++i) x[i] = (row && v0 + i < V) ? X[(size_t)d * V + v0 + i] : (T)0;
+    for (int i = tid; i < k * V; i += CNT) sW[(i / V) * WP + i % V] = W_in[i];
+    for (int i = tid; i < k * WP; i += CNT) sWt[i] = (T)0, sWu[i] = (T)0, sWp[i] = (T)0;
+    for (int i = tid; i < Dl * k; i += CNT) sH[i] = H_in[(size_t)d_lo * k + i];
+    double gamma = *gamma_in;
+    __syncthreads();
+
+    // cluster-wide sum of a CTA-uniform scalar (+ optionally the k row sums of H'), contributions added in CTA order.
+    // The contribution buffers alternate with the parity of the exchange: one cluster barrier per exchange (a CTA can only
+    // overwrite a buffer two exchanges later, after everybody has passed the barrier in between).
+    auto exchange = [&](double mine, bool with_hsum) {
+        const int b = (int)(n_xch & 1u);
+        ++n_xch;
+        __syncthreads();
+        if (tid == 0) sh.xch[b][0] = mine;
+        // (the hsum partials were written into sh.xch[b][2 + j] by the caller)
+        cluster.sync();
+        double total = 0.0;
+        for (int r = 0; r < C; ++r) total += cluster.map_shared_rank(&sh.xch[b][0], r)[0];
+        if (with_hsum && tid < k) {
+            double t = 0.0;
+            for (int r = 0; r < C; ++r) t += cluster.map_shared_rank(&sh.xch[b][0], r)[2 + tid];
+            sh.hsum[tid] = (double)(T)t;
+        }
+        return total;
+    };
+
+    // KL(X || M h) over this thread's features with float64 terms (x = 0 contributes m h)
+    auto kl_row = [&](const T* M, const T (&hv)[KT]) {
+        double kl = 0.0;
+        if (row) {
+#pragma unroll 2
+            for (int i = 0; i < CVQ; ++i) {
+                const int v = v0 + i;
+                if (v < V) {
+                    double wh = 0.0;
+#pragma unroll
+                    for (int j = 0; j < KT; ++j)
+                        if (j < k) wh += (double)M[j * WP + v] * (double)hv[j];
+                    const double xd = (double)x[i];
+                    kl += xd != 0.0 ? xd * log(xd / wh) - xd + wh : wh;
+                }
+            }
+        }
+        return kl;
+    };
+    auto logdet = [&](const T* M) {  // CTA-uniform (and, the inputs being replicated, cluster-uniform) result
+        gram<T, CNT>(M, G, GP, V, k, delta);
+        if (tid < 32) {
+            const double det = lu_det_warp(G, GP, k);
+            if (tid == 0) sh.bcast[0] = log(det);
+        }
+        __syncthreads();
+        const double r = sh.bcast[0];
+        __syncthreads();
+        return r;
+    };
+
+    double ld_W = 0.0;
+    bool have_ld = false;
+    const int n_pass = n_iter > 0 ? n_iter : (objective ? 1 : 0);
+    for (int it = 0; it < n_pass; ++it) {
+        T hd[KT];
+#pragma unroll
+        for (int j = 0; j < KT; ++j) hd[j] = (row && j < k) ? sH[dl * k + j] : (T)0;
+        if (it == 0 && objective) {  // penalised objective of the incoming iterate
+            const double kl = exchange(block_sum_c(kl_row(sW, hd), sh), false);
+            ld_W = logdet(sW), have_ld = true;
+            if (tid == 0 && cr == 0) *objective = kl + lam * ld_W;
+        }
+        if (it >= n_iter) break;  // objective-only call
+        // ---- H step ----
+        T hn[KT];
+#pragma unroll
+        for (int j = 0; j < KT; ++j) hn[j] = (T)0;
+        if (row) {
+#pragma unroll(KT <= 8 ? CVQ : 2)
+            for (int i = 0; i < CVQ; ++i) {
+                const int v = v0 + i;
+                if (v < V) {
+                    T wv[KT];
+                    T wh = (T)0;
+#pragma unroll
+                    for (int j = 0; j < KT; ++j) wv[j] = j < k ? sW[j * WP + v] : (T)0, wh += wv[j] * hd[j];
+                    const T r = tdiv(x[i], wh);
+#pragma unroll
+                    for (int j = 0; j < KT; ++j) hn[j] += wv[j] * r;
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < KT; ++j) {
+            T t = hn[j];
+            t += __shfl_xor_sync(0xffffffffu, t, 1);
+            t += __shfl_xor_sync(0xffffffffu, t, 2);
+            t += __shfl_xor_sync(0xffffffffu, t, 4);
+            hd[j] = (row && j < k) ? max(hd[j] * t, eps) : (T)0;  // h' (identical on the eight threads of a sample)
+        }
+        if (n_given >= k) {  // all signatures given: the iteration is the H step
+            __syncthreads();
+            if (row && q == 0) {
+#pragma unroll
+                for (int j = 0; j < KT; ++j)
+                    if (j < k) sH[dl * k + j] = hd[j];
+            }
+            __syncthreads();
+            continue;
+        }
+        // ---- quotient with the new exposures, previous KL, partial numerator and partial row sums of H' ----
+        double kl_prev = 0.0;
+        if (row) {
+#pragma unroll(KT <= 8 ? CVQ : 2)
+            for (int i = 0; i < CVQ; ++i) {
+                const int v = v0 + i;
+                if (v < V) {
+                    T wh = (T)0;
+                    double whd = 0.0;
+#pragma unroll
+                    for (int j = 0; j < KT; ++j)
+                        if (j < k) {
+                            const T w = sW[j * WP + v];
+                            wh += w * hd[j];
+                            if (sizeof(T) == 4) whd += (double)w * (double)hd[j];
+                        }
+                    sR[dl * RP + v] = tdiv(x[i], wh);
+                    const double xd = (double)x[i], wd = sizeof(T) == 4 ? whd : (double)wh;
+                    kl_prev += xd != 0.0 ? xd * log(xd / wd) - xd + wd : wd;
+                }
+            }
+        }
+        __syncthreads();  // every read of the old sH is done
+        if (row && q == 0) {
+#pragma unroll
+            for (int j = 0; j < KT; ++j)
+                if (j < k) sH[dl * k + j] = hd[j];
+        }
+        kl_prev = block_sum_c(kl_prev, sh);  // (its barriers also publish sR and the new sH)
+        for (int i = tid; i < k * V; i += CNT) {
+            const int j = i / V, v = i - j * V;
+            T a0 = (T)0, a1 = (T)0;
+            int dd = 0;
+            for (; dd + 1 < Dl; dd += 2) {
+                a0 += sR[dd * RP + v] * sH[dd * k + j];
+                a1 += sR[(dd + 1) * RP + v] * sH[(dd + 1) * k + j];
+            }
+            for (; dd < Dl; ++dd) a0 += sR[dd * RP + v] * sH[dd * k + j];
+            sWp[j * WP + v] = a0 + a1;
+        }
+        {
+            const int w = tid >> 5, lane = tid & 31, b = (int)(n_xch & 1u);
+            for (int j = w; j < k; j += CNT / 32) {
+                double t = 0.0;
+                for (int dd = lane; dd < Dl; dd += 32) t += (double)sH[dd * k + j];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+                if (lane == 0) sh.xch[b][2 + j] = t;
+            }
+        }
+        kl_prev = exchange(kl_prev, true);  // (its cluster barrier also publishes every CTA's partial numerator)
+        for (int i = tid; i < k * V; i += CNT) {
+            const int at = (i / V) * WP + i % V;
+            T t = (T)0;
+            for (int r = 0; r < C; ++r) t += cluster.map_shared_rank(sWp, r)[at];
+            sWu[at] = t;
+        }
+        __syncthreads();
+        if (!have_ld) ld_W = logdet(sW), have_ld = true;
+        const double prev = kl_prev + lam * ld_W;
+        // ---- unconstrained W step (replicated) ----
+        gram<T, CNT>(sW, G, GP, V, k, delta);
+        if (tid < 32) invert_warp(G, Y, sh.col, GP, k);
+        __syncthreads();
+        for (int i = tid; i < k * V; i += CNT) {
+            const int j = i / V, v = i - j * V;
+            const double w = (double)sW[j * WP + v];
+            double out;
+            if (j < n_given) {
+                out = w;
+            } else {
+                double wym = 0.0, wya = 0.0;
+                for (int a = 0; a < k; ++a) {
+                    const double y = Y[a * GP + j];
+                    const double wa = (double)sW[a * WP + v];
+                    wym += wa * fmax(0.0, -y);
+                    wya += wa * fabs(y);
+                }
+                const double r = sh.hsum[j];
+                const double a1 = r - 4.0 * lam * wym;
+                const double s2 = 8.0 * lam * wya * (double)sWu[j * WP + v];
+                const double num = sqrt(a1 * a1 + s2) + (-r + 4.0 * lam * wym);
+                out = fmax(w * num / (4.0 * lam * wya), (double)SAL_EPS_F32);
+            }
+            sWu[j * WP + v] = (T)out;
+        }
+        __syncthreads();
+        // ---- line search (replicated candidates, sharded KL) ----
+        double g_blend = -1.0, ld_t = 0.0;
+        while (true) {
+            for (int i = tid; i < k * V; i += CNT) {
+                const int j = i / V, v = i - j * V;
+                const double wu = (double)sWu[j * WP + v];
+                sWt[j * WP + v] = (T)(g_blend < 0.0 ? wu : (1.0 - g_blend) * (double)sW[j * WP + v] + g_blend * wu);
+            }
+            __syncthreads();
+            {
+                const int w = tid >> 5, lane = tid & 31;
+                for (int j = w; j < k; j += CNT / 32) {
+                    double t = 0.0;
+                    for (int v = lane; v < V; v += 32) t += (double)sWt[j * WP + v];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+                    if (lane == 0) sh.colsum[j] = (double)(T)t;
+                }
+            }
+            __syncthreads();
+            for (int i = tid; i < k * V; i += CNT) {
+                const int j = i / V, v = i - j * V;
+                sWt[j * WP + v] = (T)fmax((double)sWt[j * WP + v] / sh.colsum[j], (double)SAL_EPS_F32);
+            }
+            __syncthreads();
+            ld_t = logdet(sWt);
+            T ht[KT];
+#pragma unroll
+            for (int j = 0; j < KT; ++j) ht[j] = (row && j < k) ? max(hd[j] * (T)sh.colsum[j], eps) : (T)0;
+            const double val = exchange(block_sum_c(kl_row(sWt, ht), sh), false) + lam * ld_t;
+            if (!(val > prev && gamma > 1e-16)) break;
+            gamma *= 0.8;
+            g_blend = gamma;
+            __syncthreads();
+        }
+        gamma = fmin(1.0, 1.2 * gamma);
+        ld_W = ld_t;
+        for (int i = tid; i < k * V; i += CNT) sW[(i / V) * WP + i % V] = sWt[(i / V) * WP + i % V];
+        if (row && q == 0) {
+#pragma unroll
+            for (int j = 0; j < KT; ++j)
+                if (j < k) sH[dl * k + j] = max(hd[j] * (T)sh.colsum[j], eps);
+        }
+        __syncthreads();
+    }
+    if (cr == 0) {
+        for (int i = tid; i < k * V; i += CNT) W_out[i] = sW[(i / V) * WP + i % V];
+        if (tid == 0) *gamma_out = gamma;
+    }
+    for (int i = tid; i < Dl * k; i += CNT) H_out[(size_t)d_lo * k + i] = sH[i];
+    cluster.sync();  // nobody leaves while a neighbour may still read its shared memory
+}
+
+template <typename T>
+size_t cluster_smem(int k) {
+    return sizeof(T) * ((size_t)SPC * RP + (size_t)SPC * k + 4 * (size_t)k * WP) + 8 + sizeof(double) * 2 * (size_t)k * (k + 1);
+}
+
+template <typename T, int KT>
+int launch_cluster_t(sal_ctx* c, int csize, const void* X, const void* W_in, void* W_out, const void* H_in, void* H_out, double lam,
+                     double delta, int n_given, int n_iter, const double* gamma_in, double* gamma_out, double* objective, cudaStream_t st) {
+    const size_t smem = cluster_smem<T>(c->k);
+    SAL_CUDA(cudaFuncSetAttribute(mvnmf_cluster_kernel<T, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(csize), cfg.blockDim = dim3(CNT), cfg.dynamicSmemBytes = smem, cfg.stream = st;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = csize, attr.val.clusterDim.y = 1, attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr, cfg.numAttrs = 1;
+    const T *Xp = (const T*)X, *Wi = (const T*)W_in, *Hi = (const T*)H_in;
+    T *Wo = (T*)W_out, *Ho = (T*)H_out;
+    const int D = (int)c->D, V = c->V, k = c->k;
+    SAL_CUDA(cudaLaunchKernelEx(&cfg, mvnmf_cluster_kernel<T, KT>, Xp, Wi, Wo, Hi, Ho, D, V, k, lam, delta, n_given, n_iter, gamma_in, gamma_out,
+                                objective));
+    c->launches++;
+    return 0;
+}
+
+template <typename T>
+int launch_cluster_k(sal_ctx* c, int csize, const void* X, const void* W_in, void* W_out, const void* H_in, void* H_out, double lam,
+                     double delta, int n_given, int n_iter, const double* gamma_in, double* gamma_out, double* objective, cudaStream_t st) {
+#define SAL_MVC(KT_) launch_cluster_t<T, KT_>(c, csize, X, W_in, W_out, H_in, H_out, lam, delta, n_given, n_iter, gamma_in, gamma_out, objective, st)
+    if (c->k <= 4) return SAL_MVC(4);
+    if (c->k <= 8) return SAL_MVC(8);
+    if (c->k <= 12) return SAL_MVC(12);
+    if (c->k <= 16) return SAL_MVC(16);
+    return SAL_MVC(32);
+#undef SAL_MVC
+}
+
 template <typename T>
 size_t small_smem(int D, int k) {
     return sizeof(T) * ((size_t)D * RP + (size_t)D * k + 3 * (size_t)k * WP) + 8 + sizeof(double) * 2 * (size_t)k * (k + 1);
@@ -432,6 +784,18 @@ bool sal_mvnmf_small_ok(const sal_ctx* c) {
 int sal_launch_mvnmf_small(sal_ctx* c, const void* X, const void* W_in, void* W_out, const void* H_in, void* H_out, double lam,
                            double delta, int n_given, int n_iter, const double* gamma_in, double* gamma_out, double* objective,
                            cudaStream_t st) {
+    // enough samples for several SMs: the cluster kernel (8 CTAs, 8 threads per sample); SAL_B200_MVNMF_CLUSTER=0 keeps one CTA
+    int csize = c->D >= 64 ? CMAX : 1;
+    while (csize > 1 && (c->D + csize - 1) / csize > SPC) csize = 0;  // (cannot happen for D <= 256 = CMAX * SPC)
+    if (const char* e = getenv("SAL_B200_MVNMF_CLUSTER")) {
+        const int forced = atoi(e);
+        if (forced <= 1) csize = 1;
+        else if (forced <= CMAX && (c->D + forced - 1) / forced <= SPC) csize = forced;
+    }
+    if (csize > 1)
+        return c->dtype == SAL_F32
+                   ? launch_cluster_k<float>(c, csize, X, W_in, W_out, H_in, H_out, lam, delta, n_given, n_iter, gamma_in, gamma_out, objective, st)
+                   : launch_cluster_k<double>(c, csize, X, W_in, W_out, H_in, H_out, lam, delta, n_given, n_iter, gamma_in, gamma_out, objective, st);
     return c->dtype == SAL_F32
                ? launch_k<float>(c, X, W_in, W_out, H_in, H_out, lam, delta, n_given, n_iter, gamma_in, gamma_out, objective, st)
                : launch_k<double>(c, X, W_in, W_out, H_in, H_out, lam, delta, n_given, n_iter, gamma_in, gamma_out, objective, st);

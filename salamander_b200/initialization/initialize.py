@@ -34,7 +34,8 @@ GIVEN_PARAMETERS_CORRNMF = [
 ]
 
 
-DEFER_MIN_SIZE = 1 << 22  # exposure matrices at least this large are rescaled / clipped on the device
+DEFER_MIN_SIZE = 1 << 20  # exposure matrices at least this large are rescaled / clipped on the device (the host pass over a
+# 125k x 20 shard cost more than the whole 20-iteration fit at 8 GPUs)
 
 
 def initialize_mat(data_mat, n_signatures, method="nndsvd", given_signatures_mat=None, _defer=None, **kwargs):
