@@ -182,15 +182,14 @@ size_t small_smem(int D, int k) {
 // update is enough (a CTA can only overwrite a buffer two updates later, after everybody has passed the barrier in between).
 // ---------------------------------------------------------------------------------------------------------
 constexpr int CNT = 256;             // threads per CTA
-constexpr int TPS = 8;               // threads per sample
-constexpr int CVQ = SAL_VMAX / TPS;  // 12 features per thread
-constexpr int SPC = CNT / TPS;       // at most 32 samples per CTA
-constexpr int CMAX = 8;              // portable cluster size
+constexpr int SPC_MAX = CNT / 8;     // samples per CTA with 8 threads per sample (sizes the shared-memory tiles)
+constexpr int CMAX = 8;              // portable cluster size (8 threads per sample); 16 CTAs x 16 threads per sample where allowed
 
-template <typename T, int KT>
+template <typename T, int KT, int TPS>
 __global__ void __launch_bounds__(CNT, 1)
 klnmf_cluster_kernel(const T* X, const T* W_in, T* W_out, const T* H_in, T* H_out, int D, int V, int k, int n_given, int n_iter,
                      double* objective) {
+    constexpr int CVQ = SAL_VMAX / TPS, SPC = SPC_MAX;  // features per thread; rows of the shared-memory tiles
     cg::cluster_group cluster = cg::this_cluster();
     const int C = (int)cluster.num_blocks(), cr = (int)cluster.block_rank();
     const int Dl_max = (D + C - 1) / C;
@@ -278,6 +277,7 @@ klnmf_cluster_kernel(const T* X, const T* W_in, T* W_out, const T* H_in, T* H_ou
             t += __shfl_xor_sync(0xffffffffu, t, 1);
             t += __shfl_xor_sync(0xffffffffu, t, 2);
             t += __shfl_xor_sync(0xffffffffu, t, 4);
+            if (TPS == 16) t += __shfl_xor_sync(0xffffffffu, t, 8);
             hn[j] = t;
         }
         __syncthreads();  // sR complete, every read of the old sH / sW in phase 1 done
@@ -342,14 +342,15 @@ klnmf_cluster_kernel(const T* X, const T* W_in, T* W_out, const T* H_in, T* H_ou
 
 template <typename T>
 size_t cluster_smem(int k) {
-    return sizeof(T) * ((size_t)SPC * RP + (size_t)SPC * k + 4 * (size_t)k * SAL_VMAX);
+    return sizeof(T) * ((size_t)SPC_MAX * RP + (size_t)SPC_MAX * k + 4 * (size_t)k * SAL_VMAX);
 }
 
-template <typename T, int KT>
+template <typename T, int KT, int TPS>
 int launch_cluster_t(sal_ctx* c, int csize, const void* X, const void* W_in, void* W_out, const void* H_in, void* H_out, int n_given,
                      int n_iter, double* objective, cudaStream_t st) {
     const size_t smem = cluster_smem<T>(c->k);
-    SAL_CUDA(cudaFuncSetAttribute(klnmf_cluster_kernel<T, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SAL_CUDA(cudaFuncSetAttribute(klnmf_cluster_kernel<T, KT, TPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (csize > 8) SAL_CUDA(cudaFuncSetAttribute(klnmf_cluster_kernel<T, KT, TPS>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(csize), cfg.blockDim = dim3(CNT), cfg.dynamicSmemBytes = smem, cfg.stream = st;
     cudaLaunchAttribute attr;
@@ -359,18 +360,18 @@ int launch_cluster_t(sal_ctx* c, int csize, const void* X, const void* W_in, voi
     const T *Xp = (const T*)X, *Wi = (const T*)W_in, *Hi = (const T*)H_in;
     T *Wo = (T*)W_out, *Ho = (T*)H_out;
     const int D = (int)c->D, V = c->V, k = c->k;
-    SAL_CUDA(cudaLaunchKernelEx(&cfg, klnmf_cluster_kernel<T, KT>, Xp, Wi, Wo, Hi, Ho, D, V, k, n_given, n_iter, objective));
+    SAL_CUDA(cudaLaunchKernelEx(&cfg, klnmf_cluster_kernel<T, KT, TPS>, Xp, Wi, Wo, Hi, Ho, D, V, k, n_given, n_iter, objective));
     c->launches++;
     return 0;
 }
 
-template <typename T>
+template <typename T, int TPS>
 int launch_cluster_k(sal_ctx* c, int csize, const void* X, const void* W_in, void* W_out, const void* H_in, void* H_out, int n_given,
                      int n_iter, double* objective, cudaStream_t st) {
-    if (c->k <= 4) return launch_cluster_t<T, 4>(c, csize, X, W_in, W_out, H_in, H_out, n_given, n_iter, objective, st);
-    if (c->k <= 8) return launch_cluster_t<T, 8>(c, csize, X, W_in, W_out, H_in, H_out, n_given, n_iter, objective, st);
-    if (c->k <= 16) return launch_cluster_t<T, 16>(c, csize, X, W_in, W_out, H_in, H_out, n_given, n_iter, objective, st);
-    return launch_cluster_t<T, 32>(c, csize, X, W_in, W_out, H_in, H_out, n_given, n_iter, objective, st);
+    if (c->k <= 4) return launch_cluster_t<T, 4, TPS>(c, csize, X, W_in, W_out, H_in, H_out, n_given, n_iter, objective, st);
+    if (c->k <= 8) return launch_cluster_t<T, 8, TPS>(c, csize, X, W_in, W_out, H_in, H_out, n_given, n_iter, objective, st);
+    if (c->k <= 16) return launch_cluster_t<T, 16, TPS>(c, csize, X, W_in, W_out, H_in, H_out, n_given, n_iter, objective, st);
+    return launch_cluster_t<T, 32, TPS>(c, csize, X, W_in, W_out, H_in, H_out, n_given, n_iter, objective, st);
 }
 
 }  // namespace
@@ -405,17 +406,26 @@ int launch_small_k(sal_ctx* c, const void* X, const void* W_in, void* W_out, con
 
 int sal_launch_klnmf_small(sal_ctx* c, const void* X, const void* W_in, void* W_out, const void* H_in, void* H_out, int n_given,
                            int n_iter, double* objective, cudaStream_t st) {
-    // enough samples for several SMs: the cluster kernel (8 CTAs, 8 threads per sample); SAL_B200_KLNMF_CLUSTER=0 keeps one CTA
+    // enough samples for several SMs: the cluster kernel, 8 CTAs x 8 threads per sample (16 CTAs x 16 threads per sample, the
+    // non-portable cluster size, measured the same 121k - 123k iterations/s on PCAWG: the update is bound by its barriers, not by
+    // arithmetic); SAL_B200_KLNMF_CLUSTER = 0 / 8 / 16 forces a choice
     int csize = c->D >= 64 ? CMAX : 1;
     if (const char* e = getenv("SAL_B200_KLNMF_CLUSTER")) {
         const int forced = atoi(e);
         if (forced <= 1) csize = 1;
-        else if (forced <= CMAX && (c->D + forced - 1) / forced <= SPC) csize = forced;
+        else if (forced == 8 || (forced == 16 && c->D <= 16 * (CNT / 16))) csize = forced;
     }
-    if (csize > 1 && (c->D + csize - 1) / csize > SPC) csize = 1;
-    if (csize > 1)
-        return c->dtype == SAL_F32 ? launch_cluster_k<float>(c, csize, X, W_in, W_out, H_in, H_out, n_given, n_iter, objective, st)
-                                   : launch_cluster_k<double>(c, csize, X, W_in, W_out, H_in, H_out, n_given, n_iter, objective, st);
+    if (csize == 8 && (c->D + 7) / 8 > SPC_MAX) csize = 1;
+    if (csize == 16) {  // (refused on devices / partitions without room for a 16-CTA cluster: fall back to the portable size)
+        const int err = c->dtype == SAL_F32 ? launch_cluster_k<float, 16>(c, 16, X, W_in, W_out, H_in, H_out, n_given, n_iter, objective, st)
+                                            : launch_cluster_k<double, 16>(c, 16, X, W_in, W_out, H_in, H_out, n_given, n_iter, objective, st);
+        if (err == 0) return 0;
+        (void)cudaGetLastError();
+        csize = (c->D + 7) / 8 <= SPC_MAX ? 8 : 1;
+    }
+    if (csize == 8)
+        return c->dtype == SAL_F32 ? launch_cluster_k<float, 8>(c, 8, X, W_in, W_out, H_in, H_out, n_given, n_iter, objective, st)
+                                   : launch_cluster_k<double, 8>(c, 8, X, W_in, W_out, H_in, H_out, n_given, n_iter, objective, st);
     return c->dtype == SAL_F32 ? launch_small_k<float>(c, X, W_in, W_out, H_in, H_out, n_given, n_iter, objective, st)
                                : launch_small_k<double>(c, X, W_in, W_out, H_in, H_out, n_given, n_iter, objective, st);
 }

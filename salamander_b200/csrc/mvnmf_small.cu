@@ -408,10 +408,8 @@ mvnmf_small_kernel(const T* X, const T* W_in, T* W_out, const T* H_in, T* H_out,
 // CTA order (deterministic).  One SM's worth of float64 work becomes C SMs' worth; the serial k x k part stays.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int CNT = 256;         // threads per CTA
-constexpr int TPS = 8;           // threads per sample
-constexpr int CVQ = SAL_VMAX / TPS;  // 12 features per thread
-constexpr int SPC = CNT / TPS;   // at most 32 samples per CTA
-constexpr int CMAX = 8;          // portable cluster size
+constexpr int SPC_MAX = CNT / 8;  // samples per CTA with 8 threads per sample (sizes the shared-memory tiles)
+constexpr int CMAX = 8;           // portable cluster size (8 threads per sample); 16 CTAs x 16 threads per sample where allowed
 
 struct CShared {
     double red[CNT / 32];
@@ -433,10 +431,11 @@ __device__ double block_sum_c(double v, CShared& sh) {  // fixed order; result o
     return t;
 }
 
-template <typename T, int KT>
+template <typename T, int KT, int TPS>
 __global__ void __launch_bounds__(CNT, 1)
 mvnmf_cluster_kernel(const T* X, const T* W_in, T* W_out, const T* H_in, T* H_out, int D, int V, int k, double lam, double delta,
                      int n_given, int n_iter, const double* gamma_in, double* gamma_out, double* objective) {
+    constexpr int CVQ = SAL_VMAX / TPS, SPC = SPC_MAX;  // features per thread; rows of the shared-memory tiles
     cg::cluster_group cluster = cg::this_cluster();
     const int C = (int)cluster.num_blocks(), cr = (int)cluster.block_rank();
     const int Dl_max = (D + C - 1) / C;                       // samples per CTA (the last CTA may own fewer)
@@ -449,7 +448,7 @@ mvnmf_cluster_kernel(const T* X, const T* W_in, T* W_out, const T* H_in, T* H_ou
     T* sWt = sWu + (size_t)k * WP;         // [k][WP]  line-search candidate
     T* sWp = sWt + (size_t)k * WP;         // [k][WP]  this CTA's partial numerator (read by the whole cluster)
     const int GP = k + 1;
-    const size_t t_bytes = sizeof(T) * ((size_t)SPC * RP + (size_t)SPC * k + 4 * (size_t)k * WP);
+    const size_t t_bytes = sizeof(T) * ((size_t)SPC_MAX * RP + (size_t)SPC_MAX * k + 4 * (size_t)k * WP);
     double* G = reinterpret_cast<double*>(raw + ((t_bytes + 7) & ~(size_t)7));
     double* Y = G + k * GP;
     __shared__ CShared sh;
@@ -557,6 +556,7 @@ mvnmf_cluster_kernel(const T* X, const T* W_in, T* W_out, const T* H_in, T* H_ou
             t += __shfl_xor_sync(0xffffffffu, t, 1);
             t += __shfl_xor_sync(0xffffffffu, t, 2);
             t += __shfl_xor_sync(0xffffffffu, t, 4);
+            if (TPS == 16) t += __shfl_xor_sync(0xffffffffu, t, 8);
             hd[j] = (row && j < k) ? max(hd[j] * t, eps) : (T)0;  // h' (identical on the eight threads of a sample)
         }
         if (n_given >= k) {  // all signatures given: the iteration is the H step
@@ -711,14 +711,15 @@ mvnmf_cluster_kernel(const T* X, const T* W_in, T* W_out, const T* H_in, T* H_ou
 
 template <typename T>
 size_t cluster_smem(int k) {
-    return sizeof(T) * ((size_t)SPC * RP + (size_t)SPC * k + 4 * (size_t)k * WP) + 8 + sizeof(double) * 2 * (size_t)k * (k + 1);
+    return sizeof(T) * ((size_t)SPC_MAX * RP + (size_t)SPC_MAX * k + 4 * (size_t)k * WP) + 8 + sizeof(double) * 2 * (size_t)k * (k + 1);
 }
 
-template <typename T, int KT>
+template <typename T, int KT, int TPS>
 int launch_cluster_t(sal_ctx* c, int csize, const void* X, const void* W_in, void* W_out, const void* H_in, void* H_out, double lam,
                      double delta, int n_given, int n_iter, const double* gamma_in, double* gamma_out, double* objective, cudaStream_t st) {
     const size_t smem = cluster_smem<T>(c->k);
-    SAL_CUDA(cudaFuncSetAttribute(mvnmf_cluster_kernel<T, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SAL_CUDA(cudaFuncSetAttribute(mvnmf_cluster_kernel<T, KT, TPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (csize > 8) SAL_CUDA(cudaFuncSetAttribute(mvnmf_cluster_kernel<T, KT, TPS>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(csize), cfg.blockDim = dim3(CNT), cfg.dynamicSmemBytes = smem, cfg.stream = st;
     cudaLaunchAttribute attr;
@@ -728,16 +729,17 @@ int launch_cluster_t(sal_ctx* c, int csize, const void* X, const void* W_in, voi
     const T *Xp = (const T*)X, *Wi = (const T*)W_in, *Hi = (const T*)H_in;
     T *Wo = (T*)W_out, *Ho = (T*)H_out;
     const int D = (int)c->D, V = c->V, k = c->k;
-    SAL_CUDA(cudaLaunchKernelEx(&cfg, mvnmf_cluster_kernel<T, KT>, Xp, Wi, Wo, Hi, Ho, D, V, k, lam, delta, n_given, n_iter, gamma_in, gamma_out,
-                                objective));
+    SAL_CUDA(cudaLaunchKernelEx(&cfg, mvnmf_cluster_kernel<T, KT, TPS>, Xp, Wi, Wo, Hi, Ho, D, V, k, lam, delta, n_given, n_iter, gamma_in,
+                                gamma_out, objective));
     c->launches++;
     return 0;
 }
 
-template <typename T>
+template <typename T, int TPS>
 int launch_cluster_k(sal_ctx* c, int csize, const void* X, const void* W_in, void* W_out, const void* H_in, void* H_out, double lam,
                      double delta, int n_given, int n_iter, const double* gamma_in, double* gamma_out, double* objective, cudaStream_t st) {
-#define SAL_MVC(KT_) launch_cluster_t<T, KT_>(c, csize, X, W_in, W_out, H_in, H_out, lam, delta, n_given, n_iter, gamma_in, gamma_out, objective, st)
+#define SAL_MVC(KT_) \
+    launch_cluster_t<T, KT_, TPS>(c, csize, X, W_in, W_out, H_in, H_out, lam, delta, n_given, n_iter, gamma_in, gamma_out, objective, st)
     if (c->k <= 4) return SAL_MVC(4);
     if (c->k <= 8) return SAL_MVC(8);
     if (c->k <= 12) return SAL_MVC(12);
@@ -784,18 +786,25 @@ bool sal_mvnmf_small_ok(const sal_ctx* c) {
 int sal_launch_mvnmf_small(sal_ctx* c, const void* X, const void* W_in, void* W_out, const void* H_in, void* H_out, double lam,
                            double delta, int n_given, int n_iter, const double* gamma_in, double* gamma_out, double* objective,
                            cudaStream_t st) {
-    // enough samples for several SMs: the cluster kernel (8 CTAs, 8 threads per sample); SAL_B200_MVNMF_CLUSTER=0 keeps one CTA
-    int csize = c->D >= 64 ? CMAX : 1;
-    while (csize > 1 && (c->D + csize - 1) / csize > SPC) csize = 0;  // (cannot happen for D <= 256 = CMAX * SPC)
+    // enough samples for several SMs: the cluster kernel -- 16 CTAs x 16 threads per sample (non-portable cluster size) when the
+    // samples fit 16 per CTA, else 8 CTAs x 8 threads per sample; SAL_B200_MVNMF_CLUSTER = 0 / 8 / 16 forces a choice
+    int csize = c->D >= 64 ? (c->D <= 16 * (CNT / 16) ? 16 : CMAX) : 1;
     if (const char* e = getenv("SAL_B200_MVNMF_CLUSTER")) {
         const int forced = atoi(e);
         if (forced <= 1) csize = 1;
-        else if (forced <= CMAX && (c->D + forced - 1) / forced <= SPC) csize = forced;
+        else if (forced == 8 || (forced == 16 && c->D <= 16 * (CNT / 16))) csize = forced;
     }
-    if (csize > 1)
-        return c->dtype == SAL_F32
-                   ? launch_cluster_k<float>(c, csize, X, W_in, W_out, H_in, H_out, lam, delta, n_given, n_iter, gamma_in, gamma_out, objective, st)
-                   : launch_cluster_k<double>(c, csize, X, W_in, W_out, H_in, H_out, lam, delta, n_given, n_iter, gamma_in, gamma_out, objective, st);
+    if (csize == 8 && (c->D + 7) / 8 > SPC_MAX) csize = 1;
+#define SAL_MVCL(TT_, TPS_, CS_) \
+    launch_cluster_k<TT_, TPS_>(c, CS_, X, W_in, W_out, H_in, H_out, lam, delta, n_given, n_iter, gamma_in, gamma_out, objective, st)
+    if (csize == 16) {  // (refused where a 16-CTA cluster has no room: fall back to the portable size)
+        const int err = c->dtype == SAL_F32 ? SAL_MVCL(float, 16, 16) : SAL_MVCL(double, 16, 16);
+        if (err == 0) return 0;
+        (void)cudaGetLastError();
+        csize = (c->D + 7) / 8 <= SPC_MAX ? 8 : 1;
+    }
+    if (csize == 8) return c->dtype == SAL_F32 ? SAL_MVCL(float, 8, 8) : SAL_MVCL(double, 8, 8);
+#undef SAL_MVCL
     return c->dtype == SAL_F32
                ? launch_k<float>(c, X, W_in, W_out, H_in, H_out, lam, delta, n_given, n_iter, gamma_in, gamma_out, objective, st)
                : launch_k<double>(c, X, W_in, W_out, H_in, H_out, lam, delta, n_given, n_iter, gamma_in, gamma_out, objective, st);
