@@ -589,7 +589,7 @@ def run_ours(args):
     W_a, W_b = st.W.clone(), torch.empty_like(st.W)
     px = st.weights.get("peer_exchange")
     pkw = {} if px is None else {"peers": px.peers, "state": px.state, "n_ranks": st.world, "rank": st.rank}
-    kernel_ms = float("nan")
+    kernel_ms, long_launch_ms = float("nan"), None
     if period:
         def chain_period(n):
             for _ in range(n):
@@ -605,6 +605,18 @@ def run_ours(args):
         ev3.record()
         barrier()
         kernel_ms = max_over_ranks(ev2.elapsed_time(ev3)) / (n_chain * upd)
+        # for reference: ONE launch of 4 periods' worth of updates -- the launch's fixed cost (cooperative launch, prologue, first
+        # pipeline fill, drain: profiles/r02b_period_fixed_costs.md) weighs a quarter as much, i.e. closer to the steady-state update
+        st.ws.klnmf_period(st.X, W_a, W_b, H_a, H_b, 0, True, 4 * upd, 0, False, **pkw)
+        barrier()
+        ev4, ev5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if world > 1:
+            dist.all_reduce(align)
+        ev4.record()
+        st.ws.klnmf_period(st.X, W_a, W_b, H_a, H_b, 0, True, 4 * upd, 0, False, **pkw)
+        ev5.record()
+        barrier()
+        long_launch_ms = max_over_ranks(ev4.elapsed_time(ev5)) / (4 * upd)
     chain_flags = sal_lib.PASS_UPDATE_H | sal_lib.PASS_WNUM | sal_lib.PASS_PARTIALS_ONLY
 
     def chain_pass(n):
@@ -723,6 +735,8 @@ def run_ours(args):
                 "how": (f"one CUDA event pair around {n_chain} back-to-back launches of the period kernel ({upd} updates each, no objective) on the launch stream, max over ranks; "
                         "duration / updates = time per update including everything between two updates" if period else
                         "one CUDA event pair around 50 back-to-back launches of the pass kernel alone (reduction kernel skipped)"),
+                "one_launch_of_4_periods_ms_per_update": long_launch_ms,
+                "one_launch_of_4_periods_frac": None if long_launch_ms is None else alg_bytes / (long_launch_ms * 1e-3) / 1e9 / peak_gbs,
                 "streaming_pass_alone_ms": pass_alone_ms,
                 "streaming_pass_alone_frac": alg_bytes / (pass_alone_ms * 1e-3) / 1e9 / peak_gbs,
                 "frac_floor_from_whole_step": alg_bytes / (elapsed_ms / args.steps * 1e-3) / 1e9 / peak_gbs,
