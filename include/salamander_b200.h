@@ -231,6 +231,11 @@ int sal_mvnmf_w_unconstrained(sal_handle_t h, const void* W, const void* N, cons
  */
 int sal_mvnmf_trial(sal_handle_t h, const void* W, const void* W_unc, double gamma_blend, double delta,
                     void* W_trial, void* h_scale, double* logdet_out, void* stream);
+/* sal_mvnmf_w_unconstrained followed by the FIRST line-search candidate (sal_mvnmf_trial with gamma_blend < 0: the full step,
+ * which the line search always tries first, mvnmf.py:80-88) in one launch; same results as the two calls. */
+int sal_mvnmf_w_unconstrained_trial(sal_handle_t h, const void* W, const void* N, const void* hsum, double lam, double delta,
+                                    int n_given, void* W_unc, void* W_trial, void* h_scale, double* logdet_out,
+                                    void* stream);
 
 /*
  * Small MvNMF problems (D_local <= 256, state fits the shared memory of one SM -- BASELINE config 1, MvNMF on 96 x 192):

@@ -355,6 +355,18 @@ class Workspace:
             "sal_mvnmf_w_unconstrained",
         )
 
+    def mvnmf_w_unconstrained_trial(self, W, N, hsum, lam: float, delta: float, n_given: int, W_unc, W_trial, h_scale, logdet_out) -> None:
+        """W_unconstrained and the first line-search candidate (the full step) in one launch."""
+        kv = self.k * self.V
+        _lib.check(
+            self.lib.sal_mvnmf_w_unconstrained_trial(
+                self._h, self._ptr(W, kv, "W"), self._ptr(N, kv, "N"), self._ptr(hsum, self.k, "hsum"), float(lam), float(delta),
+                int(n_given), self._ptr(W_unc, kv, "W_unc"), self._ptr(W_trial, kv, "W_trial"), self._ptr(h_scale, self.k, "h_scale"),
+                self._ptr(logdet_out, 1, "logdet_out", torch.float64), self._stream(),
+            ),
+            "sal_mvnmf_w_unconstrained_trial",
+        )
+
     def mvnmf_trial(self, W, W_unc, gamma_blend: float, delta: float, W_trial, h_scale, logdet_out) -> None:
         kv = self.k * self.V
         _lib.check(

@@ -50,6 +50,7 @@ SYMBOLS = {
     "sal_mvnmf_logdet": (_i, [_vp, _vp, _d, _vp, _vp]),
     "sal_mvnmf_w_unconstrained": (_i, [_vp, _vp, _vp, _vp, _d, _d, _i, _vp, _vp]),
     "sal_mvnmf_trial": (_i, [_vp, _vp, _vp, _d, _d, _vp, _vp, _vp, _vp]),
+    "sal_mvnmf_w_unconstrained_trial": (_i, [_vp, _vp, _vp, _vp, _d, _d, _i, _vp, _vp, _vp, _vp, _vp]),
     "sal_mvnmf_small_supported": (_i, [_vp]),
     "sal_mvnmf_small_updates": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _d, _d, _i, _i, _vp, _vp, _vp, _vp]),
     "sal_corrnmf_max_dim": (_i, []),

@@ -449,7 +449,15 @@ int sal_mvnmf_w_unconstrained(sal_handle_t h, const void* W, const void* N, cons
     SAL_CHECK_ARG(h && W && N && hsum && W_unc, "null argument");
     SAL_CHECK_ARG(n_given >= 0 && n_given <= h->k, "n_given out of range");
     SAL_CUDA(cudaSetDevice(h->device));
-    return sal_launch_mvnmf_w_unc(h, W, N, hsum, lam, delta, n_given, W_unc, (cudaStream_t)stream);
+    return sal_launch_mvnmf_w_unc(h, W, N, hsum, lam, delta, n_given, W_unc, nullptr, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int sal_mvnmf_w_unconstrained_trial(sal_handle_t h, const void* W, const void* N, const void* hsum, double lam, double delta,
+                                    int n_given, void* W_unc, void* W_trial, void* h_scale, double* logdet_out, void* stream) {
+    SAL_CHECK_ARG(h && W && N && hsum && W_unc && W_trial && h_scale && logdet_out, "null argument");
+    SAL_CHECK_ARG(n_given >= 0 && n_given <= h->k, "n_given out of range");
+    SAL_CUDA(cudaSetDevice(h->device));
+    return sal_launch_mvnmf_w_unc(h, W, N, hsum, lam, delta, n_given, W_unc, W_trial, h_scale, logdet_out, (cudaStream_t)stream);
 }
 
 int sal_mvnmf_trial(sal_handle_t h, const void* W, const void* W_unc, double gamma_blend, double delta,

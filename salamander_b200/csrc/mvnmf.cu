@@ -6,10 +6,11 @@
 //
 // W is stored [k][V] (asignatures.X); the reference's W (V,k) is its transpose.
 #include "sal_common.cuh"
+#include "mvnmf_kk.cuh"
 
 namespace {
 
-constexpr int NT = 128;
+constexpr int NT = 256;
 constexpr int KM = SAL_KMAX;
 constexpr int GP = KM + 1;        // pitch of k x k matrices
 constexpr int WP = SAL_VMAX + 1;  // pitch of the [k][V] copy
@@ -18,6 +19,7 @@ struct Smem {
     double Wd[KM * WP];      // W (or the trial W) as double, [k][V]
     double G[KM * GP];       // Gram + delta I, destroyed by the factorisation
     double Y[KM * GP];       // inverse (w_unconstrained only)
+    double Wu[KM * WP];      // W_unconstrained as the first line-search trial reads it (fused w_unconstrained + trial)
     double colsum[KM];
     double col[KM];
     double scal[4];
@@ -35,91 +37,18 @@ __device__ void gram(Smem& s, int V, int k, double delta) {
     __syncthreads();
 }
 
-// In-place LU with partial pivoting of s.G; returns det (all threads).
+// LU determinant / Gauss-Jordan inverse of s.G on warp 0 (mvnmf_kk.cuh); result published to the block
 __device__ double lu_det(Smem& s, int k) {
-    double sign = 1.0;
-    for (int c = 0; c < k; ++c) {
-        if (threadIdx.x == 0) {
-            int p = c;
-            double best = fabs(s.G[c * GP + c]);
-            for (int r = c + 1; r < k; ++r) {
-                const double a = fabs(s.G[r * GP + c]);
-                if (a > best) best = a, p = r;
-            }
-            s.piv = p;
-        }
-        __syncthreads();
-        const int p = s.piv;
-        if (p != c) {
-            sign = -sign;
-            for (int j = threadIdx.x; j < k; j += NT) {
-                const double t = s.G[c * GP + j];
-                s.G[c * GP + j] = s.G[p * GP + j];
-                s.G[p * GP + j] = t;
-            }
-            __syncthreads();
-        }
-        const double d = s.G[c * GP + c];
-        const int nr = k - c - 1, nc = k - c - 1;
-        // factors first (column c below the diagonal), then the trailing update
-        for (int r = threadIdx.x; r < nr; r += NT) s.G[(c + 1 + r) * GP + c] /= d;
-        __syncthreads();
-        for (int i = threadIdx.x; i < nr * nc; i += NT) {
-            const int r = c + 1 + i / nc, j = c + 1 + i % nc;
-            s.G[r * GP + j] -= s.G[r * GP + c] * s.G[c * GP + j];
-        }
-        __syncthreads();
+    if (threadIdx.x < 32) {
+        const double det = lu_det_warp(s.G, GP, k);
+        if (threadIdx.x == 0) s.scal[0] = det;
     }
-    double det = sign;
-    for (int c = 0; c < k; ++c) det *= s.G[c * GP + c];
-    return det;
-}
-
-// Y = G^-1 by Gauss-Jordan with partial pivoting (G destroyed).
-__device__ void invert(Smem& s, int k) {
-    for (int i = threadIdx.x; i < k * k; i += NT) s.Y[(i / k) * GP + i % k] = (i / k == i % k) ? 1.0 : 0.0;
     __syncthreads();
-    for (int c = 0; c < k; ++c) {
-        if (threadIdx.x == 0) {
-            int p = c;
-            double best = fabs(s.G[c * GP + c]);
-            for (int r = c + 1; r < k; ++r) {
-                const double a = fabs(s.G[r * GP + c]);
-                if (a > best) best = a, p = r;
-            }
-            s.piv = p;
-        }
-        __syncthreads();
-        const int p = s.piv;
-        if (p != c) {
-            for (int j = threadIdx.x; j < 2 * k; j += NT) {
-                double* M = j < k ? s.G : s.Y;
-                const int jj = j < k ? j : j - k;
-                const double t = M[c * GP + jj];
-                M[c * GP + jj] = M[p * GP + jj];
-                M[p * GP + jj] = t;
-            }
-            __syncthreads();
-        }
-        const double inv_d = 1.0 / s.G[c * GP + c];
-        __syncthreads();
-        for (int j = threadIdx.x; j < 2 * k; j += NT) {
-            double* M = j < k ? s.G : s.Y;
-            M[c * GP + (j < k ? j : j - k)] *= inv_d;
-        }
-        __syncthreads();
-        // eliminate column c from every other row (row c itself is not touched in this step)
-        for (int r = threadIdx.x; r < k; r += NT) s.col[r] = s.G[r * GP + c];
-        __syncthreads();
-        for (int i = threadIdx.x; i < k * 2 * k; i += NT) {
-            const int r = i / (2 * k), j = i - r * 2 * k;
-            if (r == c) continue;
-            double* M = j < k ? s.G : s.Y;
-            const int jj = j < k ? j : j - k;
-            M[r * GP + jj] -= s.col[r] * M[c * GP + jj];
-        }
-        __syncthreads();
-    }
+    return s.scal[0];
+}
+__device__ void invert(Smem& s, int k) {
+    if (threadIdx.x < 32) invert_warp(s.G, s.Y, s.col, GP, k);
+    __syncthreads();
 }
 
 template <typename T>
@@ -138,9 +67,12 @@ __global__ void __launch_bounds__(NT) mvnmf_logdet_kernel(const T* W, int V, int
     if (threadIdx.x == 0) *out = log(det);
 }
 
+// W_trial != null: the first line-search candidate (the full step: normalise + clip of W_unconstrained itself, gamma ignored,
+// mvnmf.py:80-88) follows in the same launch -- what mvnmf_trial_kernel(gamma < 0) would do right behind this kernel
 template <typename T>
 __global__ void __launch_bounds__(NT) mvnmf_w_unc_kernel(const T* W, const T* N, const T* hsum, int V, int k,
-                                                        double lam, double delta, int n_given, T* W_unc) {
+                                                        double lam, double delta, int n_given, T* W_unc, T* W_trial, T* h_scale,
+                                                        double* logdet_out) {
     extern __shared__ __align__(16) unsigned char raw[];
     Smem& s = *reinterpret_cast<Smem*>(raw);
     load_w(s, W, V, k);
@@ -167,7 +99,27 @@ __global__ void __launch_bounds__(NT) mvnmf_w_unc_kernel(const T* W, const T* N,
             out = fmax(w * num / (4.0 * lam * wya), (double)SAL_EPS_F32);
         }
         W_unc[i] = (T)out;
+        if (W_trial) s.Wu[j * WP + v] = (double)(T)out;
     }
+    if (!W_trial) return;
+    __syncthreads();
+    for (int j = threadIdx.x; j < k; j += NT) {
+        double t = 0.0;
+        for (int v = 0; v < V; ++v) t += s.Wu[j * WP + v];
+        s.colsum[j] = t;
+        h_scale[j] = (T)t;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < k * V; i += NT) {
+        const int j = i / V, v = i - j * V;
+        const T wt = (T)fmax(s.Wu[j * WP + v] / s.colsum[j], (double)SAL_EPS_F32);
+        W_trial[i] = wt;
+        s.Wd[j * WP + v] = (double)wt;  // logdet of what the objective pass will actually read (W itself is not needed any more)
+    }
+    __syncthreads();
+    gram(s, V, k, delta);
+    const double det = lu_det(s, k);
+    if (threadIdx.x == 0) *logdet_out = log(det);
 }
 
 template <typename T>
@@ -221,16 +173,17 @@ int sal_launch_mvnmf_logdet(sal_ctx* c, const void* W, double delta, double* out
 }
 
 int sal_launch_mvnmf_w_unc(sal_ctx* c, const void* W, const void* N, const void* hsum, double lam,
-                           double delta, int n_given, void* W_unc, cudaStream_t st) {
+                           double delta, int n_given, void* W_unc, void* W_trial, void* h_scale, double* logdet_out, cudaStream_t st) {
     if (c->dtype == SAL_F32) {
         if (int e = set_smem(mvnmf_w_unc_kernel<float>)) return e;
         mvnmf_w_unc_kernel<float><<<1, NT, sizeof(Smem), st>>>((const float*)W, (const float*)N, (const float*)hsum,
-                                                              c->V, c->k, lam, delta, n_given, (float*)W_unc);
+                                                              c->V, c->k, lam, delta, n_given, (float*)W_unc, (float*)W_trial,
+                                                              (float*)h_scale, logdet_out);
     } else {
         if (int e = set_smem(mvnmf_w_unc_kernel<double>)) return e;
         mvnmf_w_unc_kernel<double><<<1, NT, sizeof(Smem), st>>>((const double*)W, (const double*)N,
                                                                (const double*)hsum, c->V, c->k, lam, delta,
-                                                               n_given, (double*)W_unc);
+                                                               n_given, (double*)W_unc, (double*)W_trial, (double*)h_scale, logdet_out);
     }
     SAL_CUDA(cudaGetLastError());
     c->launches++;

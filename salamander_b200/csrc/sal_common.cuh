@@ -128,7 +128,7 @@ int sal_launch_clip_counts(sal_ctx* c, void* X, int64_t n, long long* n_changed,
 int sal_launch_scale_clip_rows(sal_ctx* c, void* H, const void* scale, cudaStream_t st);
 int sal_launch_mvnmf_logdet(sal_ctx* c, const void* W, double delta, double* out, cudaStream_t st);
 int sal_launch_mvnmf_w_unc(sal_ctx* c, const void* W, const void* N, const void* hsum, double lam,
-                           double delta, int n_given, void* W_unc, cudaStream_t st);
+                           double delta, int n_given, void* W_unc, void* W_trial, void* h_scale, double* logdet_out, cudaStream_t st);
 int sal_launch_mvnmf_trial(sal_ctx* c, const void* W, const void* W_unc, double gamma, double delta,
                            void* W_trial, void* h_scale, double* logdet_out, cudaStream_t st);
 

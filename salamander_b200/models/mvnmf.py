@@ -55,6 +55,7 @@ class MvNMF(StandardNMF):
         st.weights["lhalf"] = None
         st.W_unc = torch.empty_like(st.W)
         st.W_unc_spare = torch.empty_like(st.W)  # run-ahead driver: the previous iteration's W_unconstrained stays intact
+        st.W_spare = torch.empty_like(st.W)      # ... and so does its W while the next candidate is already being written
         st.W_trial = torch.empty_like(st.W)
         st.H_trial = torch.empty_like(st.H)
         st.h_scale = torch.empty(st.k, dtype=st.dtype, device=st.device)
@@ -75,7 +76,7 @@ class MvNMF(StandardNMF):
         with self._resident() as st:
             st.ws.klnmf_pass(st.X, st.W, st.H, PASS_UPDATE_H, H_out=st.H)
 
-    def _update_W_unconstrained(self, n_given_signatures: int = 0, logdet_known: bool = False) -> None:
+    def _update_W_unconstrained(self, n_given_signatures: int = 0, logdet_known: bool = False, with_first_trial: bool = False) -> None:
         """Leaves W_unconstrained in ``st.W_unc`` and the previous objective parts in kl2[0], ld2[0].  ``logdet_known``: W is the
         candidate the last line-search trial accepted, whose log-determinant that trial left in ld2[1] (same kernel
         arithmetic on the same numbers): copied instead of recomputed."""
@@ -89,15 +90,20 @@ class MvNMF(StandardNMF):
             st.ld2[0:1].copy_(st.ld2[1:2])
         else:
             st.ws.mvnmf_logdet(st.W, self.delta, st.ld2[0:1])
-        st.ws.mvnmf_w_unconstrained(st.W, st.Wnum, st.hsum, self.lam, self.delta, n_given_signatures, st.W_unc)
+        if with_first_trial:  # ... and the first line-search candidate (the full step) in the same launch
+            st.ws.mvnmf_w_unconstrained_trial(st.W, st.Wnum, st.hsum, self.lam, self.delta, n_given_signatures, st.W_unc,
+                                              st.W_trial, st.h_scale, st.ld2[1:2])
+        else:
+            st.ws.mvnmf_w_unconstrained(st.W, st.Wnum, st.hsum, self.lam, self.delta, n_given_signatures, st.W_unc)
 
-    def _trial(self, gamma_blend: float, fuse_h_step: bool = False) -> float:
+    def _trial(self, gamma_blend: float, fuse_h_step: bool = False, candidate_ready: bool = False) -> float:
         """One line-search candidate: W_trial, the rescaled exposures and the candidate's objective parts (kl2[1], ld2[1]).
         ``fuse_h_step``: the pass also applies the NEXT iteration's H step to the rescaled exposures (it has W_trial, the
         rescaled exposures and the quotient in hand: SAL_PASS_SCALED_UPDATE) -- H_trial then holds update_H's result and the
         next iteration starts at its W step."""
         st = self._dev
-        st.ws.mvnmf_trial(st.W, st.W_unc, gamma_blend, self.delta, st.W_trial, st.h_scale, st.ld2[1:2])
+        if not candidate_ready:
+            st.ws.mvnmf_trial(st.W, st.W_unc, gamma_blend, self.delta, st.W_trial, st.h_scale, st.ld2[1:2])
         st.ws.klnmf_pass(
             st.X,
             st.W_trial,
@@ -155,16 +161,18 @@ class MvNMF(StandardNMF):
     # the four numbers the decision needs travel to a pinned slot behind it, and _confirm checks them later.
     def _first_trial(self, ring, fused: bool) -> dict:
         st = self._dev
-        self._trial(-1.0, fused)
+        self._trial(-1.0, fused, candidate_ready=True)  # (the candidate came out of _update_W_unconstrained's launch)
         st.allreduce(st.kl2)
         slot = ring["next"] % len(ring["events"])
         ring["next"] += 1
         ring["host"][slot].copy_(torch.cat([st.kl2, st.ld2]), non_blocking=True)
         ring["events"][slot].record()
-        rec = {"slot": slot, "W": st.W, "W_trial": st.W_trial, "H": st.H, "H_trial": st.H_trial, "W_unc": st.W_unc,
-               "W_unc_spare": st.W_unc_spare, "gamma": self._gamma, "fused": fused}
-        # adopt the candidate; the next iteration must not overwrite this iteration's W_unconstrained (a back-track needs it)
-        st.W, st.W_trial = st.W_trial, st.W
+        rec = {"slot": slot, "W": st.W, "W_trial": st.W_trial, "W_spare": st.W_spare, "H": st.H, "H_trial": st.H_trial,
+               "W_unc": st.W_unc, "W_unc_spare": st.W_unc_spare, "gamma": self._gamma, "fused": fused}
+        # adopt the candidate.  The next iteration's unconstrained step AND first candidate are launched before this iteration
+        # has been confirmed: they must overwrite neither this iteration's W (a back-track blends with it) nor its
+        # W_unconstrained -- three W buffers rotate (current, next candidate, the one kept), two W_unconstrained buffers
+        st.W, st.W_trial, st.W_spare = st.W_trial, st.W_spare, st.W
         st.H, st.H_trial = st.H_trial, st.H
         st.W_unc, st.W_unc_spare = st.W_unc_spare, st.W_unc
         self._gamma = min(1.0, 1.2 * self._gamma)
@@ -183,7 +191,7 @@ class MvNMF(StandardNMF):
         if not of_value > prev_of_value:
             return True
         torch.cuda.current_stream(st.device).synchronize()
-        st.W, st.W_trial, st.H, st.H_trial = rec["W"], rec["W_trial"], rec["H"], rec["H_trial"]
+        st.W, st.W_trial, st.W_spare, st.H, st.H_trial = rec["W"], rec["W_trial"], rec["W_spare"], rec["H"], rec["H_trial"]
         st.W_unc, st.W_unc_spare = rec["W_unc"], rec["W_unc_spare"]
         gamma = rec["gamma"]
         while of_value > prev_of_value and gamma > 1e-16:
@@ -218,12 +226,12 @@ class MvNMF(StandardNMF):
                 print(f"iteration: {n_iteration}; objective: {of_values[-1]:.2f}")
             if not h_step_done:
                 self._update_H()
-            self._update_W_unconstrained(n_given, logdet_known)
+            self._update_W_unconstrained(n_given, logdet_known, with_first_trial=True)
             if pending is not None and not self._confirm(pending, ring):
                 # iteration n - 1 had to back-track: what was just queued started from the wrong iterate
                 if not pending["fused"]:
                     self._update_H()
-                self._update_W_unconstrained(n_given, True)
+                self._update_W_unconstrained(n_given, True, with_first_trial=True)
             # the H step of iteration n + 1 rides on this iteration's trial pass -- unless the iterate itself is needed next:
             # for the objective of the convergence test or as the final state
             fused = bool(self.fuse_h_step) and n_iteration % freq != 0 and n_iteration < max_it
