@@ -1,7 +1,8 @@
 """
 ``MvNMF``: minimum-volume NMF, KL divergence + lam * ln det(W^T W + delta I), with the
 reference's H step, closed-form unconstrained W step and back-tracking line search
-(reference models/mvnmf.py:95-218).  Per iteration the device does:
+(reference models/mvnmf.py:95-218).  The single-step methods (``_update_H``, ``_update_W``, ``_line_search``; the reference's
+tests call them) do, per iteration:
 
     pass 1  UPDATE_H                          (update_H,               _utils_klnmf.py:220-264)
     pass 2  WNUM | HSUM | OBJECTIVE on new H  (N = (X/WH) H^T, rowsums, previous objective)
@@ -9,7 +10,12 @@ reference's H step, closed-form unconstrained W step and back-tracking line sear
     per line-search trial: 1 CTA blend/normalise/clip/logdet + pass OBJECTIVE|UPDATE_H with
             h_scale, writing the candidate H into a spare buffer that is swapped in on accept.
 
-The reference needs >= 4 passes over X per iteration plus one per back-track; this needs 3 + 1.
+``fit`` runs the same arithmetic through one of three drivers: the persistent single-CTA / thread-block-cluster kernel for
+problems that fit shared memory (whole iterations incl. the line search per launch), or -- larger problems -- the run-ahead
+driver: TWO passes over X per iteration (the next H step rides on the accepted trial's pass, SAL_PASS_SCALED_UPDATE), the
+unconstrained step and the first candidate in one launch, and an optimistic line search whose decision the host reads one
+iteration later (roll-back when the full step was rejected).  The reference needs >= 4 passes over X per iteration plus one
+per back-track.
 """
 
 from __future__ import annotations
