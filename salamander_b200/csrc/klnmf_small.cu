@@ -376,10 +376,18 @@ int launch_cluster_k(sal_ctx* c, int csize, const void* X, const void* W_in, voi
 
 }  // namespace
 
-bool sal_small_supported(const sal_ctx* c) {
-    if (c->D < 1 || c->D > DMAX || c->V > SAL_VMAX) return false;
+static bool single_cta_fits(const sal_ctx* c) {
     const size_t need = c->dtype == SAL_F32 ? small_smem<float>((int)c->D, c->k) : small_smem<double>((int)c->D, c->k);
     return need <= 220 * 1024;
+}
+static bool cluster_fits(const sal_ctx* c) {  // (the cluster kernel's tiles do not grow with D: 32 samples per CTA at most)
+    const size_t need = c->dtype == SAL_F32 ? cluster_smem<float>(c->k) : cluster_smem<double>(c->k);
+    return c->D >= 64 && (c->D + CMAX - 1) / CMAX <= SPC_MAX && need <= 220 * 1024;
+}
+
+bool sal_small_supported(const sal_ctx* c) {
+    if (c->D < 1 || c->D > DMAX || c->V > SAL_VMAX) return false;
+    return single_cta_fits(c) || cluster_fits(c);
 }
 
 template <typename T, int KT>
@@ -415,13 +423,21 @@ int sal_launch_klnmf_small(sal_ctx* c, const void* X, const void* W_in, void* W_
         if (forced <= 1) csize = 1;
         else if (forced == 8 || (forced == 16 && c->D <= 16 * (CNT / 16))) csize = forced;
     }
-    if (csize == 8 && (c->D + 7) / 8 > SPC_MAX) csize = 1;
+    if (csize == 8 && !cluster_fits(c)) csize = 1;
+    if (csize == 1 && !single_cta_fits(c)) {
+        if (cluster_fits(c)) {
+            csize = 8;  // (the only kernel this problem fits)
+        } else {
+            sal_set_error("sal_klnmf_small_updates: problem does not fit the small-problem kernels");
+            return SAL_EUNSUPPORTED;
+        }
+    }
     if (csize == 16) {  // (refused on devices / partitions without room for a 16-CTA cluster: fall back to the portable size)
         const int err = c->dtype == SAL_F32 ? launch_cluster_k<float, 16>(c, 16, X, W_in, W_out, H_in, H_out, n_given, n_iter, objective, st)
                                             : launch_cluster_k<double, 16>(c, 16, X, W_in, W_out, H_in, H_out, n_given, n_iter, objective, st);
         if (err == 0) return 0;
         (void)cudaGetLastError();
-        csize = (c->D + 7) / 8 <= SPC_MAX ? 8 : 1;
+        csize = cluster_fits(c) ? 8 : 1;
     }
     if (csize == 8)
         return c->dtype == SAL_F32 ? launch_cluster_k<float, 8>(c, 8, X, W_in, W_out, H_in, H_out, n_given, n_iter, objective, st)

@@ -693,10 +693,18 @@ int launch_k(sal_ctx* c, const void* X, const void* W_in, void* W_out, const voi
 
 }  // namespace
 
-bool sal_mvnmf_small_ok(const sal_ctx* c) {
-    if (c->D < 1 || c->D > NT / 4) return false;
+static bool single_cta_fits(const sal_ctx* c) {
     const size_t smem = c->dtype == SAL_F32 ? small_smem<float>((int)c->D, c->k) : small_smem<double>((int)c->D, c->k);
     return smem <= 220 * 1024;
+}
+static bool cluster_fits(const sal_ctx* c) {  // (the cluster kernel's tiles do not grow with D: 32 samples per CTA at most)
+    const size_t smem = c->dtype == SAL_F32 ? cluster_smem<float>(c->k) : cluster_smem<double>(c->k);
+    return c->D >= 64 && (c->D + CMAX - 1) / CMAX <= SPC_MAX && smem <= 220 * 1024;
+}
+
+bool sal_mvnmf_small_ok(const sal_ctx* c) {
+    if (c->D < 1 || c->D > NT / 4) return false;
+    return single_cta_fits(c) || cluster_fits(c);
 }
 
 int sal_launch_mvnmf_small(sal_ctx* c, const void* X, const void* W_in, void* W_out, const void* H_in, void* H_out, double lam,
@@ -710,14 +718,22 @@ int sal_launch_mvnmf_small(sal_ctx* c, const void* X, const void* W_in, void* W_
         if (forced <= 1) csize = 1;
         else if (forced == 8 || (forced == 16 && c->D <= 16 * (CNT / 16))) csize = forced;
     }
-    if (csize == 8 && (c->D + 7) / 8 > SPC_MAX) csize = 1;
+    if (csize == 8 && !cluster_fits(c)) csize = 1;
+    if (csize == 1 && !single_cta_fits(c)) {
+        if (cluster_fits(c)) {
+            csize = 8;  // (the only kernel this problem fits)
+        } else {
+            sal_set_error("sal_mvnmf_small_updates: problem does not fit the small-problem kernels");
+            return SAL_EUNSUPPORTED;
+        }
+    }
 #define SAL_MVCL(TT_, TPS_, CS_) \
     launch_cluster_k<TT_, TPS_>(c, CS_, X, W_in, W_out, H_in, H_out, lam, delta, n_given, n_iter, gamma_in, gamma_out, objective, st)
     if (csize == 16) {  // (refused where a 16-CTA cluster has no room: fall back to the portable size)
         const int err = c->dtype == SAL_F32 ? SAL_MVCL(float, 16, 16) : SAL_MVCL(double, 16, 16);
         if (err == 0) return 0;
         (void)cudaGetLastError();
-        csize = (c->D + 7) / 8 <= SPC_MAX ? 8 : 1;
+        csize = cluster_fits(c) ? 8 : 1;
     }
     if (csize == 8) return c->dtype == SAL_F32 ? SAL_MVCL(float, 8, 8) : SAL_MVCL(double, 8, 8);
 #undef SAL_MVCL
