@@ -334,6 +334,7 @@ struct CShared {
     double hsum[SAL_KMAX];
     double bcast[4];
     double xch[2][2 + SAL_KMAX];  // [parity][kl | spare | hsum partials]: this CTA's contribution to a cluster-wide sum
+    int piv;
 };
 
 __device__ double block_sum_c(double v, CShared& sh) {  // fixed order; result on every thread of the CTA
@@ -424,14 +425,7 @@ mvnmf_cluster_kernel(const T* X, const T* W_in, T* W_out, const T* H_in, T* H_ou
     };
     auto logdet = [&](const T* M) {  // CTA-uniform (and, the inputs being replicated, cluster-uniform) result
         gram<T, CNT>(M, G, GP, V, k, delta);
-        if (tid < 32) {
-            const double det = lu_det_warp(G, GP, k);
-            if (tid == 0) sh.bcast[0] = log(det);
-        }
-        __syncthreads();
-        const double r = sh.bcast[0];
-        __syncthreads();
-        return r;
+        return log(lu_det_block<CNT>(G, &sh.piv, GP, k));  // (every thread computes the same determinant; ends with a barrier)
     };
 
     double ld_W = 0.0;
@@ -547,8 +541,7 @@ mvnmf_cluster_kernel(const T* X, const T* W_in, T* W_out, const T* H_in, T* H_ou
         const double prev = kl_prev + lam * ld_W;
         // ---- unconstrained W step (replicated) ----
         gram<T, CNT>(sW, G, GP, V, k, delta);
-        if (tid < 32) invert_warp(G, Y, sh.col, GP, k);
-        __syncthreads();
+        invert_block<CNT>(G, Y, sh.col, &sh.piv, GP, k);
         for (int i = tid; i < k * V; i += CNT) {
             const int j = i / V, v = i - j * V;
             const double w = (double)sW[j * WP + v];
