@@ -37,19 +37,9 @@ __device__ void gram(Smem& s, int V, int k, double delta) {
     __syncthreads();
 }
 
-// LU determinant / Gauss-Jordan inverse of s.G on warp 0 (mvnmf_kk.cuh); result published to the block
-__device__ double lu_det(Smem& s, int k) {
-    if (threadIdx.x < 32) {
-        const double det = lu_det_warp(s.G, GP, k);
-        if (threadIdx.x == 0) s.scal[0] = det;
-    }
-    __syncthreads();
-    return s.scal[0];
-}
-__device__ void invert(Smem& s, int k) {
-    if (threadIdx.x < 32) invert_warp(s.G, s.Y, s.col, GP, k);
-    __syncthreads();
-}
+// LU determinant / Gauss-Jordan inverse of s.G (mvnmf_kk.cuh: pivot search on warp 0, row operations over the whole block)
+__device__ double lu_det(Smem& s, int k) { return lu_det_block<NT>(s.G, &s.piv, GP, k); }
+__device__ void invert(Smem& s, int k) { invert_block<NT>(s.G, s.Y, s.col, &s.piv, GP, k); }
 
 template <typename T>
 __device__ void load_w(Smem& s, const T* W, int V, int k) {
